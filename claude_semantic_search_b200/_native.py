@@ -1,0 +1,336 @@
+"""ctypes binding of libcss_b200.so (the C ABI declared in include/css_b200.h).
+
+There is no CPU fallback: if the library is missing, or no sm_100 device is
+present when a compute entry point is called, a NativeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libcss_b200.so"
+
+CSS_OK = 0
+CSS_ERR_INVALID = -1
+CSS_ERR_NO_DEVICE = -2
+CSS_ERR_CUDA = -3
+CSS_ERR_OOM = -4
+CSS_ERR_IO = -5
+CSS_ERR_UNSUPPORTED = -6
+CSS_ERR_OVERFLOW = -7
+
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+MAX_K = 128
+MAX_COLUMNS = 12
+MAX_CLAUSES = 16
+NULL_VALUE = -(2 ** 31)
+CLAUSE_RANGE = 0
+CLAUSE_SET = 1
+
+
+class NativeError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libcss_b200 error {status}: {message}")
+        self.status = status
+
+
+class NoDeviceError(NativeError):
+    pass
+
+
+class css_clause(ctypes.Structure):
+    _fields_ = [
+        ("column", c_int32),
+        ("kind", c_int32),
+        ("lo", c_int32),
+        ("hi", c_int32),
+        ("set_bits", POINTER(c_uint32)),
+        ("set_nbits", c_int32),
+        ("reserved", c_int32),
+    ]
+
+
+class css_filter(ctypes.Structure):
+    _fields_ = [
+        ("n_clauses", c_int32),
+        ("ignore_alive", c_int32),
+        ("clauses", POINTER(css_clause)),
+        ("row_mask", POINTER(c_uint32)),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/css_b200.h declares
+SIGNATURES = {
+    "css_abi_version": (c_int, []),
+    "css_last_error": (c_char_p, []),
+    "css_device_count": (c_int, [POINTER(c_int)]),
+    "css_device_info": (c_int, [c_int, POINTER(c_int64)]),
+    "css_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "css_index_destroy": (c_int, [c_void_p]),
+    "css_index_dim": (c_int, [c_void_p]),
+    "css_index_metric": (c_int, [c_void_p]),
+    "css_index_ntotal": (c_int64, [c_void_p]),
+    "css_index_capacity": (c_int64, [c_void_p]),
+    "css_index_reserve": (c_int, [c_void_p, c_int64]),
+    "css_index_reset": (c_int, [c_void_p]),
+    "css_index_add": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int64)]),
+    "css_index_add_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int64), c_void_p]),
+    "css_index_get_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
+    "css_index_set_column": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64]),
+    "css_index_set_alive": (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
+    "css_index_filter_mask": (c_int, [c_void_p, POINTER(css_filter), c_void_p, POINTER(c_int64)]),
+    "css_index_filter_mask_device": (c_int, [c_void_p, POINTER(css_filter), POINTER(c_void_p), POINTER(c_int64), c_void_p]),
+    "css_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(css_filter), c_void_p, c_void_p]),
+    "css_index_search_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "css_topk_merge_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "css_index_save": (c_int, [c_void_p, c_char_p]),
+    "css_index_load": (c_int, [c_void_p, c_char_p]),
+    "css_kernel_launch_count": (c_int64, []),
+}
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def register_signatures(extra: dict) -> None:
+    """Other modules (encoder) add their entry points here before load()."""
+    SIGNATURES.update(extra)
+
+
+def load() -> ctypes.CDLL:
+    """Load libcss_b200.so; raises NativeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = Path(os.environ.get("CSS_B200_LIB", LIB_PATH))
+    if not path.exists():
+        raise NativeError(CSS_ERR_UNSUPPORTED,
+                          f"{path} not found: build it with `python -m claude_semantic_search_b200.build` "
+                          "(there is no CPU fallback)")
+    lib = ctypes.CDLL(str(path))
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.css_abi_version() != 1:
+        raise NativeError(CSS_ERR_UNSUPPORTED, f"ABI version {lib.css_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status == CSS_OK:
+        return
+    msg = load().css_last_error().decode("utf-8", "replace")
+    if status == CSS_ERR_NO_DEVICE:
+        raise NoDeviceError(status, msg)
+    raise NativeError(status, msg)
+
+
+def device_count() -> int:
+    n = c_int(0)
+    check(load().css_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def has_device() -> bool:
+    try:
+        return device_count() > 0
+    except NativeError:
+        return False
+
+
+def device_info(device: int = 0) -> dict:
+    info = (c_int64 * 5)()
+    check(load().css_device_info(device, info))
+    return {"sm_count": info[0], "hbm_total": info[1], "hbm_free": info[2], "cc": (info[3], info[4])}
+
+
+def kernel_launch_count() -> int:
+    return int(load().css_kernel_launch_count())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Filter:
+    """Host-side builder of a css_filter; keeps the numpy buffers alive."""
+
+    def __init__(self, ignore_alive: bool = False):
+        self._clauses = []
+        self._keep = []
+        self.ignore_alive = ignore_alive
+        self.row_mask: Optional[np.ndarray] = None
+
+    def add_range(self, column: int, lo: int, hi: int) -> "Filter":
+        self._clauses.append((column, CLAUSE_RANGE, int(lo), int(hi), None, 0))
+        return self
+
+    def add_set(self, column: int, allowed_ids, universe: int) -> "Filter":
+        """Rows whose column value is one of allowed_ids (0 <= id < universe)."""
+        bits = np.zeros((max(universe, 1) + 31) // 32, dtype=np.uint32)
+        for v in allowed_ids:
+            v = int(v)
+            if 0 <= v < universe:
+                bits[v >> 5] |= np.uint32(1 << (v & 31))
+        self._clauses.append((column, CLAUSE_SET, 0, 0, bits, int(universe)))
+        return self
+
+    def set_row_mask(self, mask_words: np.ndarray) -> "Filter":
+        self.row_mask = np.ascontiguousarray(mask_words, dtype=np.uint32)
+        return self
+
+    @property
+    def n_clauses(self) -> int:
+        return len(self._clauses)
+
+    def build(self) -> css_filter:
+        n = len(self._clauses)
+        if n > MAX_CLAUSES:
+            raise NativeError(CSS_ERR_INVALID, f"{n} clauses > {MAX_CLAUSES}")
+        arr = (css_clause * max(n, 1))()
+        for i, (col, kind, lo, hi, bits, nbits) in enumerate(self._clauses):
+            arr[i].column, arr[i].kind, arr[i].lo, arr[i].hi = col, kind, lo, hi
+            arr[i].set_nbits = nbits
+            if bits is not None:
+                arr[i].set_bits = bits.ctypes.data_as(POINTER(c_uint32))
+        f = css_filter()
+        f.n_clauses = n
+        f.ignore_alive = 1 if self.ignore_alive else 0
+        f.clauses = ctypes.cast(arr, POINTER(css_clause))
+        if self.row_mask is not None:
+            f.row_mask = self.row_mask.ctypes.data_as(POINTER(c_uint32))
+        self._keep = [arr]
+        return f
+
+
+class Index:
+    """Thin OO wrapper over the css_index_* entry points."""
+
+    def __init__(self, dim: int, metric: int = METRIC_INNER_PRODUCT, device: int = 0):
+        self._lib = load()
+        self._h = c_void_p()
+        check(self._lib.css_index_create(dim, metric, device, ctypes.byref(self._h)))
+        self.dim = dim
+        self.metric = metric
+        self.device = device
+
+    # -- lifecycle --------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.css_index_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    @property
+    def ntotal(self) -> int:
+        return int(self._lib.css_index_ntotal(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(self._lib.css_index_capacity(self._h))
+
+    def reserve(self, capacity: int) -> None:
+        check(self._lib.css_index_reserve(self._h, capacity))
+
+    def reset(self) -> None:
+        check(self._lib.css_index_reset(self._h))
+
+    # -- data ---------------------------------------------------------------
+    def add(self, x, normalize: bool = False) -> int:
+        x = _f32(x)
+        if x.ndim != 2 or x.shape[1] != self.dim:
+            raise ValueError(f"expected [n, {self.dim}] float32, got {x.shape}")
+        first = c_int64(0)
+        check(self._lib.css_index_add(self._h, x.ctypes.data, x.shape[0], 1 if normalize else 0,
+                                      ctypes.byref(first)))
+        return first.value
+
+    def add_device(self, x_dev_ptr: int, n: int, normalize: bool = False, stream: int = 0) -> int:
+        first = c_int64(0)
+        check(self._lib.css_index_add_device(self._h, c_void_p(x_dev_ptr), n, 1 if normalize else 0,
+                                             ctypes.byref(first), c_void_p(stream)))
+        return first.value
+
+    def get_rows(self, start: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.float32)
+        check(self._lib.css_index_get_rows(self._h, start, n, out.ctypes.data))
+        return out
+
+    def set_column(self, column: int, values, start: int = 0) -> None:
+        v = np.ascontiguousarray(values, dtype=np.int32)
+        check(self._lib.css_index_set_column(self._h, column, v.ctypes.data, start, v.shape[0]))
+
+    def set_alive(self, alive, start: int = 0) -> None:
+        a = np.ascontiguousarray(alive, dtype=np.uint8)
+        check(self._lib.css_index_set_alive(self._h, a.ctypes.data, start, a.shape[0]))
+
+    # -- filter / search ----------------------------------------------------
+    def filter_mask(self, flt: Optional[Filter]) -> tuple:
+        n = self.ntotal
+        words = np.zeros((n + 31) // 32, dtype=np.uint32)
+        n_pass = c_int64(0)
+        cf = flt.build() if flt is not None else None
+        check(self._lib.css_index_filter_mask(self._h, ctypes.byref(cf) if cf is not None else None,
+                                              words.ctypes.data, ctypes.byref(n_pass)))
+        return words, n_pass.value
+
+    def search(self, q, k: int, flt: Optional[Filter] = None) -> tuple:
+        q = _f32(q)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        if q.shape[1] != self.dim:
+            raise ValueError(f"expected [nq, {self.dim}] float32, got {q.shape}")
+        nq = q.shape[0]
+        D = np.empty((nq, k), np.float32)
+        I = np.empty((nq, k), np.int64)
+        cf = flt.build() if flt is not None else None
+        check(self._lib.css_index_search(self._h, q.ctypes.data, nq, k,
+                                         ctypes.byref(cf) if cf is not None else None,
+                                         D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def filter_mask_device(self, flt: Optional[Filter], stream: int = 0, want_count: bool = False):
+        ptr = c_void_p()
+        n_pass = c_int64(0)
+        cf = flt.build() if flt is not None else None
+        check(self._lib.css_index_filter_mask_device(
+            self._h, ctypes.byref(cf) if cf is not None else None, ctypes.byref(ptr),
+            ctypes.byref(n_pass) if want_count else None, c_void_p(stream)))
+        return (ptr.value or 0), (n_pass.value if want_count else None)
+
+    def search_device(self, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int, mask_ptr: int = 0,
+                      id_offset: int = 0, stream: int = 0) -> None:
+        check(self._lib.css_index_search_device(self._h, c_void_p(q_ptr), nq, k,
+                                                c_void_p(mask_ptr) if mask_ptr else None, id_offset,
+                                                c_void_p(D_ptr), c_void_p(I_ptr), c_void_p(stream)))
+
+    # -- persistence --------------------------------------------------------
+    def save(self, path) -> None:
+        check(self._lib.css_index_save(self._h, str(path).encode()))
+
+    def load(self, path) -> None:
+        check(self._lib.css_index_load(self._h, str(path).encode()))
+        self.metric = int(self._lib.css_index_metric(self._h))
+
+
+def topk_merge_device(D_in_ptr: int, I_in_ptr: int, n_lists: int, nq: int, k: int, metric: int,
+                      D_out_ptr: int, I_out_ptr: int, stream: int = 0) -> None:
+    check(load().css_topk_merge_device(c_void_p(D_in_ptr), c_void_p(I_in_ptr), n_lists, nq, k, metric,
+                                       c_void_p(D_out_ptr), c_void_p(I_out_ptr), c_void_p(stream)))

@@ -1,0 +1,492 @@
+// index_kernels.cuh -- device kernels of the flat index:
+//   S1  row normalise on add (+ bf16 shadow copy)        src/storage.py:347-350
+//   S2  streaming fp32 scan with fused warp/block/grid top-k   src/storage.py:436 (faiss IndexFlat.search, small nq)
+//   S4  filter predicate -> row bitmask                  src/storage.py:508-543
+//   S5  merge of per-shard top-k lists
+//
+// Roofline: S2 is HBM-bound.  Algorithmic bytes = ntotal * dim * 4 per query
+// (3072 B per 768-d row); the kernel reads every passing
+// row exactly once with 128-bit streaming loads and keeps the top-k in
+// registers, so nothing but k results per block is ever written.
+#pragma once
+#include "css_common.cuh"
+
+namespace css {
+
+constexpr int kScanThreads = 512;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kRowsPerUnit = 8;      // one mask byte
+constexpr int kRowsPerGroup = 4;     // rows in flight per warp iteration
+constexpr int kMergeCap = 4096;      // entries sorted per round by the last block
+
+struct KeyId {
+  float key;
+  int id;
+};
+
+// ------------------------------------------------------------------------
+// Bitonic sort (descending by `better`) of n = power-of-two entries in smem.
+// ------------------------------------------------------------------------
+struct KeyId64 {
+  float key;
+  int pad;
+  long long id;
+};
+__device__ __forceinline__ bool better(const KeyId& a, const KeyId& b) {
+  return better(a.key, a.id, b.key, b.id);
+}
+__device__ __forceinline__ bool better(const KeyId64& a, const KeyId64& b) {
+  return (a.key > b.key) || (a.key == b.key && a.id < b.id);
+}
+
+template <typename E>
+__device__ __forceinline__ void bitonic_sort_desc(E* s, int n, int tid, int nthreads) {
+  for (int size = 2; size <= n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (n >> 1); t += nthreads) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        E a = s[lo], b = s[hi];
+        bool a_better = better(a, b);
+        if (a_better != desc) {
+          s[lo] = b;
+          s[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------
+// Per-warp top-k held in registers: lane l owns KPL slots.
+// ------------------------------------------------------------------------
+template <int KPL>
+struct WarpTopK {
+  float key[KPL];
+  int id[KPL];
+  float lw_key;  // this lane's worst slot
+  int lw_id;
+  int lw_slot;
+  float thr_key;  // warp-wide worst entry (uniform)
+  int thr_id;
+
+  __device__ __forceinline__ void init(int lane, int k) {
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      // Slots beyond k are permanently "full of +inf" so they are never the worst
+      // and never selected: the list then holds exactly k live entries.
+      bool live = (lane * KPL + s) < k;
+      key[s] = live ? -INFINITY : INFINITY;
+      id[s] = live ? kEmptyId : -1;
+    }
+    recompute();
+  }
+
+  __device__ __forceinline__ void recompute() {
+    lw_key = key[0];
+    lw_id = id[0];
+    lw_slot = 0;
+#pragma unroll
+    for (int s = 1; s < KPL; ++s) {
+      if (better(lw_key, lw_id, key[s], id[s])) {
+        lw_key = key[s];
+        lw_id = id[s];
+        lw_slot = s;
+      }
+    }
+    float wk = lw_key;
+    int wi = lw_id;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ok = __shfl_xor_sync(0xffffffffu, wk, o);
+      int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+      if (better(wk, wi, ok, oi)) {
+        wk = ok;
+        wi = oi;
+      }
+    }
+    thr_key = wk;
+    thr_id = wi;
+  }
+
+  // Warp-uniform call: (k_, i_) identical in all lanes.
+  __device__ __forceinline__ void consider(float k_, int i_, int lane) {
+    if (!better(k_, i_, thr_key, thr_id)) return;
+    unsigned owners = __ballot_sync(0xffffffffu, lw_key == thr_key && lw_id == thr_id);
+    int owner = __ffs(owners) - 1;
+    if (lane == owner) {
+#pragma unroll
+      for (int s = 0; s < KPL; ++s) {
+        if (s == lw_slot) {
+          key[s] = k_;
+          id[s] = i_;
+        }
+      }
+    }
+    recompute();
+  }
+};
+
+struct ScanParams {
+  const float* x;        // [n, d]
+  int64_t n;
+  int d;
+  const float* q;        // [nq, d]
+  const uint32_t* mask;  // nullable bitmask over rows
+  int k;
+  KeyId* part;           // [nq][gridDim.x][k]
+  unsigned int* ticket;  // [nq], zero on entry, zero on exit
+  int64_t id_offset;
+  float* D;              // [nq, k]
+  int64_t* I;            // [nq, k]
+};
+
+// Dot products (or negated squared distances) of up to 4 rows against the query.
+template <int METRIC, bool D768>
+__device__ __forceinline__ void score_rows(const ScanParams& p, const float4* qreg,
+                                           const float* q_s, const int64_t (&r)[kRowsPerGroup],
+                                           int lane, float (&acc)[kRowsPerGroup]) {
+  if constexpr (D768) {
+    float4 v[kRowsPerGroup][6];
+#pragma unroll
+    for (int i = 0; i < kRowsPerGroup; ++i) {
+      const float4* row = reinterpret_cast<const float4*>(p.x + r[i] * 768);
+#pragma unroll
+      for (int j = 0; j < 6; ++j) v[i][j] = ld_stream_f4(row + j * 32 + lane);
+    }
+#pragma unroll
+    for (int i = 0; i < kRowsPerGroup; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) {
+          a = fmaf(v[i][j].x, qreg[j].x, a);
+          a = fmaf(v[i][j].y, qreg[j].y, a);
+          a = fmaf(v[i][j].z, qreg[j].z, a);
+          a = fmaf(v[i][j].w, qreg[j].w, a);
+        } else {
+          float t;
+          t = v[i][j].x - qreg[j].x; a = fmaf(t, t, a);
+          t = v[i][j].y - qreg[j].y; a = fmaf(t, t, a);
+          t = v[i][j].z - qreg[j].z; a = fmaf(t, t, a);
+          t = v[i][j].w - qreg[j].w; a = fmaf(t, t, a);
+        }
+      }
+      acc[i] = a;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kRowsPerGroup; ++i) acc[i] = 0.f;
+    for (int j = lane; j < p.d; j += 32) {
+      float qj = q_s[j];
+#pragma unroll
+      for (int i = 0; i < kRowsPerGroup; ++i) {
+        float xv = __ldg(p.x + r[i] * (int64_t)p.d + j);
+        if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) {
+          acc[i] = fmaf(xv, qj, acc[i]);
+        } else {
+          float t = xv - qj;
+          acc[i] = fmaf(t, t, acc[i]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRowsPerGroup; ++i) {
+    acc[i] = warp_sum(acc[i]);
+    if constexpr (METRIC == CSS_METRIC_L2) acc[i] = -acc[i];
+  }
+}
+
+// grid = (blocks, nq).  Each warp owns a contiguous range of 8-row units, keeps
+// a register top-k, the block merges its 16 warps in shared memory, and the last
+// block to finish (atomic ticket) merges the per-block lists into D/I.
+template <int KPL, int METRIC, bool D768>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
+  float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int qi = blockIdx.y;
+  const float* q = p.q + (int64_t)qi * p.d;
+
+  float4 qreg[6];
+  if constexpr (D768) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) qreg[j] = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
+  } else {
+    for (int j = tid; j < p.d; j += kScanThreads) q_s[j] = q[j];
+    __syncthreads();
+  }
+
+  WarpTopK<KPL> top;
+  top.init(lane, p.k);
+
+  const int64_t units = (p.n + kRowsPerUnit - 1) / kRowsPerUnit;
+  const int64_t nwarps = (int64_t)gridDim.x * kScanWarps;
+  const int64_t gw = (int64_t)blockIdx.x * kScanWarps + warp;
+  const int64_t u_begin = (units * gw) / nwarps;
+  const int64_t u_end = (units * (gw + 1)) / nwarps;
+  const unsigned char* mask8 = reinterpret_cast<const unsigned char*>(p.mask);
+
+  for (int64_t ub = u_begin; ub < u_end; ub += 32) {
+    // one coalesced mask fetch for the next 32 units (256 rows)
+    unsigned mb = 0;
+    {
+      int64_t u = ub + lane;
+      if (u < u_end) {
+        mb = mask8 ? (unsigned)mask8[u] : 0xFFu;
+        int64_t rows_left = p.n - u * kRowsPerUnit;
+        if (rows_left < kRowsPerUnit) mb &= (1u << rows_left) - 1u;
+      }
+    }
+    const int nu = (int)min((int64_t)32, u_end - ub);
+    for (int j = 0; j < nu; ++j) {
+      unsigned m = __shfl_sync(0xffffffffu, mb, j);
+      const int64_t row0 = (ub + j) * kRowsPerUnit;
+      while (m) {
+        int64_t r[kRowsPerGroup];
+        int cnt = 0;
+#pragma unroll
+        for (int i = 0; i < kRowsPerGroup; ++i) {
+          if (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            r[i] = row0 + b;
+            cnt = i + 1;
+          } else {
+            r[i] = r[0];
+          }
+        }
+        float acc[kRowsPerGroup];
+        score_rows<METRIC, D768>(p, qreg, q_s, r, lane, acc);
+#pragma unroll
+        for (int i = 0; i < kRowsPerGroup; ++i)
+          if (i < cnt) top.consider(acc[i], (int)r[i], lane);
+      }
+    }
+  }
+
+  // ---- block merge: 16 warps x 32 lanes x KPL slots -> sorted smem list ----
+  constexpr int kBlockEntries = kScanThreads * KPL;  // power of two
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < KPL; ++s) {
+    KeyId e;
+    bool live = (lane * KPL + s) < p.k;
+    e.key = live ? top.key[s] : -INFINITY;
+    e.id = live ? top.id[s] : kEmptyId;
+    s_list[tid * KPL + s] = e;
+  }
+  bitonic_sort_desc(s_list, kBlockEntries, tid, kScanThreads);
+  KeyId* my_part = p.part + ((int64_t)qi * gridDim.x + blockIdx.x) * p.k;
+  for (int i = tid; i < p.k; i += kScanThreads) my_part[i] = s_list[i];
+
+  // ---- grid merge by the last block -----------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned t = atomicAdd(p.ticket + qi, 1u);
+    s_is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+
+  const KeyId* all = p.part + (int64_t)qi * gridDim.x * p.k;
+  const int total = gridDim.x * p.k;
+  // s_list[0..k) always holds the best-so-far; each round appends up to
+  // kMergeCap - k new entries, pads with sentinels and sorts.
+  int consumed = 0;
+  bool first = true;
+  while (consumed < total) {
+    int keep = first ? 0 : p.k;
+    int take = min(kMergeCap - keep, total - consumed);
+    __syncthreads();
+    for (int i = tid; i < kMergeCap - keep; i += kScanThreads) {
+      KeyId e;
+      if (i < take) {
+        unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(all + consumed + i));
+        e.key = __uint_as_float((unsigned)(raw & 0xffffffffull));
+        e.id = (int)(raw >> 32);
+      } else {
+        e.key = -INFINITY;
+        e.id = kEmptyId;
+      }
+      s_list[keep + i] = e;
+    }
+    // sort only as many entries as needed (next power of two >= keep + take)
+    int n_sort = 32;
+    while (n_sort < keep + take) n_sort <<= 1;
+    bitonic_sort_desc(s_list, n_sort, tid, kScanThreads);
+    consumed += take;
+    first = false;
+  }
+  for (int i = tid; i < p.k; i += kScanThreads) {
+    KeyId e = s_list[i];
+    bool empty = (e.id == kEmptyId);
+    float dval;
+    if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
+    else dval = empty ? FLT_MAX : -e.key;
+    p.D[(int64_t)qi * p.k + i] = dval;
+    p.I[(int64_t)qi * p.k + i] = empty ? (int64_t)-1 : (int64_t)e.id + p.id_offset;
+  }
+  if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
+}
+
+// ------------------------------------------------------------------------
+// S1: append rows.  One warp per row: optional L2 normalisation with the
+// reference's epsilon (x / (||x|| + 1e-8)), fp32 store + bf16 shadow store.
+// ------------------------------------------------------------------------
+static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t n, int d, int normalize,
+                                   float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* s = src + row * d;
+  float denom = 1.f;
+  if (normalize) {
+    float ss = 0.f;
+    for (int j = lane; j < d; j += 32) {
+      float v = s[j];
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    denom = sqrtf(ss) + 1e-8f;
+  }
+  for (int j = lane; j < d; j += 32) {
+    // numpy computes x / (norm + 1e-8); a true division keeps the last bit identical
+    float v = normalize ? s[j] / denom : s[j];
+    dst[row * d + j] = v;
+    if (dst_bf16) dst_bf16[row * d + j] = __float2bfloat16_rn(v);
+  }
+}
+
+static __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// Set bits [start, start+n) of a row bitmask to `value`.
+static __global__ void set_bits_kernel(uint32_t* bits, int64_t start, int64_t n, int value) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // word index relative to start/32
+  int64_t w0 = start >> 5;
+  int64_t w1 = (start + n - 1) >> 5;
+  int64_t word = w0 + w;
+  if (word > w1) return;
+  int64_t lo = max(start, word << 5) - (word << 5);
+  int64_t hi = min(start + n, (word + 1) << 5) - (word << 5);  // exclusive
+  uint32_t m = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((lo == 0) ? 0u : ((1u << lo) - 1u));
+  if (value) atomicOr(bits + word, m);
+  else atomicAnd(bits + word, ~m);
+}
+
+// alive bytes (0/1 per row) -> bits
+static __global__ void alive_bytes_to_bits_kernel(const uint8_t* alive, int64_t start, int64_t n,
+                                           uint32_t* bits) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int64_t row = start + i;
+  uint32_t bit = 1u << (row & 31);
+  if (alive[i]) atomicOr(bits + (row >> 5), bit);
+  else atomicAnd(bits + (row >> 5), ~bit);
+}
+
+// ------------------------------------------------------------------------
+// S4: filter predicate -> bitmask.  One thread per row, one ballot per warp.
+// ------------------------------------------------------------------------
+struct DevClause {
+  const int32_t* col;     // nullptr: column never set -> all NULL -> nothing matches
+  int32_t kind;
+  int32_t lo, hi;
+  const uint32_t* bits;   // device bitset
+  int32_t nbits;
+};
+struct FilterParams {
+  DevClause c[CSS_MAX_CLAUSES];
+  int n_clauses;
+  const uint32_t* alive;     // nullable
+  const uint32_t* row_mask;  // nullable (device)
+  int64_t n;
+  uint32_t* out;             // ceil(n/32) words
+  unsigned long long* n_pass;
+};
+
+static __global__ void filter_mask_kernel(FilterParams p) {
+  const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool pass = row < p.n;
+  if (pass && p.alive) pass = (p.alive[row >> 5] >> (row & 31)) & 1u;
+  if (pass && p.row_mask) pass = (p.row_mask[row >> 5] >> (row & 31)) & 1u;
+  for (int i = 0; i < p.n_clauses && pass; ++i) {
+    const DevClause& c = p.c[i];
+    if (!c.col) {
+      pass = false;
+      break;
+    }
+    int32_t v = c.col[row];
+    if (v == CSS_NULL_VALUE) {
+      pass = false;
+    } else if (c.kind == CSS_CLAUSE_RANGE) {
+      pass = (v >= c.lo) && (v <= c.hi);
+    } else {
+      pass = (v >= 0) && (v < c.nbits) && ((c.bits[v >> 5] >> (v & 31)) & 1u);
+    }
+  }
+  unsigned w = __ballot_sync(0xffffffffu, pass);
+  if ((threadIdx.x & 31) == 0 && row < p.n) {
+    p.out[row >> 5] = w;
+    if (w) atomicAdd(p.n_pass, (unsigned long long)__popc(w));
+  }
+}
+
+// ------------------------------------------------------------------------
+// S5: merge n_lists top-k lists per query (one block per query).
+// ------------------------------------------------------------------------
+template <int METRIC>
+__global__ void merge_lists_kernel(const float* __restrict__ D_in, const int64_t* __restrict__ I_in,
+                                   int n_lists, int nq, int k, float* __restrict__ D_out,
+                                   int64_t* __restrict__ I_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyId64* s = reinterpret_cast<KeyId64*>(smem_raw);
+  const int qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int total = n_lists * k;
+  int n_sort = 32;
+  while (n_sort < total) n_sort <<= 1;
+  for (int i = tid; i < n_sort; i += blockDim.x) {
+    KeyId64 e;
+    e.pad = 0;
+    e.key = -INFINITY;
+    e.id = LLONG_MAX;
+    if (i < total) {
+      int l = i / k, j = i % k;
+      int64_t src = ((int64_t)l * nq + qi) * k + j;
+      int64_t id = I_in[src];
+      if (id >= 0) {
+        float dv = D_in[src];
+        e.key = (METRIC == CSS_METRIC_INNER_PRODUCT) ? dv : -dv;
+        e.id = id;
+      }
+    }
+    s[i] = e;
+  }
+  bitonic_sort_desc(s, n_sort, tid, blockDim.x);
+  for (int i = tid; i < k; i += blockDim.x) {
+    KeyId64 e = s[i];  // n_sort >= 32 >= ... k <= total <= n_sort
+    bool empty = (e.id == LLONG_MAX);
+    float dv;
+    if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dv = empty ? -FLT_MAX : e.key;
+    else dv = empty ? FLT_MAX : -e.key;
+    D_out[(int64_t)qi * k + i] = dv;
+    I_out[(int64_t)qi * k + i] = empty ? (int64_t)-1 : (int64_t)e.id;
+  }
+}
+
+}  // namespace css

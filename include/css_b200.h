@@ -1,0 +1,181 @@
+/*
+ * css_b200.h -- C ABI of the B200-native hot path for claude-semantic-search.
+ *
+ * This is the drop-in boundary: everything the reference computes through
+ * `faiss` (src/storage.py) and `sentence_transformers` (src/embeddings.py) is
+ * reached through the entry points below.  Plain pointers and sizes only; no
+ * torch / C++ types.  The shared library is libcss_b200.so (built by
+ * claude_semantic_search_b200/build.py with nvcc for sm_100a).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative css_status otherwise;
+ *     css_last_error() returns a thread-local message for the last failure.
+ *   - the caller owns every host buffer; the library owns all device memory.
+ *   - "_device" variants take device pointers + a CUDA stream (as void*) and do
+ *     not synchronise; the plain variants take HOST buffers, copy in/out and
+ *     return when the result is in the host buffer.
+ *   - handles are internally locked: add/save/reset exclude search.
+ *   - there is no CPU fallback: without an sm_100 device every compute entry
+ *     point fails with CSS_ERR_NO_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   faiss.IndexFlatIP(d) / IndexFlatL2(d)      src/storage.py:252-258  -> css_index_create
+ *   faiss_index.add(x)                         src/storage.py:358-359  -> css_index_add
+ *   faiss_index.ntotal                         src/storage.py:308,421  -> css_index_ntotal
+ *   faiss_index.search(q, k)                   src/storage.py:436      -> css_index_search
+ *   _matches_filters per candidate row         src/storage.py:508-543  -> css_index_filter_mask (+ filter arg of search)
+ *   faiss.write_index / read_index             src/storage.py:306,879-884 -> css_index_save / css_index_load
+ *   SentenceTransformer(...).encode(...)       src/embeddings.py:184-188,216-222 -> css_encoder_encode
+ *   SentenceTransformer(name).to(device)       src/embeddings.py:86-97 -> css_encoder_create
+ */
+#ifndef CSS_B200_H
+#define CSS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSS_ABI_VERSION 1
+
+typedef enum css_status {
+  CSS_OK = 0,
+  CSS_ERR_INVALID = -1,      /* bad argument */
+  CSS_ERR_NO_DEVICE = -2,    /* no sm_100 CUDA device / driver */
+  CSS_ERR_CUDA = -3,         /* a CUDA call failed; see css_last_error() */
+  CSS_ERR_OOM = -4,          /* device or host allocation failed */
+  CSS_ERR_IO = -5,           /* file I/O or file format */
+  CSS_ERR_UNSUPPORTED = -6,  /* valid request this build cannot serve (e.g. k too large) */
+  CSS_ERR_OVERFLOW = -7      /* internal candidate buffer overflow (never silently truncated) */
+} css_status;
+
+typedef enum css_metric {
+  CSS_METRIC_INNER_PRODUCT = 0, /* faiss.METRIC_INNER_PRODUCT, IndexFlatIP */
+  CSS_METRIC_L2 = 1             /* faiss.METRIC_L2, IndexFlatL2 (squared distances) */
+} css_metric;
+
+int css_abi_version(void);
+const char* css_last_error(void);
+/* Number of usable sm_100 devices (CSS_ERR_NO_DEVICE if none). */
+int css_device_count(int* n_out);
+/* {SM count, HBM bytes total, HBM bytes free, cc major, cc minor} of `device`. */
+int css_device_info(int device, int64_t info_out[5]);
+
+/* ------------------------------------------------------------------ */
+/* Flat index (half B of the hot path)                                 */
+/* ------------------------------------------------------------------ */
+typedef struct css_index css_index;
+
+/* Maximum k served by the fused scan (reference uses k' = min(100, ntotal),
+ * src/storage.py:432). */
+#define CSS_MAX_K 128
+/* Number of int32 metadata columns an index can carry for filtering. */
+#define CSS_MAX_COLUMNS 12
+#define CSS_MAX_CLAUSES 16
+
+int css_index_create(int dim, int metric, int device, css_index** out);
+int css_index_destroy(css_index* h);
+int css_index_dim(const css_index* h);
+int css_index_metric(const css_index* h);
+int64_t css_index_ntotal(const css_index* h);
+int64_t css_index_capacity(const css_index* h);
+/* Pre-size device storage (rows).  Growth is otherwise geometric. */
+int css_index_reserve(css_index* h, int64_t capacity);
+/* Drop all rows (faiss Index.reset()). */
+int css_index_reset(css_index* h);
+
+/* Append n rows (row-major float32 [n, dim], HOST memory).  If normalize != 0
+ * each row is scaled by 1 / (||x||_2 + 1e-8) on the device, the arithmetic of
+ * src/storage.py:347-350.  Row i receives id first_id + i; ids are dense,
+ * append-only and never reused (faiss IndexFlat semantics). */
+int css_index_add(css_index* h, const float* x_host, int64_t n, int normalize,
+                  int64_t* first_id_out);
+/* Same with x in DEVICE memory of the index's device (e.g. encoder output). */
+int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normalize,
+                         int64_t* first_id_out, void* stream);
+/* faiss reconstruct_n: copy rows [start, start+n) back to host. */
+int css_index_get_rows(css_index* h, int64_t start, int64_t n, float* out_host);
+
+/* Metadata columns (int32, one value per row; dictionary ids / ranks / raw
+ * integers chosen by the host, CSS_NULL_VALUE for SQL NULL). */
+#define CSS_NULL_VALUE INT32_MIN
+int css_index_set_column(css_index* h, int column, const int32_t* values_host,
+                         int64_t start, int64_t n);
+/* alive[i] != 0 -> row start+i may be returned.  New rows are alive.  Rows
+ * whose chunk was deleted/re-indexed are orphans in the reference
+ * (src/storage.py:449-451,836-846) and are cleared here. */
+int css_index_set_alive(css_index* h, const uint8_t* alive_host, int64_t start, int64_t n);
+
+typedef enum css_clause_kind {
+  CSS_CLAUSE_RANGE = 0, /* lo <= v <= hi (inclusive, on the int32 column value) */
+  CSS_CLAUSE_SET = 1    /* 0 <= v < set_nbits and bit v of set_bits is 1 */
+} css_clause_kind;
+
+typedef struct css_clause {
+  int32_t column;
+  int32_t kind;             /* css_clause_kind */
+  int32_t lo, hi;           /* RANGE */
+  const uint32_t* set_bits; /* SET: HOST bitset, ceil(set_nbits/32) words */
+  int32_t set_nbits;
+  int32_t reserved;
+} css_clause;
+
+/* Conjunction of clauses AND alive AND (optional) explicit row bitmask. */
+typedef struct css_filter {
+  int32_t n_clauses;
+  int32_t ignore_alive;       /* 0: dead rows never match (default) */
+  const css_clause* clauses;  /* n_clauses entries */
+  const uint32_t* row_mask;   /* optional HOST bitmask, ceil(ntotal/32) words, bit i = row i */
+} css_filter;
+
+/* Evaluate the filter over all rows on the device and copy the bitmask
+ * (ceil(ntotal/32) words; bit i%32 of word i/32 = row i) to host.  This is the
+ * bit-exact counterpart of evaluating src/storage.py:508-543 row by row. */
+int css_index_filter_mask(css_index* h, const css_filter* f, uint32_t* mask_out_host,
+                          int64_t* n_pass_out);
+
+/* Exact top-k of nq queries (HOST float32 [nq, dim]) over the rows passing
+ * `filter` (NULL = every alive row).  D: float32 [nq, k], I: int64 [nq, k],
+ * both HOST.  Rows are ordered best first (IP: score descending; L2: squared
+ * distance ascending), ties broken by ascending id; unfilled slots carry
+ * id -1 and score -FLT_MAX (IP) / FLT_MAX (L2) like faiss.
+ * nq < CSS_BATCH_MIN_NQ runs the HBM-bound fp32 streaming scan; larger batches
+ * run the tcgen05 score GEMM with in-epilogue candidate selection followed by
+ * an exact fp32 re-score of the candidates. */
+int css_index_search(css_index* h, const float* q_host, int nq, int k,
+                     const css_filter* filter, float* D_host, int64_t* I_host);
+
+/* Device-pointer variant: q_dev float32 [nq, dim], D_dev float32 [nq,k], I_dev
+ * int64 [nq,k]; mask_dev is an optional DEVICE bitmask as produced by
+ * css_index_filter_mask_device (NULL = all alive rows).  id_offset is added
+ * to every returned id (global id of a row shard).  Asynchronous on `stream`. */
+int css_index_search_device(css_index* h, const float* q_dev, int nq, int k,
+                            const uint32_t* mask_dev, int64_t id_offset,
+                            float* D_dev, int64_t* I_dev, void* stream);
+/* Evaluate a filter into the index's internal device mask and return its
+ * device address (valid until the next call that changes the index/mask). */
+int css_index_filter_mask_device(css_index* h, const css_filter* f,
+                                 const uint32_t** mask_dev_out, int64_t* n_pass_out,
+                                 void* stream);
+
+/* Merge `n_lists` sorted top-k lists per query (e.g. one per GPU after the
+ * NCCL all-gather): D_in float32 [n_lists, nq, k], I_in int64 [n_lists, nq, k],
+ * all DEVICE; writes the merged best-k per query.  metric as in css_metric. */
+int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, int nq,
+                          int k, int metric, float* D_out, int64_t* I_out, void* stream);
+
+/* faiss-compatible persistence: IndexFlatIP ("IxFI") / IndexFlatL2 ("IxF2")
+ * files as written by faiss.write_index (src/storage.py:879-884). */
+int css_index_save(css_index* h, const char* path);
+int css_index_load(css_index* h, const char* path);
+
+/* Timing hook for benchmarks: number of kernels this library has launched in
+ * this process (all handles). */
+int64_t css_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSS_B200_H */
