@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- hot-path benchmark of claude_semantic_search_b200 (contract in the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Headline workload (BASELINE.json configs[1]): exact top-10 over a 1M x 768 fp32
+corpus, batch-1 queries, one B200.  A "step" is one query call.  With N > 1 ranks
+(torchrun) every rank holds its own 1M-row shard (weak scaling: the corpus grows
+with N), queries are replicated, each rank scans its shard, the local top-k are
+all-gathered over NCCL and merged on every rank; `value` counts 1M-row shard scans
+per second over all ranks (= QPS x N), `config.qps` is the plain query rate.
+
+Extra legs (own timers, reported under "extra"): batch-1024 search on the same
+corpus, the MPNet encoder at seq len 384 (BASELINE configs[2]) and the 10M-row
+filtered search (configs[4], N=1 only, opt-in with --full).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D = 768
+K = 10
+ROWS = 1_000_000
+BYTES_PER_ROW = D * 4  # 3072 B per corpus row per batch-1 query
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"],
+                "bf16_tflops_sustained": j.get("bf16_tflops_sustained", j["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+def cpu_search_baseline(sample_rows: int = 250_000, n_queries: int = 16):
+    """The oracle's C restatement of faiss IndexFlatIP.search (oracle/flat_ip.c,
+    OpenMP over rows) on a bounded sample of the workload, scaled linearly in N."""
+    from oracle import search_oracle as so
+    rng = np.random.default_rng(42)
+    x = so.normalize_rows(rng.standard_normal((sample_rows, D), dtype=np.float32))
+    q = so.normalize_rows(np.random.default_rng(43).standard_normal((n_queries, D), dtype=np.float32))
+    cores = so.c_lib().oracle_num_threads()
+    so.flat_search_c(x, q[:2], K)  # warm-up
+    t0 = time.perf_counter()
+    so.flat_search_c(x, q, K)
+    dt = time.perf_counter() - t0
+    qps_sample = n_queries / dt
+    qps_1m = qps_sample * sample_rows / ROWS
+    return {"value": qps_1m, "unit": "queries/s", "cores": int(cores), "kind": "port",
+            "sample": f"{n_queries} batch-1 queries over the first {sample_rows} rows x {D} fp32 "
+                      f"(oracle/flat_ip.c, OpenMP), scaled linearly to {ROWS} rows"}, dt / n_queries
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = args.steps, args.warmup
+    from oracle import search_oracle as so
+    sample_rows = 250_000
+    rng = np.random.default_rng(42)
+    x = so.normalize_rows(rng.standard_normal((sample_rows, D), dtype=np.float32))
+    q = so.normalize_rows(np.random.default_rng(43).standard_normal((max(steps + warm, 1), D), dtype=np.float32))
+    cores = so.c_lib().oracle_num_threads()
+    steps = min(steps, 200)
+    for i in range(min(warm, 5)):
+        so.flat_search_c(x, q[i:i + 1], K)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        so.flat_search_c(x, q[warm + i:warm + i + 1], K)
+    dt = time.perf_counter() - t0
+    ms = dt / steps * 1e3 * (ROWS / sample_rows)
+    qps = 1e3 / ms
+    sample = (f"each step = 1 batch-1 query over {sample_rows} rows x {D} fp32 on the host "
+              f"(oracle/flat_ip.c, the port of faiss IndexFlatIP.search), time scaled x{ROWS // sample_rows} to {ROWS} rows")
+    line = {"impl": "reference", "metric": "exact top-10 QPS @ 1Mx768 fp32, batch-1", "value": qps,
+            "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": "exact top-10, 1M x 768 fp32 corpus, batch-1 queries (BASELINE configs[1])"},
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": int(cores), "kind": "port", "sample": sample},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+def build_shard(torch, native, dev, rows: int, seed: int):
+    """Corpus shard generated on the device in 1M-row tiles (N(0,1), row-normalised by
+    the add kernel with the reference's x/(||x||+1e-8))."""
+    idx = native.Index(D, native.METRIC_INNER_PRODUCT, dev.index)
+    idx.reserve(rows)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    tile = 250_000
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for r0 in range(0, rows, tile):
+        nr = min(tile, rows - r0)
+        blk = torch.randn((nr, D), generator=g, device=dev, dtype=torch.float32)
+        idx.add_device(blk.data_ptr(), nr, normalize=True, stream=stream)
+        torch.cuda.current_stream(dev).synchronize()
+        del blk
+    return idx
+
+
+def time_region(torch, dev, fn, steps: int, dist=None):
+    """Barrier + sync, K steps bracketed by CUDA events on the launching stream, sync + barrier."""
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1), wall * 1e3
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS, help="corpus rows per GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the batch-1024 / encoder legs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--full", action="store_true", help="also run the 10M-row filtered leg")
+    ap.add_argument("--encode-seqs", type=int, default=4096)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    from claude_semantic_search_b200 import _native as native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    # a non-default stream: libcss_b200 treats stream 0 as "use the handle's own stream",
+    # and the CUDA events below must sit on the stream the kernels are launched on
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist_mod.init_process_group("nccl", device_id=dev)
+        dist = dist_mod
+    pk = peaks()
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu:
+        cpu_base, _ = cpu_search_baseline()
+
+    rows = args.rows
+    idx = build_shard(torch, native, dev, rows, seed=42 + rank)
+    gq = torch.Generator(device=dev)
+    gq.manual_seed(43)
+    nq_pool = 1024
+    qs = torch.randn((nq_pool, D), generator=gq, device=dev, dtype=torch.float32)
+    qs = qs / (qs.norm(dim=1, keepdim=True) + 1e-8)
+    qs_host = qs.cpu().pin_memory()
+    stream = torch.cuda.current_stream(dev)
+    sp = stream.cuda_stream
+
+    D_loc = torch.empty((1, K), device=dev, dtype=torch.float32)
+    I_loc = torch.empty((1, K), device=dev, dtype=torch.int64)
+    if world > 1:
+        D_all = torch.empty((world, 1, K), device=dev, dtype=torch.float32)
+        I_all = torch.empty((world, 1, K), device=dev, dtype=torch.int64)
+        D_out = torch.empty((1, K), device=dev, dtype=torch.float32)
+        I_out = torch.empty((1, K), device=dev, dtype=torch.int64)
+    id_offset = rank * rows
+    launches_per_step = 1 if world == 1 else 2
+
+    def step(i):
+        q = qs[i % nq_pool]
+        idx.search_device(q.data_ptr(), 1, K, D_loc.data_ptr(), I_loc.data_ptr(), 0, id_offset, sp)
+        if world > 1:
+            dist.all_gather_into_tensor(D_all, D_loc)
+            dist.all_gather_into_tensor(I_all, I_loc)
+            native.topk_merge_device(D_all.data_ptr(), I_all.data_ptr(), world, 1, K, native.METRIC_INNER_PRODUCT,
+                                     D_out.data_ptr(), I_out.data_ptr(), sp)
+
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = native.kernel_launch_count()
+    ms_total, _ = time_region(torch, dev, step, args.steps, dist)
+    n_launch = native.kernel_launch_count() - l0
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    qps = 1e3 / ms_step
+
+    # kernel-only duration of the scan (events around the launch alone), for the roofline
+    def scan_only(i):
+        idx.search_device(qs[i % nq_pool].data_ptr(), 1, K, D_loc.data_ptr(), I_loc.data_ptr(), 0, id_offset, sp)
+    ms_scan, _ = time_region(torch, dev, scan_only, args.steps, dist)
+    ms_scan /= args.steps
+    achieved = rows * BYTES_PER_ROW / (ms_scan * 1e-3) / 1e9
+
+    # ---- e2e: the C-ABI call with HOST buffers (H2D of the query + D2H of D/I inside) ----
+    qh = qs_host.numpy()
+
+    def e2e_step(i):
+        Dh, Ih = idx.search(qh[i % nq_pool:i % nq_pool + 1], K)
+        if world > 1:
+            # host-side exchange of the local lists: tiny (k x 12 B per rank) all_gather + merge
+            Dl = torch.from_numpy(Dh).to(dev, non_blocking=True)
+            Il = torch.from_numpy(Ih + id_offset).to(dev, non_blocking=True)
+            dist.all_gather_into_tensor(D_all, Dl)
+            dist.all_gather_into_tensor(I_all, Il)
+            native.topk_merge_device(D_all.data_ptr(), I_all.data_ptr(), world, 1, K, native.METRIC_INNER_PRODUCT,
+                                     D_out.data_ptr(), I_out.data_ptr(), sp)
+            D_out.cpu()
+    for i in range(args.warmup):
+        e2e_step(i)
+    e2e_steps = args.steps
+    _, wall_ms = time_region(torch, dev, e2e_step, e2e_steps, dist)
+    if world > 1:
+        t = torch.tensor([wall_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall_ms = float(t.item())
+    e2e_qps = e2e_steps / (wall_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    extra = {}
+    if not args.no_extra:
+        try:
+            extra.update(bench_batched(torch, native, dev, idx, qs, pk, world, rank, rows, dist))
+        except Exception as e:  # report, never hide
+            extra["batch1024_error"] = repr(e)
+        try:
+            from bench_encoder import bench_encoder
+            extra.update(bench_encoder(torch, dev, pk, world, rank, dist, args))
+        except ImportError:
+            pass
+        except Exception as e:
+            extra["encode_error"] = repr(e)
+    idx.close()
+
+    if rank == 0:
+        line = {
+            "metric": "exact top-10 QPS @ 1Mx768 fp32, batch-1",
+            "value": qps * world, "unit": "queries/s" if world == 1 else "1M-row shard scans/s (= QPS x n_gpus)",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "exact top-10, 1M x 768 fp32 corpus per GPU, batch-1 queries (BASELINE configs[1])",
+                       "rows_per_gpu": rows, "corpus_rows": rows * world, "dim": D, "k": K, "qps": qps,
+                       "l2": "corpus (3.07 GB) >> 126 MB L2, no flush needed",
+                       "exchange": "none" if world == 1 else "2 x ncclAllGather (k x 4 B + k x 8 B per rank) + merge kernel"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "kernel": "scan_topk_kernel", "kernel_ms": ms_scan,
+                         "algorithmic_bytes_per_launch": rows * BYTES_PER_ROW},
+            "cpu_baseline": cpu_base,
+            "e2e": {"value": e2e_qps * world, "unit": "queries/s" if world == 1 else "1M-row shard scans/s",
+                    "h2d_bytes_per_step": D * 4, "d2h_bytes_per_step": K * 12,
+                    "api": "css_index_search (host q -> host D,I)"},
+            "gpu_launches": int(n_launch), "launches_per_step": launches_per_step,
+            "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_batched(torch, native, dev, idx, qs, pk, world, rank, rows, dist):
+    """Batch-1024 exact top-10 on the same shard (tensor-core bound)."""
+    nq = 1024
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    Db = torch.empty((nq, K), device=dev, dtype=torch.float32)
+    Ib = torch.empty((nq, K), device=dev, dtype=torch.int64)
+
+    def step(i):
+        idx.search_device(qs.data_ptr(), nq, K, Db.data_ptr(), Ib.data_ptr(), 0, rank * rows, sp)
+    for _ in range(3):
+        step(0)
+    ms, _ = time_region(torch, dev, step, 10, dist)
+    ms /= 10
+    flops = 2.0 * nq * rows * D
+    tf = flops / (ms * 1e-3) / 1e12
+    return {"batch1024": {"qps": nq / (ms * 1e-3), "ms_per_call": ms, "achieved_tflops": tf,
+                          "frac_of_bf16_peak": tf / pk["bf16_tflops"], "peak": pk["bf16_tflops"],
+                          "algorithmic_flops": flops}}
+
+
+if __name__ == "__main__":
+    main()
