@@ -66,6 +66,25 @@ class css_filter(ctypes.Structure):
     ]
 
 
+class css_mpnet_config(ctypes.Structure):
+    _fields_ = [(n, c_int32) for n in ("vocab_size", "hidden_size", "num_layers", "num_heads", "intermediate_size",
+                                       "max_position", "rel_buckets", "rel_max_distance", "pad_token_id")] + \
+               [("layer_norm_eps", c_float)]
+
+
+_LAYER_FIELDS = ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "o_b", "ln1_w", "ln1_b",
+                 "ffn1_w", "ffn1_b", "ffn2_w", "ffn2_b", "ln2_w", "ln2_b")
+
+
+class css_mpnet_layer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in _LAYER_FIELDS]
+
+
+class css_mpnet_weights(ctypes.Structure):
+    _fields_ = [("word_emb", c_void_p), ("pos_emb", c_void_p), ("emb_ln_w", c_void_p), ("emb_ln_b", c_void_p),
+                ("rel_bias", c_void_p), ("layers", POINTER(css_mpnet_layer))]
+
+
 # name -> (restype, argtypes); every symbol include/css_b200.h declares
 SIGNATURES = {
     "css_abi_version": (c_int, []),
@@ -93,6 +112,18 @@ SIGNATURES = {
     "css_index_save": (c_int, [c_void_p, c_char_p]),
     "css_index_load": (c_int, [c_void_p, c_char_p]),
     "css_kernel_launch_count": (c_int64, []),
+    "css_mpnet_relative_bucket": (c_int, [c_int, c_int, c_int]),
+    "css_encoder_create": (c_int, [POINTER(css_mpnet_config), POINTER(css_mpnet_weights), c_int, c_int64,
+                                   POINTER(c_void_p)]),
+    "css_encoder_destroy": (c_int, [c_void_p]),
+    "css_encoder_dim": (c_int, [c_void_p]),
+    "css_encoder_max_tokens": (c_int64, [c_void_p]),
+    "css_encoder_max_seq_len": (c_int, [c_void_p]),
+    "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
+    "css_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "css_debug_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
+    "css_encoder_encode_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p,
+                                          c_void_p]),
 }
 
 _lib: Optional[ctypes.CDLL] = None

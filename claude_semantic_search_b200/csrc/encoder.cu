@@ -1,0 +1,488 @@
+// encoder.cu -- host side of the MPNet chunk encoder C ABI (include/css_b200.h).
+//
+// Forward pass of one packed batch of T tokens (n_seq sequences):
+//   E1  embed + LayerNorm                      -> x    bf16 [T, 768]
+//   per layer (12x):
+//     E2  x * Wqkv^T + b                       -> qkv  bf16 [T, 2304]   tcgen05 GEMM
+//     E3  softmax(q k^T / 8 + rel_bias) v      -> ctx  bf16 [T, 768]
+//     E4  ctx * Wo^T + b + x                   -> pre  f32  [T, 768]    tcgen05 GEMM
+//     E5  LayerNorm(pre)                       -> x1   bf16 [T, 768]
+//     E6a gelu(x1 * W1^T + b)                  -> h    bf16 [T, 3072]   tcgen05 GEMM
+//     E6b h * W2^T + b + x1                    -> pre  f32  [T, 768]    tcgen05 GEMM
+//     E5  LayerNorm(pre)                       -> x    bf16 [T, 768]
+//   E7  mean over tokens, L2 normalise         -> out  f32  [n_seq, 768]
+#include "encoder_kernels.cuh"
+#include "gemm_tc.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+using namespace css;
+using namespace css::enc;
+
+struct EncLayer {
+  __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+};
+
+struct css_encoder {
+  css_mpnet_config cfg{};
+  int device = 0;
+  int n_sm = 148;
+  int max_seq = 512;
+  int64_t max_tokens = 0;
+  cudaStream_t stream = nullptr;
+  // weights
+  float *word_emb = nullptr, *pos_emb = nullptr, *emb_ln_w = nullptr, *emb_ln_b = nullptr;
+  float* rel_table = nullptr;  // [heads][2*rel_half+1]
+  int rel_half = 0;
+  std::vector<EncLayer> layers;
+  std::vector<void*> owned;  // every device allocation, freed on destroy
+  // workspace
+  __nv_bfloat16 *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
+  float* pre = nullptr;
+  int32_t *ids_dev = nullptr, *cu_dev = nullptr;
+  float* out_dev = nullptr;
+  int64_t max_seqs = 0;
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  std::mutex mu;
+};
+
+namespace {
+
+template <typename T>
+int enc_alloc(css_encoder* e, T** p, size_t count) {
+  *p = nullptr;
+  if (count == 0) return CSS_OK;
+  cudaError_t err = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(err));
+    return CSS_ERR_OOM;
+  }
+  e->owned.push_back(*p);
+  return CSS_OK;
+}
+
+int upload_f32(css_encoder* e, float** dst, const float* src, size_t n) {
+  CSS_REQUIRE(src != nullptr, "a weight pointer is NULL");
+  CSS_CHECK(enc_alloc(e, dst, n));
+  CSS_CUDA(cudaMemcpyAsync(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  return CSS_OK;
+}
+
+// Upload fp32 [n] into a bf16 buffer slice through a device staging buffer.
+int upload_bf16_into(css_encoder* e, __nv_bfloat16* dst, const float* src, size_t n, float* stage) {
+  CSS_REQUIRE(src != nullptr, "a weight pointer is NULL");
+  CSS_CUDA(cudaMemcpyAsync(stage, src, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, e->stream>>>(stage, dst, (int64_t)n);
+  CSS_LAUNCHED();
+  // `stage` is reused by the next upload: same stream, so ordering is preserved, but the
+  // pageable source must be consumed before the caller may free it -> sync here.
+  CSS_CUDA(cudaStreamSynchronize(e->stream));
+  return CSS_OK;
+}
+
+int ensure_pinned(css_encoder* e, size_t bytes) {
+  if (bytes <= e->pinned_bytes) return CSS_OK;
+  if (e->pinned) {
+    cudaStreamSynchronize(e->stream);
+    cudaFreeHost(e->pinned);
+  }
+  e->pinned = nullptr;
+  e->pinned_bytes = 0;
+  size_t want = std::max<size_t>(bytes, (size_t)1 << 20);
+  cudaError_t err = cudaMallocHost(&e->pinned, want);
+  if (err != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(err));
+    return CSS_ERR_OOM;
+  }
+  e->pinned_bytes = want;
+  return CSS_OK;
+}
+
+// One forward pass over T packed tokens; everything on `st`.
+int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n_seq, int T, int max_len,
+            int normalize, float* out_dev, cudaStream_t st) {
+  const css_mpnet_config& c = e->cfg;
+  const int warps_per_block = 8;
+  const unsigned row_blocks = (unsigned)((T + warps_per_block - 1) / warps_per_block);
+  embed_ln_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(ids_dev, cu_dev, n_seq, T, e->word_emb, e->pos_emb,
+                                                               c.vocab_size, c.max_position, c.pad_token_id,
+                                                               e->emb_ln_w, e->emb_ln_b, c.layer_norm_eps, e->x);
+  CSS_LAUNCHED();
+  const int Lp = (max_len + 63) & ~63;
+  const size_t attn_smem = (size_t)Lp * 256 + (size_t)2 * Lp * sizeof(float);
+  CSS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
+  const dim3 attn_grid((unsigned)((max_len + kAttnQRows - 1) / kAttnQRows), kHeads, (unsigned)n_seq);
+
+  for (int l = 0; l < c.num_layers; ++l) {
+    const EncLayer& w = e->layers[l];
+    {
+      EpiBiasBf16<false>::Params p{e->qkv, w.bqkv, 3 * kHidden};
+      CSS_CHECK((gemm::launch<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
+                                                      e->n_sm, st)));
+    }
+    attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half, e->ctx);
+    CSS_LAUNCHED();
+    {
+      EpiBiasResidF32::Params p{e->pre, w.bo, e->x, kHidden};
+      CSS_CHECK((gemm::launch<256, EpiBiasResidF32>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
+                                                   e->n_sm, st)));
+    }
+    layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln1_w, w.ln1_b, c.layer_norm_eps,
+                                                                  e->x1);
+    CSS_LAUNCHED();
+    {
+      EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn};
+      CSS_CHECK((gemm::launch<256, EpiBiasBf16<true>>(e->x1, kHidden, w.w1, kHidden, T, kFfn, kHidden, 0, p, e->n_sm,
+                                                     st)));
+    }
+    {
+      EpiBiasResidF32::Params p{e->pre, w.b2, e->x1, kHidden};
+      CSS_CHECK((gemm::launch<256, EpiBiasResidF32>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
+    }
+    layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln2_w, w.ln2_b, c.layer_norm_eps,
+                                                                  e->x);
+    CSS_LAUNCHED();
+  }
+  pool_normalize_kernel<<<(unsigned)n_seq, 256, 0, st>>>(e->x, cu_dev, normalize, out_dev);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+int validate_cu(const css_encoder* e, const int32_t* cu, int n_seq, int* max_len_out) {
+  CSS_REQUIRE(cu[0] == 0, "cu_seqlens[0] must be 0");
+  int mx = 0;
+  for (int i = 0; i < n_seq; ++i) {
+    const int len = cu[i + 1] - cu[i];
+    CSS_REQUIRE(len >= 1, "sequence %d is empty (length %d)", i, len);
+    CSS_REQUIRE(len <= e->max_seq, "sequence %d has %d tokens, limit is %d", i, len, e->max_seq);
+    mx = std::max(mx, len);
+  }
+  *max_len_out = mx;
+  return CSS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int css_mpnet_relative_bucket(int relative_position, int num_buckets, int max_distance) {
+  // MPNetEncoder.relative_position_bucket (modeling_mpnet.py:338-357), float32 arithmetic
+  // in the order torch evaluates it.
+  int ret = 0;
+  int n = -relative_position;
+  num_buckets /= 2;
+  if (n < 0) {
+    ret += num_buckets;
+    n = -n;
+  }
+  const int max_exact = num_buckets / 2;
+  if (n < max_exact) return ret + n;
+  float v = logf((float)n / (float)max_exact);
+  v = v / (float)log((double)max_distance / (double)max_exact);
+  v = v * (float)(num_buckets - max_exact);
+  int large = max_exact + (int)v;
+  if (large > num_buckets - 1) large = num_buckets - 1;
+  return ret + large;
+}
+
+int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, int device, int64_t max_tokens,
+                       css_encoder** out) {
+  CSS_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  CSS_REQUIRE(cfg != nullptr && w != nullptr, "cfg / weights is NULL");
+  if (cfg->hidden_size != kHidden || cfg->num_heads != kHeads || cfg->intermediate_size != kFfn) {
+    set_error("this build serves hidden=768, heads=12, ffn=3072 (got %d, %d, %d)", cfg->hidden_size, cfg->num_heads,
+              cfg->intermediate_size);
+    return CSS_ERR_UNSUPPORTED;
+  }
+  CSS_REQUIRE(cfg->num_layers >= 1 && cfg->num_layers <= 64, "num_layers %d out of range", cfg->num_layers);
+  CSS_REQUIRE(cfg->vocab_size >= 2 && cfg->max_position >= 4, "bad vocab_size / max_position");
+  CSS_REQUIRE(cfg->rel_buckets >= 4 && cfg->rel_buckets % 2 == 0 && cfg->rel_max_distance > cfg->rel_buckets / 4,
+              "bad relative-position bucket configuration");
+  CSS_REQUIRE(w->layers != nullptr, "weights->layers is NULL");
+  CSS_CHECK(ensure_device(device));
+  DeviceGuard g(device);
+  css_encoder* e = new (std::nothrow) css_encoder();
+  if (!e) {
+    set_error("out of host memory");
+    return CSS_ERR_OOM;
+  }
+  e->cfg = *cfg;
+  e->device = device;
+  e->n_sm = sm_count(device);
+  e->max_seq = std::min(kMaxSeq, cfg->max_position - cfg->pad_token_id - 1);
+  if (max_tokens <= 0) max_tokens = 128 * 1024;
+  max_tokens = std::max<int64_t>(max_tokens, e->max_seq);
+  max_tokens = (max_tokens + 127) / 128 * 128;
+  e->max_tokens = max_tokens;
+  e->max_seqs = max_tokens;  // every sequence has >= 1 token
+  int rc = CSS_OK;
+  auto fail = [&](int code) {
+    css_encoder_destroy(e);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    return fail(CSS_ERR_CUDA);
+  }
+  const size_t H = kHidden;
+  if ((rc = upload_f32(e, &e->word_emb, w->word_emb, (size_t)cfg->vocab_size * H)) != CSS_OK) return fail(rc);
+  if ((rc = upload_f32(e, &e->pos_emb, w->pos_emb, (size_t)cfg->max_position * H)) != CSS_OK) return fail(rc);
+  if ((rc = upload_f32(e, &e->emb_ln_w, w->emb_ln_w, H)) != CSS_OK) return fail(rc);
+  if ((rc = upload_f32(e, &e->emb_ln_b, w->emb_ln_b, H)) != CSS_OK) return fail(rc);
+  // dense relative-position bias table: rel_table[h][d + rel_half] = rel_bias[bucket(d)][h]
+  {
+    if (!w->rel_bias) {
+      set_error("weights->rel_bias is NULL");
+      return fail(CSS_ERR_INVALID);
+    }
+    e->rel_half = e->max_seq - 1;
+    const int width = 2 * e->rel_half + 1;
+    std::vector<float> table((size_t)kHeads * width);
+    for (int d = -e->rel_half; d <= e->rel_half; ++d) {
+      const int b = css_mpnet_relative_bucket(d, cfg->rel_buckets, cfg->rel_max_distance);
+      for (int hh = 0; hh < kHeads; ++hh) table[(size_t)hh * width + d + e->rel_half] = w->rel_bias[(size_t)b * kHeads + hh];
+    }
+    if ((rc = enc_alloc(e, &e->rel_table, table.size())) != CSS_OK) return fail(rc);
+    if (cudaMemcpy(e->rel_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("rel_table upload failed");
+      return fail(CSS_ERR_CUDA);
+    }
+  }
+  float* stage = nullptr;
+  if ((rc = enc_alloc(e, &stage, (size_t)kFfn * H)) != CSS_OK) return fail(rc);
+  e->layers.resize(cfg->num_layers);
+  for (int l = 0; l < cfg->num_layers; ++l) {
+    const css_mpnet_layer& s = w->layers[l];
+    EncLayer& d = e->layers[l];
+    if ((rc = enc_alloc(e, &d.wqkv, 3 * H * H)) != CSS_OK) return fail(rc);
+    if ((rc = enc_alloc(e, &d.wo, H * H)) != CSS_OK) return fail(rc);
+    if ((rc = enc_alloc(e, &d.w1, (size_t)kFfn * H)) != CSS_OK) return fail(rc);
+    if ((rc = enc_alloc(e, &d.w2, (size_t)kFfn * H)) != CSS_OK) return fail(rc);
+    if ((rc = enc_alloc(e, &d.bqkv, 3 * H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.wqkv, s.q_w, H * H, stage)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.wqkv + H * H, s.k_w, H * H, stage)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.wqkv + 2 * H * H, s.v_w, H * H, stage)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.wo, s.o_w, H * H, stage)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.w1, s.ffn1_w, (size_t)kFfn * H, stage)) != CSS_OK) return fail(rc);
+    if ((rc = upload_bf16_into(e, d.w2, s.ffn2_w, (size_t)kFfn * H, stage)) != CSS_OK) return fail(rc);
+    if (!s.q_b || !s.k_b || !s.v_b) {
+      set_error("layer %d: a q/k/v bias pointer is NULL", l);
+      return fail(CSS_ERR_INVALID);
+    }
+    if (cudaMemcpyAsync(d.bqkv, s.q_b, H * 4, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaMemcpyAsync(d.bqkv + H, s.k_b, H * 4, cudaMemcpyHostToDevice, e->stream) != cudaSuccess ||
+        cudaMemcpyAsync(d.bqkv + 2 * H, s.v_b, H * 4, cudaMemcpyHostToDevice, e->stream) != cudaSuccess) {
+      set_error("bias upload failed");
+      return fail(CSS_ERR_CUDA);
+    }
+    if ((rc = upload_f32(e, &d.bo, s.o_b, H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.b1, s.ffn1_b, kFfn)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.b2, s.ffn2_b, H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.ln1_w, s.ln1_w, H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.ln1_b, s.ln1_b, H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.ln2_w, s.ln2_w, H)) != CSS_OK) return fail(rc);
+    if ((rc = upload_f32(e, &d.ln2_b, s.ln2_b, H)) != CSS_OK) return fail(rc);
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+      set_error("weight upload failed");
+      return fail(CSS_ERR_CUDA);
+    }
+  }
+  // workspace
+  const size_t T = (size_t)max_tokens;
+  if ((rc = enc_alloc(e, &e->x, T * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->x1, T * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->qkv, T * 3 * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->ctx, T * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->h, T * kFfn)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->pre, T * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->ids_dev, T)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->cu_dev, (size_t)e->max_seqs + 1)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->out_dev, (size_t)e->max_seqs * H)) != CSS_OK) return fail(rc);
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+    set_error("encoder initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail(CSS_ERR_CUDA);
+  }
+  *out = e;
+  return CSS_OK;
+}
+
+int css_encoder_destroy(css_encoder* e) {
+  if (!e) return CSS_OK;
+  {
+    DeviceGuard g(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->owned) cudaFree(p);
+    if (e->pinned) cudaFreeHost(e->pinned);
+    if (e->stream) cudaStreamDestroy(e->stream);
+  }
+  delete e;
+  return CSS_OK;
+}
+
+int css_encoder_dim(const css_encoder* e) { return e ? e->cfg.hidden_size : CSS_ERR_INVALID; }
+int64_t css_encoder_max_tokens(const css_encoder* e) { return e ? e->max_tokens : (int64_t)CSS_ERR_INVALID; }
+int css_encoder_max_seq_len(const css_encoder* e) { return e ? e->max_seq : CSS_ERR_INVALID; }
+
+int css_encoder_encode_device(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_seqlens_dev,
+                              const int32_t* cu_seqlens_host, int32_t n_seq, int normalize, float* out_dev,
+                              void* stream) {
+  CSS_REQUIRE(e != nullptr, "encoder is NULL");
+  CSS_REQUIRE(n_seq >= 0, "n_seq < 0");
+  if (n_seq == 0) return CSS_OK;
+  CSS_REQUIRE(ids_dev && cu_seqlens_dev && cu_seqlens_host && out_dev, "NULL buffer");
+  int max_len = 0;
+  CSS_CHECK(validate_cu(e, cu_seqlens_host, n_seq, &max_len));
+  const int T = cu_seqlens_host[n_seq];
+  CSS_REQUIRE(T <= e->max_tokens, "%d tokens exceed the workspace (%lld)", T, (long long)e->max_tokens);
+  std::lock_guard<std::mutex> lk(e->mu);
+  DeviceGuard g(e->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : e->stream;
+  return forward(e, ids_dev, cu_seqlens_dev, n_seq, T, max_len, normalize, out_dev, st);
+}
+
+int css_encoder_encode(css_encoder* e, const int32_t* ids_host, const int32_t* cu_seqlens_host, int32_t n_seq,
+                       int normalize, float* out_host) {
+  CSS_REQUIRE(e != nullptr, "encoder is NULL");
+  CSS_REQUIRE(n_seq >= 0, "n_seq < 0");
+  if (n_seq == 0) return CSS_OK;
+  CSS_REQUIRE(ids_host && cu_seqlens_host && out_host, "NULL buffer");
+  int max_len_all = 0;
+  CSS_CHECK(validate_cu(e, cu_seqlens_host, n_seq, &max_len_all));
+  CSS_CHECK(ensure_device(e->device));
+  std::lock_guard<std::mutex> lk(e->mu);
+  DeviceGuard g(e->device);
+  cudaStream_t st = e->stream;
+  const size_t H = kHidden;
+  int s0 = 0;
+  while (s0 < n_seq) {
+    // greedy pass: as many whole sequences as fit max_tokens
+    int s1 = s0;
+    int max_len = 0;
+    const int base = cu_seqlens_host[s0];
+    while (s1 < n_seq && cu_seqlens_host[s1 + 1] - base <= e->max_tokens && s1 - s0 < e->max_seqs) {
+      max_len = std::max(max_len, cu_seqlens_host[s1 + 1] - cu_seqlens_host[s1]);
+      ++s1;
+    }
+    const int ns = s1 - s0;
+    const int T = cu_seqlens_host[s1] - base;
+    const size_t ids_bytes = (size_t)T * 4, cu_bytes = (size_t)(ns + 1) * 4, out_bytes = (size_t)ns * H * 4;
+    const size_t cu_off = (ids_bytes + 15) / 16 * 16, out_off = (cu_off + cu_bytes + 15) / 16 * 16;
+    CSS_CHECK(ensure_pinned(e, out_off + out_bytes));
+    unsigned char* pin = reinterpret_cast<unsigned char*>(e->pinned);
+    memcpy(pin, ids_host + base, ids_bytes);
+    int32_t* cu_pin = reinterpret_cast<int32_t*>(pin + cu_off);
+    for (int i = 0; i <= ns; ++i) cu_pin[i] = cu_seqlens_host[s0 + i] - base;
+    CSS_CUDA(cudaMemcpyAsync(e->ids_dev, pin, ids_bytes, cudaMemcpyHostToDevice, st));
+    CSS_CUDA(cudaMemcpyAsync(e->cu_dev, cu_pin, cu_bytes, cudaMemcpyHostToDevice, st));
+    CSS_CHECK(forward(e, e->ids_dev, e->cu_dev, ns, T, max_len, normalize, e->out_dev, st));
+    CSS_CUDA(cudaMemcpyAsync(pin + out_off, e->out_dev, out_bytes, cudaMemcpyDeviceToHost, st));
+    CSS_CUDA(cudaStreamSynchronize(st));
+    memcpy(out_host + (size_t)s0 * H, pin + out_off, out_bytes);
+    s0 = s1;
+  }
+  return CSS_OK;
+}
+
+// ---- diagnostics ---------------------------------------------------------------------
+namespace {
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  int alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cudaMalloc(%zu) failed", bytes);
+      return CSS_ERR_OOM;
+    }
+    return CSS_OK;
+  }
+};
+static __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = __bfloat162float(s[i]);
+}
+int to_bf16_dev(const float* host, size_t n, DevBuf& f32, DevBuf& b16, cudaStream_t st) {
+  CSS_CHECK(f32.alloc(n * 4));
+  CSS_CHECK(b16.alloc(n * 2));
+  CSS_CUDA(cudaMemcpyAsync(f32.p, host, n * 4, cudaMemcpyHostToDevice, st));
+  f32_to_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const float*)f32.p, (__nv_bfloat16*)b16.p, (int64_t)n);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+}  // namespace
+
+int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int N, int K, int gelu, int device,
+                   float* out) {
+  CSS_REQUIRE(A && B && bias && out, "NULL buffer");
+  CSS_CHECK(ensure_device(device));
+  DeviceGuard g(device);
+  cudaStream_t st = nullptr;
+  DevBuf a32, a16, b32, b16, biasd, o16, o32;
+  CSS_CHECK(to_bf16_dev(A, (size_t)M * K, a32, a16, st));
+  CSS_CHECK(to_bf16_dev(B, (size_t)N * K, b32, b16, st));
+  CSS_CHECK(biasd.alloc((size_t)N * 4));
+  CSS_CUDA(cudaMemcpyAsync(biasd.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CSS_CHECK(o16.alloc((size_t)M * N * 2));
+  CSS_CHECK(o32.alloc((size_t)M * N * 4));
+  CSS_CUDA(cudaMemsetAsync(o16.p, 0xff, (size_t)M * N * 2, st));
+  int rc;
+  if (gelu) {
+    EpiBiasBf16<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
+    rc = gemm::launch<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+  } else {
+    EpiBiasBf16<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
+    rc = gemm::launch<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+  }
+  CSS_CHECK(rc);
+  const int64_t n = (int64_t)M * N;
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o16.p, (float*)o32.p, n);
+  CSS_LAUNCHED();
+  CSS_CUDA(cudaMemcpyAsync(out, o32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CSS_CUDA(cudaStreamSynchronize(st));
+  return CSS_OK;
+}
+
+int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, const float* rel_table, int rel_half,
+                        int device, float* ctx) {
+  CSS_REQUIRE(qkv && cu_seqlens && rel_table && ctx && n_seq >= 1, "bad arguments");
+  CSS_CHECK(ensure_device(device));
+  DeviceGuard g(device);
+  cudaStream_t st = nullptr;
+  const int T = cu_seqlens[n_seq];
+  int max_len = 0;
+  for (int i = 0; i < n_seq; ++i) max_len = std::max(max_len, cu_seqlens[i + 1] - cu_seqlens[i]);
+  CSS_REQUIRE(max_len >= 1 && max_len <= kMaxSeq && rel_half >= max_len - 1, "bad sequence lengths");
+  DevBuf q32, q16, cud, reld, c16, c32;
+  CSS_CHECK(to_bf16_dev(qkv, (size_t)T * 3 * kHidden, q32, q16, st));
+  CSS_CHECK(cud.alloc((size_t)(n_seq + 1) * 4));
+  CSS_CUDA(cudaMemcpyAsync(cud.p, cu_seqlens, (size_t)(n_seq + 1) * 4, cudaMemcpyHostToDevice, st));
+  const size_t rel_n = (size_t)kHeads * (2 * rel_half + 1);
+  CSS_CHECK(reld.alloc(rel_n * 4));
+  CSS_CUDA(cudaMemcpyAsync(reld.p, rel_table, rel_n * 4, cudaMemcpyHostToDevice, st));
+  CSS_CHECK(c16.alloc((size_t)T * kHidden * 2));
+  CSS_CHECK(c32.alloc((size_t)T * kHidden * 4));
+  const int Lp = (max_len + 63) & ~63;
+  const size_t smem = (size_t)Lp * 256 + (size_t)2 * Lp * sizeof(float);
+  CSS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((max_len + kAttnQRows - 1) / kAttnQRows), kHeads, (unsigned)n_seq);
+  attention_kernel<<<grid, kAttnThreads, smem, st>>>((const __nv_bfloat16*)q16.p, (const int32_t*)cud.p,
+                                                     (const float*)reld.p, rel_half, (__nv_bfloat16*)c16.p);
+  CSS_LAUNCHED();
+  const int64_t n = (int64_t)T * kHidden;
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)c16.p, (float*)c32.p, n);
+  CSS_LAUNCHED();
+  CSS_CUDA(cudaMemcpyAsync(ctx, c32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CSS_CUDA(cudaStreamSynchronize(st));
+  return CSS_OK;
+}
+
+}  // extern "C"

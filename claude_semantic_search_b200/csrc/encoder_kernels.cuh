@@ -1,0 +1,411 @@
+// encoder_kernels.cuh -- device kernels of the MPNet chunk encoder other than the GEMM
+// main loop (gemm_tc.cuh):
+//   E1  token + position embedding gather, LayerNorm            modeling_mpnet.py:72-96
+//   E3  multi-head attention with relative-position bias        modeling_mpnet.py:144-185,322-360
+//   E5  LayerNorm over (GEMM + bias + residual)                 modeling_mpnet.py:206,242
+//   E7  masked mean pooling + L2 normalisation                  sentence-transformers Pooling / Normalize
+//   GEMM epilogue functors: +bias, +bias+GELU(erf), +bias+residual
+//
+// Token layout: sequences are packed back to back (no padding rows); cu_seqlens[i] is the
+// first token of sequence i.  Activations are [T, C] row-major.
+#pragma once
+#include "tc_common.cuh"
+
+namespace css {
+namespace enc {
+
+constexpr int kHidden = 768;
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 64;
+constexpr int kFfn = 3072;
+constexpr int kMaxSeq = 512;
+
+__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// ------------------------------------------------------------------------
+// fp32 -> bf16 (weights at load time)
+// ------------------------------------------------------------------------
+static __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
+}
+
+// ------------------------------------------------------------------------
+// Row LayerNorm helper: one warp per row of 768, 24 values per lane held as 6 float4
+// (lane owns columns j*128 + lane*4 .. +3).  Two-pass (mean, then centred variance).
+// ------------------------------------------------------------------------
+__device__ __forceinline__ void warp_layernorm_768(float4 (&v)[6], const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, float eps, int lane) {
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  const float mean = warp_sum(s) * (1.f / kHidden);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    ss += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.f / kHidden) + eps);
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + j * 32 + lane);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + j * 32 + lane);
+    v[j].x = (v[j].x - mean) * rstd * g.x + b.x;
+    v[j].y = (v[j].y - mean) * rstd * g.y + b.y;
+    v[j].z = (v[j].z - mean) * rstd * g.z + b.z;
+    v[j].w = (v[j].w - mean) * rstd * g.w + b.w;
+  }
+}
+
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* __restrict__ row, const float4 (&v)[6], int lane) {
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    uint2 p;
+    p.x = pack_bf16(v[j].x, v[j].y);
+    p.y = pack_bf16(v[j].z, v[j].w);
+    *reinterpret_cast<uint2*>(row + j * 128 + lane * 4) = p;
+  }
+}
+
+// E1: x[t] = LayerNorm(word_emb[ids[t]] + pos_emb[pad_id + 1 + index_in_sequence]).
+static __global__ void embed_ln_kernel(const int32_t* __restrict__ ids, const int32_t* __restrict__ cu, int n_seq,
+                                       int T, const float* __restrict__ word_emb, const float* __restrict__ pos_emb,
+                                       int vocab, int max_pos, int pad_id, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ x) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  // sequence of token t: last i with cu[i] <= t
+  int lo = 0, hi = n_seq;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(cu + mid) <= t) lo = mid; else hi = mid;
+  }
+  int id = __ldg(ids + t);
+  id = min(max(id, 0), vocab - 1);
+  // create_position_ids_from_input_ids: cumsum(ids != pad) * (ids != pad) + pad; packed
+  // input holds no pad tokens, so the position is index + 1 + pad.
+  int pos = (t - __ldg(cu + lo)) + 1 + pad_id;
+  if (id == pad_id) pos = pad_id;
+  pos = min(pos, max_pos - 1);
+  const float4* w = reinterpret_cast<const float4*>(word_emb + (size_t)id * kHidden);
+  const float4* p = reinterpret_cast<const float4*>(pos_emb + (size_t)pos * kHidden);
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    float4 a = __ldg(w + j * 32 + lane), b = __ldg(p + j * 32 + lane);
+    v[j] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+  warp_layernorm_768(v, gamma, beta, eps, lane);
+  store_row_bf16(x + (size_t)t * kHidden, v, lane);
+}
+
+// E5: y[t] = LayerNorm(pre[t]) ; pre already holds GEMM + bias + residual in fp32.
+static __global__ void layernorm_kernel(const float* __restrict__ pre, int T, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  const float4* r = reinterpret_cast<const float4*>(pre + (size_t)t * kHidden);
+  float4 v[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) v[j] = ld_stream_f4(r + j * 32 + lane);
+  warp_layernorm_768(v, gamma, beta, eps, lane);
+  store_row_bf16(y + (size_t)t * kHidden, v, lane);
+}
+
+// E7: out[s] = normalise(mean over tokens of x).  One CTA (256 threads) per sequence,
+// thread c owns columns c, c+256, c+512.
+static __global__ void pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu,
+                                             int normalize, float* __restrict__ out) {
+  const int s = blockIdx.x;
+  const int t0 = cu[s], t1 = cu[s + 1];
+  const int c = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const __nv_bfloat16* r = x + (size_t)t * kHidden;
+    a0 += __bfloat162float(r[c]);
+    a1 += __bfloat162float(r[c + 256]);
+    a2 += __bfloat162float(r[c + 512]);
+  }
+  const float denom = fmaxf((float)(t1 - t0), 1e-9f);  // Pooling: clamp(sum(mask), min=1e-9)
+  a0 /= denom; a1 /= denom; a2 /= denom;
+  if (normalize) {
+    __shared__ float red[8];
+    float ss = a0 * a0 + a1 * a1 + a2 * a2;
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float nrm = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+    a0 /= nrm; a1 /= nrm; a2 /= nrm;
+  }
+  float* o = out + (size_t)s * kHidden;
+  o[c] = a0; o[c + 256] = a1; o[c + 512] = a2;
+}
+
+// ------------------------------------------------------------------------
+// E3: attention.  CTA = 4 warps = 64 query rows of one (sequence, head); the whole K and
+// V of that (sequence, head) live in shared memory (L <= 512 keys x 64 dims x bf16), each
+// warp runs an online-softmax sweep over 64-key blocks with mma.sync m16n8k16 (bf16 in,
+// fp32 accumulate).  scores = q.k / 8 + rel_table[h][j - i]; keys >= L do not exist in
+// the packed layout (the reference masks its padded keys with finfo.min -> weight 0).
+// ------------------------------------------------------------------------
+constexpr int kAttnThreads = 128;
+constexpr int kAttnQRows = 64;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void cp_async_16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+
+// smem: K [Lp][64] bf16 (128 B rows, 16-byte chunks XOR-swizzled by row & 7), V likewise,
+// rel [2*Lp] fp32 (rel[d + Lp - 1] = bias of relative position d = j - i).
+static __global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
+                 const float* __restrict__ rel_table, int rel_half /* table holds d in [-rel_half, rel_half] */,
+                 __nv_bfloat16* __restrict__ ctx) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int s = blockIdx.z, h = blockIdx.y;
+  const int t0 = cu[s];
+  const int L = cu[s + 1] - t0;
+  const int q0 = blockIdx.x * kAttnQRows;
+  if (q0 >= L) return;
+  const int Lp = (L + 63) & ~63;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + (size_t)Lp * 128;
+  float* sRel = reinterpret_cast<float*>(smem + (size_t)Lp * 256);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kLd = 3 * kHidden;
+
+  // ---- stage K, V (cp.async) and the bias window ----
+  {
+    const int chunk = tid & 7;
+    for (int r = tid >> 3; r < Lp; r += kAttnThreads / 8) {
+      const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+      if (r < L) {
+        const __nv_bfloat16* g = qkv + (size_t)(t0 + r) * kLd + h * kHeadDim + chunk * 8;
+        cp_async_16(tc::smem_u32(sK) + off, g + kHidden);
+        cp_async_16(tc::smem_u32(sV) + off, g + 2 * kHidden);
+      } else {
+        *reinterpret_cast<uint4*>(sK + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sV + off) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* rt = rel_table + (size_t)h * (2 * rel_half + 1);
+    for (int i = tid; i < 2 * Lp - 1; i += kAttnThreads) {
+      int d = i - (Lp - 1);
+      d = max(-rel_half, min(rel_half, d));
+      sRel[i] = rt[d + rel_half];
+    }
+  }
+
+  // ---- Q fragments straight from global (rows of this warp) ----
+  const int qrow = q0 + warp * 16 + (lane >> 2);  // and qrow + 8
+  uint32_t qa[4][4];
+  {
+    const __nv_bfloat16* g0 = qkv + (size_t)(t0 + min(qrow, L - 1)) * kLd + h * kHeadDim + (lane & 3) * 2;
+    const __nv_bfloat16* g1 = qkv + (size_t)(t0 + min(qrow + 8, L - 1)) * kLd + h * kHeadDim + (lane & 3) * 2;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(g0 + ks * 16));
+      qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(g1 + ks * 16));
+      qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(g0 + ks * 16 + 8));
+      qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(g1 + ks * 16 + 8));
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  float o[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  constexpr float kLog2e = 1.4426950408889634f;
+  const uint32_t sK_u = tc::smem_u32(sK), sV_u = tc::smem_u32(sV);
+
+  for (int kb = 0; kb < Lp; kb += 64) {
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      const int key = kb + nt * 8 + (lane & 7);
+#pragma unroll
+      for (int ks2 = 0; ks2 < 2; ++ks2) {
+        uint32_t b[4];
+        const int c = ks2 * 4 + (lane >> 3);
+        ldmatrix_x4(b, sK_u + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4));
+        mma_bf16_16816(sc[nt], qa[ks2 * 2], b[0], b[1]);
+        mma_bf16_16816(sc[nt], qa[ks2 * 2 + 1], b[2], b[3]);
+      }
+    }
+    // scale, bias, mask; running max
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = kb + nt * 8 + (lane & 3) * 2 + (e & 1);
+        const int i = qrow + ((e >> 1) << 3);
+        float v = sc[nt][e] * 0.125f + sRel[j - i + Lp - 1];
+        v = (j < L) ? v : -INFINITY;
+        sc[nt][e] = v;
+        if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: key kb is always < L
+    const float corr0 = exp2f((m0 - mn0) * kLog2e), corr1 = exp2f((m1 - mn1) * kLog2e);
+    m0 = mn0; m1 = mn1;
+    float rs0 = 0.f, rs1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = exp2f((sc[nt][0] - mn0) * kLog2e), p1 = exp2f((sc[nt][1] - mn0) * kLog2e);
+      const float p2 = exp2f((sc[nt][2] - mn1) * kLog2e), p3 = exp2f((sc[nt][3] - mn1) * kLog2e);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pa[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16(p0, p1);
+      pa[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16(p2, p3);
+    }
+    l0 = l0 * corr0 + rs0;
+    l1 = l1 * corr1 + rs1;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      o[nd][0] *= corr0; o[nd][1] *= corr0; o[nd][2] *= corr1; o[nd][3] *= corr1;
+    }
+    // O += P V
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int key = kb + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+      for (int nd2 = 0; nd2 < 4; ++nd2) {
+        uint32_t b[4];
+        const int c = nd2 * 2 + (lane >> 4);
+        ldmatrix_x4_trans(b, sV_u + (uint32_t)key * 128u + (uint32_t)((c ^ (key & 7)) << 4));
+        mma_bf16_16816(o[nd2 * 2], pa[kk], b[0], b[1]);
+        mma_bf16_16816(o[nd2 * 2 + 1], pa[kk], b[2], b[3]);
+      }
+    }
+  }
+  // row sums across the quad
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1;
+  __nv_bfloat16* c0 = ctx + (size_t)(t0 + qrow) * kHidden + h * kHeadDim + (lane & 3) * 2;
+  __nv_bfloat16* c1 = c0 + (size_t)8 * kHidden;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) {
+    if (qrow < L) *reinterpret_cast<uint32_t*>(c0 + nd * 8) = pack_bf16(o[nd][0] * inv0, o[nd][1] * inv0);
+    if (qrow + 8 < L) *reinterpret_cast<uint32_t*>(c1 + nd * 8) = pack_bf16(o[nd][2] * inv1, o[nd][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------------
+// GEMM epilogue functors (see gemm_tc.cuh for the concept).
+// ------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+// out_bf16[m, n] = acc + bias[n]            (QKV projection)
+// out_bf16[m, n] = gelu(acc + bias[n])      (FFN up-projection)
+template <bool kGelu>
+struct EpiBiasBf16 {
+  struct Params {
+    __nv_bfloat16* out;
+    const float* bias;
+    int ldo;
+  };
+  const Params& p;
+  __device__ EpiBiasBf16(const Params& p_, int) : p(p_) {}
+  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
+    if (!row_ok) return;
+    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + n0);
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
+      float f[8];
+      f[0] = __uint_as_float(v[g * 8 + 0]) + ba.x; f[1] = __uint_as_float(v[g * 8 + 1]) + ba.y;
+      f[2] = __uint_as_float(v[g * 8 + 2]) + ba.z; f[3] = __uint_as_float(v[g * 8 + 3]) + ba.w;
+      f[4] = __uint_as_float(v[g * 8 + 4]) + bb.x; f[5] = __uint_as_float(v[g * 8 + 5]) + bb.y;
+      f[6] = __uint_as_float(v[g * 8 + 6]) + bb.z; f[7] = __uint_as_float(v[g * 8 + 7]) + bb.w;
+      if constexpr (kGelu) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = gelu_erf(f[i]);
+      }
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+      o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+      dst[g] = o;
+    }
+  }
+  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void finish() {}
+};
+
+// out_f32[m, n] = acc + bias[n] + resid_bf16[m, n]   (attention output / FFN down projections;
+// the LayerNorm kernel consumes out_f32)
+struct EpiBiasResidF32 {
+  struct Params {
+    float* out;
+    const float* bias;
+    const __nv_bfloat16* resid;
+    int ld;  // leading dimension of out and resid
+  };
+  const Params& p;
+  __device__ EpiBiasResidF32(const Params& p_, int) : p(p_) {}
+  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
+    if (!row_ok) return;
+    float4* dst = reinterpret_cast<float4*>(p.out + (size_t)m * p.ld + n0);
+    const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + (size_t)m * p.ld + n0);
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const uint4 r = __ldg(r4 + g);
+      const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
+      float4 o0, o1;
+      o0.x = __uint_as_float(v[g * 8 + 0]) + ba.x + bf16_lo(r.x);
+      o0.y = __uint_as_float(v[g * 8 + 1]) + ba.y + bf16_hi(r.x);
+      o0.z = __uint_as_float(v[g * 8 + 2]) + ba.z + bf16_lo(r.y);
+      o0.w = __uint_as_float(v[g * 8 + 3]) + ba.w + bf16_hi(r.y);
+      o1.x = __uint_as_float(v[g * 8 + 4]) + bb.x + bf16_lo(r.z);
+      o1.y = __uint_as_float(v[g * 8 + 5]) + bb.y + bf16_hi(r.z);
+      o1.z = __uint_as_float(v[g * 8 + 6]) + bb.z + bf16_lo(r.w);
+      o1.w = __uint_as_float(v[g * 8 + 7]) + bb.w + bf16_hi(r.w);
+      dst[g * 2] = o0;
+      dst[g * 2 + 1] = o1;
+    }
+  }
+  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void finish() {}
+};
+
+}  // namespace enc
+}  // namespace css

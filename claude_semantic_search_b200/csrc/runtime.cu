@@ -1,5 +1,5 @@
 // runtime.cu -- error state, device probing and small shared utilities.
-#include "css_common.cuh"
+#include "tc_common.cuh"
 
 namespace css {
 
@@ -43,6 +43,57 @@ int sm_count(int device) {
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 148;
   return n > 0 ? n : 148;
+}
+
+
+// ---- TMA tensor maps ---------------------------------------------------------------
+// libcuda is not linked (the .so must load on a box without a driver); the encoder is
+// resolved through the runtime's driver entry point query on first use.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+  static std::atomic<void*> cached{nullptr};
+  void* fn = cached.load(std::memory_order_acquire);
+  if (fn) return reinterpret_cast<PFN_encodeTiled>(fn);
+  cudaDriverEntryPointQueryResult qres;
+  void* p = nullptr;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) {
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  cached.store(p, std::memory_order_release);
+  return reinterpret_cast<PFN_encodeTiled>(p);
+}
+
+int encode_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                        uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return CSS_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0 || box_cols * 2 != 128 ||
+      box_rows > 256) {
+    set_error("tensor map: unsupported alignment / box (base %p, ld %llu, box %u x %u)", base,
+              (unsigned long long)ld_elems, box_rows, box_cols);
+    return CSS_ERR_INVALID;
+  }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %llu cols %llu ld %llu)", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+    return CSS_ERR_CUDA;
+  }
+  return CSS_OK;
 }
 
 }  // namespace css

@@ -171,6 +171,87 @@ int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, i
 int css_index_save(css_index* h, const char* path);
 int css_index_load(css_index* h, const char* path);
 
+
+/* ------------------------------------------------------------------ */
+/* MPNet chunk encoder (half A of the hot path)                        */
+/* ------------------------------------------------------------------ */
+/* Replaces SentenceTransformer("all-mpnet-base-v2").encode(...) as called at
+ * src/embeddings.py:184-188 (single text) and :216-222 (batch): MPNetModel forward
+ * (transformers modeling_mpnet.py), masked mean pooling and L2 normalisation, on
+ * already-tokenised input.  bf16 tensor-core GEMMs with fp32 accumulation, fp32
+ * LayerNorm / softmax / pooling. */
+typedef struct css_encoder css_encoder;
+
+typedef struct css_mpnet_config {
+  int32_t vocab_size;          /* 30527 */
+  int32_t hidden_size;         /* 768  (only value this build serves) */
+  int32_t num_layers;          /* 12 */
+  int32_t num_heads;           /* 12   (head dim must be 64) */
+  int32_t intermediate_size;   /* 3072 */
+  int32_t max_position;        /* 514  rows of the position table */
+  int32_t rel_buckets;         /* 32 */
+  int32_t rel_max_distance;    /* 128 */
+  int32_t pad_token_id;        /* 1: position ids are pad_token_id + 1 + index */
+  float layer_norm_eps;        /* 1e-5 */
+} css_mpnet_config;
+
+/* One transformer layer; every pointer is HOST float32, nn.Linear layout [out, in]. */
+typedef struct css_mpnet_layer {
+  const float *q_w, *q_b, *k_w, *k_b, *v_w, *v_b, *o_w, *o_b; /* attention.attn.{q,k,v,o} */
+  const float *ln1_w, *ln1_b;                                 /* attention.LayerNorm */
+  const float *ffn1_w, *ffn1_b;                               /* intermediate.dense [3072,768] */
+  const float *ffn2_w, *ffn2_b;                               /* output.dense [768,3072] */
+  const float *ln2_w, *ln2_b;                                 /* output.LayerNorm */
+} css_mpnet_layer;
+
+typedef struct css_mpnet_weights {
+  const float* word_emb;   /* [vocab_size, hidden] */
+  const float* pos_emb;    /* [max_position, hidden] */
+  const float *emb_ln_w, *emb_ln_b;
+  const float* rel_bias;   /* encoder.relative_attention_bias.weight [rel_buckets, num_heads] */
+  const css_mpnet_layer* layers; /* num_layers entries */
+} css_mpnet_weights;
+
+/* Bucket of a relative position (memory - context), the arithmetic of
+ * MPNetEncoder.relative_position_bucket.  Pure host function (no device needed). */
+int css_mpnet_relative_bucket(int relative_position, int num_buckets, int max_distance);
+
+/* Uploads the weights (linear weights converted to bf16, Q/K/V fused) and sizes the
+ * activation workspace for `max_tokens` tokens per forward pass (0 = default). */
+int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, int device,
+                       int64_t max_tokens, css_encoder** out);
+int css_encoder_destroy(css_encoder* h);
+int css_encoder_dim(const css_encoder* h);
+int64_t css_encoder_max_tokens(const css_encoder* h);
+/* Longest sequence one call accepts (max_position - pad_token_id - 1, at most 512). */
+int css_encoder_max_seq_len(const css_encoder* h);
+
+/* Encode n_seq token sequences packed back to back: ids[cu_seqlens[i] .. cu_seqlens[i+1])
+ * is sequence i (already truncated, with its <s> ... </s> framing, no padding).
+ * out: HOST float32 [n_seq, hidden]: mean over the sequence's tokens of the last
+ * hidden state (sentence-transformers Pooling, mean mode), then if normalize != 0
+ * divided by max(||.||_2, 1e-12) (sentence-transformers Normalize).  Any number of
+ * tokens: the call splits into passes of at most max_tokens. */
+int css_encoder_encode(css_encoder* h, const int32_t* ids_host, const int32_t* cu_seqlens_host,
+                       int32_t n_seq, int normalize, float* out_host);
+/* Device variant: ids_dev / cu_seqlens_dev / out_dev on the encoder's device;
+ * cu_seqlens_host is still needed to size the launch.  total tokens <= max_tokens.
+ * Asynchronous on `stream` (NULL = the handle's stream). */
+int css_encoder_encode_device(css_encoder* h, const int32_t* ids_dev, const int32_t* cu_seqlens_dev,
+                              const int32_t* cu_seqlens_host, int32_t n_seq, int normalize,
+                              float* out_dev, void* stream);
+
+/* Diagnostic entry points used by the kernel-level parity tests (HOST float32 buffers,
+ * rounded to bf16 on the device exactly as the encoder does):
+ *   gemm:      out[M,N] = bf16(A[M,K]) * bf16(B[N,K])^T + bias[N], optionally GELU(erf),
+ *              through the tcgen05 kernel of the encoder; out is the bf16 result widened.
+ *   attention: ctx[T,768] from packed qkv[T,2304] (q | k | v), per-head relative bias
+ *              rel_table[12][2*rel_half+1] indexed by (key - query) + rel_half. */
+int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int N, int K, int gelu,
+                   int device, float* out);
+int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, const float* rel_table,
+                        int rel_half, int device, float* ctx);
+
 /* Timing hook for benchmarks: number of kernels this library has launched in
  * this process (all handles). */
 int64_t css_kernel_launch_count(void);
