@@ -198,8 +198,9 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS, help="corpus rows per GPU")
     ap.add_argument("--no-extra", action="store_true", help="skip the batch-1024 / encoder legs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--only", default="", choices=["", "encode", "batched"], help="profiling aid: run one extra leg only")
     ap.add_argument("--full", action="store_true", help="also run the 10M-row filtered leg")
-    ap.add_argument("--encode-seqs", type=int, default=4096)
+    ap.add_argument("--encode-seqs", type=int, default=256)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -228,6 +229,10 @@ def main():
     if rank == 0 and not args.no_cpu:
         cpu_base, _ = cpu_search_baseline()
 
+    if args.only == "encode":
+        from bench_encoder import bench_encoder
+        print(json.dumps(bench_encoder(torch, dev, pk, world, rank, dist, args)))
+        return
     rows = args.rows
     idx = build_shard(torch, native, dev, rows, seed=42 + rank)
     gq = torch.Generator(device=dev)

@@ -1,0 +1,90 @@
+"""Encoder leg of bench.py (BASELINE configs[2]: MPNet encode at seq len 384, bf16,
+data-parallel over the ranks with no collective)."""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+SEQ_LEN = 384
+FLOP_PER_CHUNK = 12 * (24 * SEQ_LEN * 768 ** 2 + 4 * SEQ_LEN ** 2 * 768)  # 70.67 GFLOP
+
+
+def synthetic_batch(n_seq: int, seed: int):
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(4, 30526, size=(n_seq, SEQ_LEN), dtype=np.int64).astype(np.int32)
+    ids[:, 0] = 0
+    ids[:, -1] = 2
+    cu = (np.arange(n_seq + 1, dtype=np.int64) * SEQ_LEN).astype(np.int32)
+    return np.ascontiguousarray(ids.reshape(-1)), cu
+
+
+def cpu_encoder_baseline(n_seq: int = 16):
+    """The reference's CPU path for this half: transformers MPNetModel fp32 + the restated
+    sentence-transformers pooling (oracle/encoder_oracle.py) on a bounded sample."""
+    import torch
+    from oracle import encoder_oracle as eo
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = eo.build_model(seed=0)
+    seqs = eo.synthetic_ids(n_seq, [SEQ_LEN], seed=7)
+    eo.st_encode_ids(model, seqs[:2])
+    t0 = time.perf_counter()
+    eo.st_encode_ids(model, seqs, batch_size=16)
+    dt = time.perf_counter() - t0
+    return {"value": n_seq / dt, "unit": "chunks/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n_seq} chunks x {SEQ_LEN} tokens, batch 16, fp32 transformers MPNetModel + ST pooling on the host"}
+
+
+def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 5, warmup: int = 3):
+    from claude_semantic_search_b200 import _native as native
+    from claude_semantic_search_b200.encoder import MPNetEncoder, random_state_dict
+    n_seq = int(getattr(args, "encode_seqs", 256))
+    T = n_seq * SEQ_LEN
+    enc = MPNetEncoder(random_state_dict(0), device=dev.index, max_tokens=T)
+    ids, cu = synthetic_batch(n_seq, seed=7 + rank)
+    ids_d = torch.from_numpy(ids).to(dev)
+    cu_d = torch.from_numpy(cu).to(dev)
+    out_d = torch.empty((n_seq, 768), device=dev, dtype=torch.float32)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+
+    def step(_i):
+        enc.encode_device(ids_d.data_ptr(), cu_d.data_ptr(), cu, out_d.data_ptr(), True, sp)
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize(dev)
+    l0 = native.kernel_launch_count()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = native.kernel_launch_count() - l0
+    if dist is not None:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    chunks_s = n_seq * steps / (ms * 1e-3) * world
+    tf = chunks_s / world * FLOP_PER_CHUNK / 1e12
+    # e2e: host ids -> host embeddings through css_encoder_encode
+    t0 = time.perf_counter()
+    emb = enc.encode_packed(ids, cu)
+    t_e2e = time.perf_counter() - t0
+    assert np.isfinite(emb).all() and abs(float(np.linalg.norm(emb[0])) - 1) < 1e-3
+    enc.close()
+    res = {"encode": {"chunks_per_s": chunks_s, "ms_per_step": ms / steps, "chunks_per_step_per_gpu": n_seq,
+                      "seq_len": SEQ_LEN, "achieved_tflops_per_gpu": tf,
+                      "frac_of_bf16_peak": tf / pk["bf16_tflops_sustained"], "peak": pk["bf16_tflops_sustained"],
+                      "peak_kind": "sustained bf16 (MEASURED_PEAKS.json)", "flop_per_chunk": FLOP_PER_CHUNK,
+                      "gpu_launches": int(launches),
+                      "e2e_chunks_per_s": n_seq / t_e2e * world, "h2d_bytes_per_step": int(ids.nbytes + cu.nbytes),
+                      "d2h_bytes_per_step": int(emb.nbytes)}}
+    if rank == 0 and not getattr(args, "no_cpu", False):
+        res["encode"]["cpu_baseline"] = cpu_encoder_baseline()
+    return res

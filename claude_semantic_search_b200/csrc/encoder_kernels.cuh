@@ -337,6 +337,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + er
 // out_bf16[m, n] = gelu(acc + bias[n])      (FFN up-projection)
 template <bool kGelu>
 struct EpiBiasBf16 {
+  static constexpr bool kMasksColumns = false;
   struct Params {
     __nv_bfloat16* out;
     const float* bias;
@@ -373,6 +374,7 @@ struct EpiBiasBf16 {
 // out_f32[m, n] = acc + bias[n] + resid_bf16[m, n]   (attention output / FFN down projections;
 // the LayerNorm kernel consumes out_f32)
 struct EpiBiasResidF32 {
+  static constexpr bool kMasksColumns = false;
   struct Params {
     float* out;
     const float* bias;

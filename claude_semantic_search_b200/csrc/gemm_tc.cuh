@@ -82,7 +82,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
 
   const int num_m = (shape.M + BM - 1) / BM;
-  const int num_n = shape.N / BN;
+  const int num_n = (shape.N + BN - 1) / BN;  // a ragged last block is zero-filled by TMA; Epi masks it
   const int num_tiles = num_m * num_n;
   const int num_kb = shape.K / BK;
 
@@ -196,18 +196,20 @@ template <int BN, class Epi>
 int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int m_fastest,
            const typename Epi::Params& ep, int n_sm, cudaStream_t st) {
   using C = Cfg<BN>;
-  CSS_REQUIRE(M >= 1 && N % BN == 0 && K % BK == 0 && K >= BK, "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M,
-              N, K, BN);
+  CSS_REQUIRE(M >= 1 && N >= 1 && (N % BN == 0 || Epi::kMasksColumns) && K % BK == 0 && K >= BK,
+              "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M, N, K, BN);
   CUtensorMap ta, tb;
   CSS_CHECK(encode_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK));
   CSS_CHECK(encode_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK));
   auto kern = gemm_tc_kernel<BN, Epi>;
-  static bool attr_set = false;  // per instantiation
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
+  int dev = 0;
+  CSS_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load(std::memory_order_relaxed) >> (dev & 63) & 1)) {
     CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_set = true;
+    attr_set.fetch_or(uint64_t(1) << (dev & 63), std::memory_order_relaxed);
   }
-  const int tiles = ((M + BM - 1) / BM) * (N / BN);
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
   Shape shape{M, N, K, m_fastest};
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);

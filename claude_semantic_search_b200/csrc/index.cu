@@ -93,7 +93,7 @@ int append_from_device(css_index* h, const float* src_dev, int64_t n, int normal
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
   const size_t off = (size_t)h->ntotal * h->dim;
   append_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(
-      src_dev, n, h->dim, normalize, h->x + off, h->xb + off);
+      src_dev, n, h->dim, normalize, h->x + off, h->xb + off, h->max_norm_dev);
   CSS_LAUNCHED();
   // new rows are alive
   int64_t w0 = h->ntotal >> 5, w1 = (h->ntotal + n - 1) >> 5;
@@ -299,6 +299,8 @@ int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t*
     p.id_offset = id_offset;
     p.D = D_dev + (size_t)q0 * k;
     p.I = I_dev + (size_t)q0 * k;
+    p.qlist = nullptr;
+    p.qcount = nullptr;
     if (h->metric == CSS_METRIC_INNER_PRODUCT)
       CSS_CHECK((launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, p, nqc, st)));
     else
@@ -338,7 +340,9 @@ int css_index_create(int dim, int metric, int device, css_index** out) {
     delete h;
     return CSS_ERR_CUDA;
   }
-  if (dev_alloc(&h->n_pass_dev, 1) != CSS_OK) {
+  if (dev_alloc(&h->n_pass_dev, 1) != CSS_OK || dev_alloc(&h->max_norm_dev, 1) != CSS_OK ||
+      cudaMemset(h->max_norm_dev, 0, sizeof(float)) != cudaSuccess) {
+    cudaFree(h->n_pass_dev);
     cudaStreamDestroy(h->stream);
     delete h;
     return CSS_ERR_OOM;
@@ -366,6 +370,7 @@ int css_index_destroy(css_index* h) {
     cudaFree(h->set_scratch);
     cudaFree(h->rowmask_scratch);
     cudaFree(h->n_pass_dev);
+    cudaFree(h->max_norm_dev);
     if (h->pinned) cudaFreeHost(h->pinned);
     cudaStreamDestroy(h->stream);
   }
@@ -392,6 +397,7 @@ int css_index_reset(css_index* h) {
   DeviceGuard g(h->device);
   h->ntotal = 0;
   h->any_dead = false;
+  CSS_CUDA(cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream));
   if (h->capacity > 0) {
     CSS_CUDA(cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, h->stream));
     for (int c = 0; c < CSS_MAX_COLUMNS; ++c) {
@@ -754,6 +760,7 @@ int css_index_load(css_index* h, const char* path) {
   if (rc == CSS_OK) {
     h->ntotal = 0;
     h->any_dead = false;
+    cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream);
     h->metric = (cc == fourcc("IxF2")) ? CSS_METRIC_L2 : CSS_METRIC_INNER_PRODUCT;
     if (h->capacity > 0)
       cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, h->stream);

@@ -25,6 +25,7 @@ struct css_index {
   uint32_t* alive = nullptr;
   uint32_t* mask = nullptr;
   bool any_dead = false;
+  float* max_norm_dev = nullptr;     // largest row norm stored (upper bound), 1 float
 
   // scratch (device)
   int scan_blocks = 148;

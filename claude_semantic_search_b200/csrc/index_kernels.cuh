@@ -142,6 +142,8 @@ struct ScanParams {
   int64_t id_offset;
   float* D;              // [nq, k]
   int64_t* I;            // [nq, k]
+  const int* qlist;      // nullable: explicit list of query indices to scan (device)
+  const int* qcount;     // number of entries of qlist (device)
 };
 
 // Dot products (or negated squared distances) of up to 4 rows against the query.
@@ -205,7 +207,7 @@ __device__ __forceinline__ void score_rows(const ScanParams& p, const float4* qr
 // a register top-k, the block merges its 16 warps in shared memory, and the last
 // block to finish (atomic ticket) merges the per-block lists into D/I.
 template <int KPL, int METRIC, bool D768>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
+__device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
   float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
@@ -214,7 +216,6 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int qi = blockIdx.y;
   const float* q = p.q + (int64_t)qi * p.d;
 
   float4 qreg[6];
@@ -341,26 +342,47 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p
   if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
 }
 
+// grid = (blocks, nq) scans query blockIdx.y; with p.qlist set, grid = (blocks, F) and
+// slice y walks the listed queries y, y+F, ... (device-side fallback of the batched path).
+template <int KPL, int METRIC, bool D768>
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
+  if (p.qlist == nullptr) {
+    scan_one_query<KPL, METRIC, D768>(p, blockIdx.y);
+    return;
+  }
+  const int cnt = *p.qcount;
+  for (int slot = blockIdx.y; slot < cnt; slot += gridDim.y) {
+    scan_one_query<KPL, METRIC, D768>(p, p.qlist[slot]);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------
 // S1: append rows.  One warp per row: optional L2 normalisation with the
 // reference's epsilon (x / (||x|| + 1e-8)), fp32 store + bf16 shadow store.
 // ------------------------------------------------------------------------
 static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t n, int d, int normalize,
-                                   float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16) {
+                                   float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16,
+                                   float* __restrict__ max_norm) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* s = src + row * d;
   float denom = 1.f;
-  if (normalize) {
-    float ss = 0.f;
-    for (int j = lane; j < d; j += 32) {
-      float v = s[j];
-      ss = fmaf(v, v, ss);
-    }
-    ss = warp_sum(ss);
-    denom = sqrtf(ss) + 1e-8f;
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    float v = s[j];
+    ss = fmaf(v, v, ss);
   }
+  ss = warp_sum(ss);
+  float nrm = sqrtf(ss);
+  if (normalize) {
+    denom = nrm + 1e-8f;
+    nrm = nrm / denom;
+  }
+  // largest stored row norm: the batched search derives its bf16 error bound from it
+  // (non-negative floats order like their bit patterns)
+  if (lane == 0 && max_norm && nrm == nrm) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm * 1.0001f));
   for (int j = lane; j < d; j += 32) {
     // numpy computes x / (norm + 1e-8); a true division keeps the last bit identical
     float v = normalize ? s[j] / denom : s[j];

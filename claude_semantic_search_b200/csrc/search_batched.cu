@@ -1,15 +1,405 @@
-// search_batched.cu -- batched (nq >= CSS_BATCH_MIN_NQ) exact top-k.
-// Placeholder body until the tcgen05 score-GEMM lands: routes through the
-// streaming scan (still CUDA, still exact), one grid row per query.
+// search_batched.cu -- S3: exact top-k for query batches (nq >= CSS_BATCH_MIN_NQ) on the
+// tensor cores.  Replaces faiss IndexFlatIP.search's sgemm path (src/storage.py:436 with a
+// batch of queries) without materialising the nq x N score matrix.
+//
+//   1. queries -> bf16 A operand; the corpus' bf16 shadow copy (xb) is the B operand.
+//   2. the corpus is swept in passes of geometrically growing size (2K, 8K, 32K ... rows).
+//      Each pass is one tcgen05 GEMM (gemm_tc.cuh) whose epilogue compares every score with
+//      a per-query threshold and appends (score, row) to the query's candidate list.
+//   3. after each pass a small kernel sorts every list, sets the next threshold to
+//      (k-th best bf16 score) - 2*eps_q and drops entries below it.
+//   4. the final kernel re-scores the surviving candidates in fp32 with the arithmetic of the
+//      streaming scan (bit-identical scores to the batch-1 path) and writes the top-k.
+//
+// Exactness.  bf16 rounding of both operands perturbs a score by at most
+//   eps_q = 2^-8 * 1.05 * ||q|| * max_row_norm          (|x.q| <= ||x|| ||q||, u = 2^-9)
+// so every row of the true top-k has a bf16 score >= (true k-th bf16 score) - 2 eps_q, which
+// is never below the running threshold: no true neighbour is ever filtered.  A candidate
+// list that would exceed its capacity flags the query, and flagged queries are re-run by
+// the exact streaming scan (never truncated silently).
 #include "index_internal.h"
+#include "gemm_tc.cuh"
+
+#include <algorithm>
 
 namespace css {
+namespace {
 
-int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
-                   int64_t id_offset, float* D_dev, int64_t* I_dev, cudaStream_t st) {
-  return scan_search(h, q_dev, nq, k, mask_dev, id_offset, D_dev, I_dev, st);
+constexpr int kCap = 4096;          // candidate slots per query
+constexpr int kQChunk = 1024;       // queries per sweep
+constexpr int kFirstPassRows = 2048;
+constexpr int kPassGrowth = 4;
+constexpr int kSelThreads = 512;
+constexpr int kFallbackSlices = 8;
+
+struct Cand {
+  float score;
+  int row;
+};
+
+struct BatchedState {
+  int max_nq = 0;
+  __nv_bfloat16* qb = nullptr;   // [max_nq, dim] bf16 queries
+  float* qnorm = nullptr;        // [max_nq]
+  float* thr = nullptr;          // [max_nq] threshold of the current pass
+  unsigned* count = nullptr;     // [max_nq]
+  Cand* cand = nullptr;          // [max_nq][kCap]
+  int* ovf_flag = nullptr;       // [max_nq] 1 = list overflowed
+  int* ovf_list = nullptr;       // [max_nq] compacted overflowed query indices
+  int* ovf_count = nullptr;      // [1]
+};
+
+// ---- 1. query preparation -------------------------------------------------------------
+__global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, __nv_bfloat16* __restrict__ qb,
+                                    float* __restrict__ qnorm, float* __restrict__ thr, unsigned* __restrict__ count,
+                                    int* __restrict__ ovf_flag, int* __restrict__ ovf_count) {
+  const int lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *ovf_count = 0;
+  if (qi >= nq) return;
+  const float* src = q + (size_t)qi * d;
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    const float v = src[j];
+    ss = fmaf(v, v, ss);
+    qb[(size_t)qi * d + j] = __float2bfloat16_rn(v);
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    qnorm[qi] = sqrtf(ss);
+    thr[qi] = -INFINITY;
+    count[qi] = 0;
+    ovf_flag[qi] = 0;
+  }
 }
 
-void batched_release(css_index* h) { (void)h; }
+// ---- 2. GEMM epilogue: threshold filter -------------------------------------------------
+struct EpiSearch {
+  static constexpr bool kMasksColumns = true;
+  struct Params {
+    const float* thr;       // [nq]
+    unsigned* count;        // [nq]
+    Cand* cand;             // [nq][kCap]
+    int* ovf_flag;          // [nq]
+    const uint32_t* mask;   // nullable row bitmask (global rows)
+    int row0;               // global row of column 0 of this pass
+    int n_rows;             // rows in this pass
+  };
+  const Params& p;
+  __device__ EpiSearch(const Params& p_, int) : p(p_) {}
+  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
+    if (!row_ok) return;
+    const float t = __ldg(p.thr + m);
+    float mx = __uint_as_float(v[0]);
+#pragma unroll
+    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    if (!(mx >= t)) return;
+    // rare path; fully unrolled so v[] stays in registers (no dynamic indexing)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float s = __uint_as_float(v[j]);
+      if (s >= t) offer(m, n0 + j, s);
+    }
+  }
+  __device__ __noinline__ void offer(int m, int r, float s) {
+    if (r >= p.n_rows) return;
+    const int g = p.row0 + r;
+    if (p.mask && !((__ldg(p.mask + (g >> 5)) >> (g & 31)) & 1u)) return;
+    const unsigned pos = atomicAdd(p.count + m, 1u);
+    if (pos < (unsigned)kCap) {
+      Cand c;
+      c.score = s;
+      c.row = g;
+      p.cand[(size_t)m * kCap + pos] = c;
+    } else {
+      p.ovf_flag[m] = 1;
+    }
+  }
+  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void finish() {}
+};
+
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
+  return (a.score > b.score) || (a.score == b.score && a.row < b.row);
+}
+
+__device__ __forceinline__ void sort_cands(Cand* s, int n_sort, int tid) {
+  for (int size = 2; size <= n_sort; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < (n_sort >> 1); t += kSelThreads) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const Cand a = s[lo], b = s[hi];
+        if (cand_better(a, b) != desc) {
+          s[lo] = b;
+          s[hi] = a;
+        }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// ---- 3./4. per-query list maintenance -------------------------------------------------
+// One CTA per query.  kFinal = false: sort, set thr = kth - 2 eps, compact.
+// kFinal = true: additionally re-score the survivors in fp32 and emit D/I.
+struct SelectParams {
+  const float* x;       // fp32 corpus
+  const float* q;       // fp32 queries [nq, d]
+  int d;
+  int k;
+  float eps_scale;      // 2^-8 * 1.05
+  const float* max_norm;
+  const float* qnorm;
+  float* thr;
+  unsigned* count;
+  Cand* cand;
+  int* ovf_flag;
+  int* ovf_list;
+  int* ovf_count;
+  int64_t id_offset;
+  float* D;
+  int64_t* I;
+};
+
+template <bool kFinal>
+__global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
+  __shared__ Cand s[kCap];
+  const int qi = blockIdx.x;
+  const int tid = threadIdx.x;
+  unsigned cnt = p.count[qi];
+  const bool overflow = cnt > (unsigned)kCap || p.ovf_flag[qi] != 0;
+  if (overflow) {
+    // the exact scan re-runs this query; nothing here may be trusted
+    if (kFinal && tid == 0) {
+      const int slot = atomicAdd(p.ovf_count, 1);
+      p.ovf_list[slot] = qi;
+    }
+    if (!kFinal && tid == 0) p.ovf_flag[qi] = 1;
+    return;
+  }
+  int n_sort = 32;
+  while (n_sort < (int)cnt) n_sort <<= 1;
+  Cand* list = p.cand + (size_t)qi * kCap;
+  for (int i = tid; i < n_sort; i += kSelThreads) {
+    Cand c;
+    if (i < (int)cnt) {
+      c = list[i];
+    } else {
+      c.score = -INFINITY;
+      c.row = INT_MAX;
+    }
+    s[i] = c;
+  }
+  sort_cands(s, n_sort, tid);
+  const float eps = p.eps_scale * p.qnorm[qi] * (*p.max_norm);
+  float thr = -INFINITY;
+  if ((int)cnt >= p.k) thr = s[p.k - 1].score - 2.f * eps;
+  // survivors: sorted prefix with score >= thr
+  __shared__ int s_keep;
+  if (tid == 0) s_keep = (int)cnt;
+  __syncthreads();
+  for (int i = tid; i < (int)cnt; i += kSelThreads) {
+    const bool here = s[i].score >= thr;
+    const bool next = (i + 1 < (int)cnt) ? (s[i + 1].score >= thr) : false;
+    if (here && !next) s_keep = i + 1;
+    if (i == 0 && !here) s_keep = 0;
+  }
+  __syncthreads();
+  const int keep = s_keep;
+  if (!kFinal) {
+    for (int i = tid; i < keep; i += kSelThreads) list[i] = s[i];
+    if (tid == 0) {
+      p.count[qi] = (unsigned)keep;
+      p.thr[qi] = thr;
+    }
+    return;
+  }
+  // ---- final: exact fp32 re-score of the survivors (same arithmetic as scan_topk_kernel) ----
+  const int lane = tid & 31, warp = tid >> 5;
+  const float* q = p.q + (size_t)qi * p.d;
+  for (int i = warp; i < keep; i += kSelThreads / 32) {
+    const float* row = p.x + (size_t)s[i].row * p.d;
+    float a = 0.f;
+    if (p.d == 768) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const float4 xv = ld_stream_f4(reinterpret_cast<const float4*>(row) + j * 32 + lane);
+        const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
+        a = fmaf(xv.x, qv.x, a);
+        a = fmaf(xv.y, qv.y, a);
+        a = fmaf(xv.z, qv.z, a);
+        a = fmaf(xv.w, qv.w, a);
+      }
+    } else {
+      for (int j = lane; j < p.d; j += 32) a = fmaf(__ldg(row + j), q[j], a);
+    }
+    a = warp_sum(a);
+    __syncwarp();
+    if (lane == 0) s[i].score = a;
+  }
+  __syncthreads();
+  int n2 = 32;
+  while (n2 < keep) n2 <<= 1;
+  for (int i = keep + tid; i < n2; i += kSelThreads) {
+    s[i].score = -INFINITY;
+    s[i].row = INT_MAX;
+  }
+  sort_cands(s, n2, tid);
+  for (int i = tid; i < p.k; i += kSelThreads) {
+    const bool filled = i < keep && s[i].row != INT_MAX;
+    p.D[(size_t)qi * p.k + i] = filled ? s[i].score : -FLT_MAX;
+    p.I[(size_t)qi * p.k + i] = filled ? (int64_t)s[i].row + p.id_offset : (int64_t)-1;
+  }
+}
+
+int ensure_state(css_index* h, int nq) {
+  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+  if (!st) {
+    st = new (std::nothrow) BatchedState();
+    if (!st) {
+      set_error("out of host memory");
+      return CSS_ERR_OOM;
+    }
+    h->batched = st;
+  }
+  if (nq <= st->max_nq) return CSS_OK;
+  cudaFree(st->qb); cudaFree(st->qnorm); cudaFree(st->thr); cudaFree(st->count); cudaFree(st->cand);
+  cudaFree(st->ovf_flag); cudaFree(st->ovf_list); cudaFree(st->ovf_count);
+  *st = BatchedState();
+  const size_t n = (size_t)nq;
+  auto A = [&](void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+      return (int)CSS_ERR_OOM;
+    }
+    return (int)CSS_OK;
+  };
+  CSS_CHECK(A((void**)&st->qb, n * h->dim * 2));
+  CSS_CHECK(A((void**)&st->qnorm, n * 4));
+  CSS_CHECK(A((void**)&st->thr, n * 4));
+  CSS_CHECK(A((void**)&st->count, n * 4));
+  CSS_CHECK(A((void**)&st->cand, n * kCap * sizeof(Cand)));
+  CSS_CHECK(A((void**)&st->ovf_flag, n * 4));
+  CSS_CHECK(A((void**)&st->ovf_list, n * 4));
+  CSS_CHECK(A((void**)&st->ovf_count, 4));
+  st->max_nq = nq;
+  return CSS_OK;
+}
+
+template <int KPL>
+int launch_fallback(css_index* h, const ScanParams& p, cudaStream_t st) {
+  const bool d768 = (h->dim == 768);
+  size_t smem = sizeof(KeyId) * kMergeCap + (d768 ? 0 : (size_t)h->dim * 4);
+  dim3 grid((unsigned)h->scan_blocks, kFallbackSlices);
+  if (d768) {
+    auto kern = scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, true>;
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanThreads, smem, st>>>(p);
+  } else {
+    auto kern = scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, false>;
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanThreads, smem, st>>>(p);
+  }
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+}  // namespace
+
+int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev, int64_t id_offset,
+                   float* D_dev, int64_t* I_dev, cudaStream_t stream) {
+  CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
+  CSS_REQUIRE(h->dim % gemm::BK == 0, "batched search needs dim %% 64 == 0");
+  CSS_CHECK(ensure_state(h, std::min(nq, kQChunk)));
+  CSS_CHECK(ensure_query_scratch(h, std::min(nq, kQChunk)));
+  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+  const int d = h->dim;
+  const int64_t N = h->ntotal;
+
+  for (int q0 = 0; q0 < nq; q0 += kQChunk) {
+    const int nqc = std::min(kQChunk, nq - q0);
+    const float* qc = q_dev + (size_t)q0 * d;
+    prep_queries_kernel<<<(unsigned)((nqc + 7) / 8), 256, 0, stream>>>(qc, nqc, d, st->qb, st->qnorm, st->thr,
+                                                                       st->count, st->ovf_flag, st->ovf_count);
+    CSS_LAUNCHED();
+    SelectParams sp;
+    sp.x = h->x;
+    sp.q = qc;
+    sp.d = d;
+    sp.k = k;
+    sp.eps_scale = 1.05f / 256.f;
+    sp.max_norm = h->max_norm_dev;
+    sp.qnorm = st->qnorm;
+    sp.thr = st->thr;
+    sp.count = st->count;
+    sp.cand = st->cand;
+    sp.ovf_flag = st->ovf_flag;
+    sp.ovf_list = st->ovf_list;
+    sp.ovf_count = st->ovf_count;
+    sp.id_offset = id_offset;
+    sp.D = D_dev + (size_t)q0 * k;
+    sp.I = I_dev + (size_t)q0 * k;
+
+    int64_t r0 = 0;
+    int64_t pass_rows = kFirstPassRows;
+    while (r0 < N) {
+      int64_t nr = std::min<int64_t>(pass_rows, N - r0);
+      // fold a short tail into this pass
+      if (N - (r0 + nr) < nr / 2) nr = N - r0;
+      EpiSearch::Params ep;
+      ep.thr = st->thr;
+      ep.count = st->count;
+      ep.cand = st->cand;
+      ep.ovf_flag = st->ovf_flag;
+      ep.mask = mask_dev;
+      ep.row0 = (int)r0;
+      ep.n_rows = (int)nr;
+      CSS_CHECK((gemm::launch<256, EpiSearch>(st->qb, d, h->xb + (size_t)r0 * d, d, nqc, (int)nr, d,
+                                             /*m_fastest=*/1, ep, h->n_sm, stream)));
+      r0 += nr;
+      if (r0 < N) {
+        select_kernel<false><<<(unsigned)nqc, kSelThreads, 0, stream>>>(sp);
+        CSS_LAUNCHED();
+      }
+      pass_rows *= kPassGrowth;
+    }
+    select_kernel<true><<<(unsigned)nqc, kSelThreads, 0, stream>>>(sp);
+    CSS_LAUNCHED();
+
+    // overflowed queries (if any): exact streaming scan, driven by the device-side list
+    ScanParams p;
+    p.x = h->x;
+    p.n = N;
+    p.d = d;
+    p.q = qc;
+    p.mask = mask_dev;
+    p.k = k;
+    p.part = h->part;
+    p.ticket = h->ticket;
+    p.id_offset = id_offset;
+    p.D = sp.D;
+    p.I = sp.I;
+    p.qlist = st->ovf_list;
+    p.qcount = st->ovf_count;
+    if (k <= 32) CSS_CHECK(launch_fallback<1>(h, p, stream));
+    else if (k <= 64) CSS_CHECK(launch_fallback<2>(h, p, stream));
+    else CSS_CHECK(launch_fallback<4>(h, p, stream));
+  }
+  return CSS_OK;
+}
+
+void batched_release(css_index* h) {
+  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+  if (!st) return;
+  cudaFree(st->qb); cudaFree(st->qnorm); cudaFree(st->thr); cudaFree(st->count); cudaFree(st->cand);
+  cudaFree(st->ovf_flag); cudaFree(st->ovf_list); cudaFree(st->ovf_count);
+  delete st;
+  h->batched = nullptr;
+}
 
 }  // namespace css

@@ -197,3 +197,35 @@ class MPNetEncoder:
 
 def relative_bucket(rel: int, num_buckets: int = 32, max_distance: int = 128) -> int:
     return int(_native.load().css_mpnet_relative_bucket(int(rel), num_buckets, max_distance))
+
+
+def random_state_dict(seed: int = 0, config: Optional[dict] = None) -> Dict[str, np.ndarray]:
+    """Random-init MPNet weights of the all-mpnet-base-v2 architecture (normal(0, 0.02)
+    linear / embedding weights, zero biases, unit LayerNorm), for synthetic benchmarks
+    where the pretrained checkpoint is unavailable."""
+    cfg = dict(DEFAULT_CONFIG)
+    cfg.update(config or {})
+    rng = np.random.default_rng(seed)
+    H, F = cfg["hidden_size"], cfg["intermediate_size"]
+
+    def w(*shape):
+        return (rng.standard_normal(shape, dtype=np.float32) * 0.02).astype(np.float32)
+
+    sd = {"embeddings.word_embeddings.weight": w(cfg["vocab_size"], H),
+          "embeddings.position_embeddings.weight": w(cfg["max_position_embeddings"], H),
+          "embeddings.LayerNorm.weight": np.ones(H, np.float32), "embeddings.LayerNorm.bias": np.zeros(H, np.float32),
+          "encoder.relative_attention_bias.weight": w(cfg["relative_attention_num_buckets"],
+                                                      cfg["num_attention_heads"])}
+    sd["embeddings.word_embeddings.weight"][cfg["pad_token_id"]] = 0
+    sd["embeddings.position_embeddings.weight"][cfg["pad_token_id"]] = 0
+    shapes = {"q_w": (H, H), "k_w": (H, H), "v_w": (H, H), "o_w": (H, H), "ffn1_w": (F, H), "ffn2_w": (H, F)}
+    for l in range(cfg["num_hidden_layers"]):
+        for field, suffix in _LAYER_NAMES.items():
+            name = f"encoder.layer.{l}.{suffix}"
+            if field in shapes:
+                sd[name] = w(*shapes[field])
+            elif field.startswith("ln") and field.endswith("_w"):
+                sd[name] = np.ones(H, np.float32)
+            else:
+                sd[name] = np.zeros(F if field == "ffn1_b" else H, np.float32)
+    return sd
