@@ -244,24 +244,16 @@ def main():
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
 
+    from claude_semantic_search_b200.sharded import ShardedSearch
+    id_offset = rank * rows
+    sharded = ShardedSearch(idx, id_offset)
     D_loc = torch.empty((1, K), device=dev, dtype=torch.float32)
     I_loc = torch.empty((1, K), device=dev, dtype=torch.int64)
-    if world > 1:
-        D_all = torch.empty((world, 1, K), device=dev, dtype=torch.float32)
-        I_all = torch.empty((world, 1, K), device=dev, dtype=torch.int64)
-        D_out = torch.empty((1, K), device=dev, dtype=torch.float32)
-        I_out = torch.empty((1, K), device=dev, dtype=torch.int64)
-    id_offset = rank * rows
     launches_per_step = 1 if world == 1 else 2
 
     def step(i):
-        q = qs[i % nq_pool]
-        idx.search_device(q.data_ptr(), 1, K, D_loc.data_ptr(), I_loc.data_ptr(), 0, id_offset, sp)
-        if world > 1:
-            dist.all_gather_into_tensor(D_all, D_loc)
-            dist.all_gather_into_tensor(I_all, I_loc)
-            native.topk_merge_device(D_all.data_ptr(), I_all.data_ptr(), world, 1, K, native.METRIC_INNER_PRODUCT,
-                                     D_out.data_ptr(), I_out.data_ptr(), sp)
+        # local scan (+ for N > 1: all-gather of the k x 12 B lists and merge kernel)
+        sharded.search_device(qs[i % nq_pool:i % nq_pool + 1], K)
 
     for i in range(args.warmup):
         step(i)
@@ -290,16 +282,8 @@ def main():
     qh = qs_host.numpy()
 
     def e2e_step(i):
-        Dh, Ih = idx.search(qh[i % nq_pool:i % nq_pool + 1], K)
-        if world > 1:
-            # host-side exchange of the local lists: tiny (k x 12 B per rank) all_gather + merge
-            Dl = torch.from_numpy(Dh).to(dev, non_blocking=True)
-            Il = torch.from_numpy(Ih + id_offset).to(dev, non_blocking=True)
-            dist.all_gather_into_tensor(D_all, Dl)
-            dist.all_gather_into_tensor(I_all, Il)
-            native.topk_merge_device(D_all.data_ptr(), I_all.data_ptr(), world, 1, K, native.METRIC_INNER_PRODUCT,
-                                     D_out.data_ptr(), I_out.data_ptr(), sp)
-            D_out.cpu()
+        # host query in, host result out; N > 1 adds the gather of the local lists
+        sharded.search_host(qh[i % nq_pool:i % nq_pool + 1], K)
     for i in range(args.warmup):
         e2e_step(i)
     e2e_steps = args.steps

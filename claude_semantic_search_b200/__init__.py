@@ -19,8 +19,7 @@ __all__ = [
     "SearchResult",
 ]
 
-try:  # the encoder half is optional at import time only while it is being built
-    from .embedding_generator import EmbeddingConfig, EmbeddingGenerator, EmbeddingStats  # noqa: F401
-    __all__ += ["EmbeddingGenerator", "EmbeddingConfig", "EmbeddingStats"]
-except ImportError:  # pragma: no cover
-    pass
+from .embedding_generator import EmbeddingConfig, EmbeddingGenerator, EmbeddingStats  # noqa: E402
+from .encoder import MPNetEncoder  # noqa: E402
+
+__all__ += ["EmbeddingGenerator", "EmbeddingConfig", "EmbeddingStats", "MPNetEncoder"]

@@ -1,0 +1,109 @@
+"""Multi-GPU layout of the hot path: one process per GPU,
+`torch.distributed` for the plumbing.
+
+  * search: the corpus is row-sharded contiguously (global id = id_offset + local row),
+    queries are replicated, every rank scans its shard (css_index_search_device), the local
+    top-k lists (k x 12 B per query and rank) are all-gathered and merged on every rank
+    (css_topk_merge_device).  One exchange step, no other collective.
+  * encode: sequences are split contiguously across ranks; no collective (each rank's rows
+    can be appended to its own corpus shard).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import _native
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous split of n items over `world` ranks (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_topk_host(D_all: np.ndarray, I_all: np.ndarray, k: int, metric: int = _native.METRIC_INNER_PRODUCT):
+    """[W, nq, k] lists -> [nq, k]; best first, ties by ascending id, -1 ids are holes.
+    Host restatement of css_topk_merge_device (used on the gloo/CPU path and in tests)."""
+    W, nq, _ = D_all.shape
+    D = np.full((nq, k), -np.finfo(np.float32).max if metric == 0 else np.finfo(np.float32).max, np.float32)
+    I = np.full((nq, k), -1, np.int64)
+    for q in range(nq):
+        d = D_all[:, q, :].reshape(-1)
+        i = I_all[:, q, :].reshape(-1)
+        ok = i >= 0
+        d, i = d[ok], i[ok]
+        key = -d.astype(np.float64) if metric == 0 else d.astype(np.float64)
+        o = np.lexsort((i, key))[:k]
+        D[q, :len(o)] = d[o]
+        I[q, :len(o)] = i[o]
+    return D, I
+
+
+class ShardedSearch:
+    """Exact top-k over a row-sharded corpus; call collectively on every rank."""
+
+    def __init__(self, index: Optional[_native.Index], id_offset: int, group=None,
+                 local_search: Optional[Callable] = None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.index = index
+        self.id_offset = int(id_offset)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local_search = local_search  # CPU/gloo tests inject a host search; None = the device index
+        self._bufs = {}
+
+    def _device_bufs(self, torch, dev, nq, k):
+        key = (nq, k)
+        if key not in self._bufs:
+            self._bufs[key] = dict(
+                D_loc=torch.empty((nq, k), device=dev, dtype=torch.float32),
+                I_loc=torch.empty((nq, k), device=dev, dtype=torch.int64),
+                D_all=torch.empty((self.world, nq, k), device=dev, dtype=torch.float32),
+                I_all=torch.empty((self.world, nq, k), device=dev, dtype=torch.int64),
+                D_out=torch.empty((nq, k), device=dev, dtype=torch.float32),
+                I_out=torch.empty((nq, k), device=dev, dtype=torch.int64))
+        return self._bufs[key]
+
+    def search_device(self, q, k: int, mask_ptr: int = 0):
+        """q: CUDA float32 tensor [nq, d] (replicated).  Returns (D, I) CUDA tensors holding the
+        merged global top-k on every rank.  Runs on torch's current stream."""
+        import torch
+        dev = q.device
+        nq = q.shape[0]
+        b = self._device_bufs(torch, dev, nq, k)
+        sp = torch.cuda.current_stream(dev).cuda_stream
+        self.index.search_device(q.data_ptr(), nq, k, b["D_loc"].data_ptr(), b["I_loc"].data_ptr(), mask_ptr,
+                                 self.id_offset, sp)
+        if self.world == 1:
+            return b["D_loc"], b["I_loc"]
+        self.dist.all_gather_into_tensor(b["D_all"], b["D_loc"], group=self.group)
+        self.dist.all_gather_into_tensor(b["I_all"], b["I_loc"], group=self.group)
+        _native.topk_merge_device(b["D_all"].data_ptr(), b["I_all"].data_ptr(), self.world, nq, k, self.index.metric,
+                                  b["D_out"].data_ptr(), b["I_out"].data_ptr(), sp)
+        return b["D_out"], b["I_out"]
+
+    def search_host(self, q: np.ndarray, k: int):
+        """Host buffers in and out (gloo or NCCL group): local search, gather, host merge."""
+        import torch
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, q.shape[-1])
+        if self.local_search is not None:
+            D, I = self.local_search(q, k)
+            I = np.where(I >= 0, I + self.id_offset, -1)
+        else:
+            D, I = self.index.search(q, k)
+            I = np.where(I >= 0, I + self.id_offset, -1)
+        if self.world == 1:
+            return D, I
+        backend = self.dist.get_backend(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        Dl = torch.from_numpy(np.ascontiguousarray(D)).to(dev)
+        Il = torch.from_numpy(np.ascontiguousarray(I)).to(dev)
+        Dg = [torch.empty_like(Dl) for _ in range(self.world)]
+        Ig = [torch.empty_like(Il) for _ in range(self.world)]
+        self.dist.all_gather(Dg, Dl, group=self.group)
+        self.dist.all_gather(Ig, Il, group=self.group)
+        return merge_topk_host(torch.stack(Dg).cpu().numpy(), torch.stack(Ig).cpu().numpy(), k)

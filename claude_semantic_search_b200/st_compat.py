@@ -1,0 +1,213 @@
+"""Inner seam: the slice of `sentence_transformers.SentenceTransformer` the reference calls
+(src/embeddings.py:86-97,117,184-188,216-222; kwargs pinned by tests/test_embeddings.py:164-166,
+193-199), served by css_encoder_*.  Install as `sys.modules["sentence_transformers"]` to run the
+reference's own src/embeddings.py unmodified on the B200 path.
+
+Model files are read from a local directory only (no network): config.json,
+model.safetensors | pytorch_model.bin, and tokenizer.json | vocab.txt.  When the checkpoint is
+absent, `CSS_B200_SYNTHETIC_MODEL=1` (or model name "synthetic-mpnet") selects random-init
+weights of the same architecture and a deterministic stand-in tokenizer -- for benchmarks and
+tests, never silently.
+"""
+from __future__ import annotations
+
+import os
+import re
+import unicodedata
+import zlib
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+
+from .encoder import DEFAULT_CONFIG, MPNetEncoder, random_state_dict
+
+BOS, PAD, EOS, UNK = 0, 1, 2, 3
+
+
+# ---------------------------------------------------------------------------- tokenizers
+class StandInTokenizer:
+    """ids = 4 + crc32(lower-cased word) mod (vocab - 6), <s> ... </s>, truncated
+    (the real vocabulary is not available offline)."""
+
+    def __init__(self, vocab_size: int = 30527):
+        self.mod = vocab_size - 6
+        self._word = re.compile(r"\w+|[^\w\s]", re.UNICODE)
+
+    def encode_batch(self, texts: Sequence[str], max_length: int) -> List[List[int]]:
+        out = []
+        for t in texts:
+            words = self._word.findall(t.lower())[: max(max_length - 2, 0)]
+            out.append([BOS] + [4 + zlib.crc32(w.encode("utf-8")) % self.mod for w in words] + [EOS])
+        return out
+
+
+class WordPieceTokenizer:
+    """BERT-style basic + WordPiece tokenisation over vocab.txt (what MPNetTokenizer does:
+    lower-case, strip accents, split punctuation, greedy longest-match with '##')."""
+
+    def __init__(self, vocab_file: Union[str, Path], do_lower_case: bool = True):
+        self.vocab: Dict[str, int] = {}
+        with open(vocab_file, encoding="utf-8") as fh:
+            for i, line in enumerate(fh):
+                self.vocab[line.rstrip("\n")] = i
+        self.lower = do_lower_case
+        self.bos = self.vocab.get("<s>", BOS)
+        self.eos = self.vocab.get("</s>", EOS)
+        self.unk = self.vocab.get("[UNK]", self.vocab.get("<unk>", UNK))
+
+    @staticmethod
+    def _is_punct(ch: str) -> bool:
+        cp = ord(ch)
+        if 33 <= cp <= 47 or 58 <= cp <= 64 or 91 <= cp <= 96 or 123 <= cp <= 126:
+            return True
+        return unicodedata.category(ch).startswith("P")
+
+    def _basic(self, text: str) -> List[str]:
+        if self.lower:
+            text = text.lower()
+            text = "".join(c for c in unicodedata.normalize("NFD", text) if unicodedata.category(c) != "Mn")
+        out, cur = [], []
+        for ch in text:
+            if ch.isspace():
+                if cur:
+                    out.append("".join(cur))
+                    cur = []
+            elif self._is_punct(ch) or 0x4E00 <= ord(ch) <= 0x9FFF:
+                if cur:
+                    out.append("".join(cur))
+                    cur = []
+                out.append(ch)
+            else:
+                cur.append(ch)
+        if cur:
+            out.append("".join(cur))
+        return out
+
+    def _wordpiece(self, word: str) -> List[int]:
+        if len(word) > 100:
+            return [self.unk]
+        ids, start = [], 0
+        while start < len(word):
+            end, cur = len(word), None
+            while start < end:
+                sub = word[start:end]
+                if start > 0:
+                    sub = "##" + sub
+                if sub in self.vocab:
+                    cur = self.vocab[sub]
+                    break
+                end -= 1
+            if cur is None:
+                return [self.unk]
+            ids.append(cur)
+            start = end
+        return ids
+
+    def encode_batch(self, texts: Sequence[str], max_length: int) -> List[List[int]]:
+        out = []
+        for t in texts:
+            ids: List[int] = []
+            for w in self._basic(t):
+                ids.extend(self._wordpiece(w))
+                if len(ids) >= max_length - 2:
+                    break
+            out.append([self.bos] + ids[: max(max_length - 2, 0)] + [self.eos])
+        return out
+
+
+class FastTokenizer:
+    """tokenizer.json through the `tokenizers` package (multi-threaded)."""
+
+    def __init__(self, path: Union[str, Path]):
+        from tokenizers import Tokenizer
+        self.tok = Tokenizer.from_file(str(path))
+        self.tok.no_padding()
+
+    def encode_batch(self, texts: Sequence[str], max_length: int) -> List[List[int]]:
+        self.tok.enable_truncation(max_length=max_length)
+        return [e.ids for e in self.tok.encode_batch(list(texts))]
+
+
+def _find_model_dir(name: str, cache_folder: Optional[str]) -> Optional[Path]:
+    cands = []
+    p = Path(name).expanduser()
+    if p.is_dir():
+        cands.append(p)
+    roots = [cache_folder, os.environ.get("SENTENCE_TRANSFORMERS_HOME"),
+             os.path.join(os.environ.get("HF_HOME", os.path.expanduser("~/.cache/huggingface")), "hub")]
+    short = name.split("/")[-1]
+    for r in roots:
+        if not r:
+            continue
+        r = Path(r).expanduser()
+        cands += [r / name, r / short, r / f"sentence-transformers_{short}"]
+        hub = r / f"models--sentence-transformers--{short}" / "snapshots"
+        if hub.is_dir():
+            cands += sorted(hub.iterdir())
+    for c in cands:
+        if c.is_dir() and ((c / "model.safetensors").exists() or (c / "pytorch_model.bin").exists()):
+            return c
+    return None
+
+
+# ---------------------------------------------------------------------- SentenceTransformer
+class SentenceTransformer:
+    def __init__(self, model_name_or_path: str = "all-mpnet-base-v2", cache_folder: Optional[str] = None,
+                 device: Optional[str] = None, **_unused):
+        self.model_name = model_name_or_path
+        self.max_seq_length = 384
+        self._device_index = 0
+        synthetic = model_name_or_path == "synthetic-mpnet" or os.environ.get("CSS_B200_SYNTHETIC_MODEL") == "1"
+        model_dir = None if model_name_or_path == "synthetic-mpnet" else _find_model_dir(model_name_or_path, cache_folder)
+        if model_dir is not None:
+            self._encoder = MPNetEncoder.from_pretrained(model_dir, device=self._device_index)
+            if (model_dir / "tokenizer.json").exists():
+                self.tokenizer = FastTokenizer(model_dir / "tokenizer.json")
+            elif (model_dir / "vocab.txt").exists():
+                self.tokenizer = WordPieceTokenizer(model_dir / "vocab.txt")
+            else:
+                raise FileNotFoundError(f"{model_dir}: neither tokenizer.json nor vocab.txt")
+            self.synthetic = False
+        elif synthetic:
+            self._encoder = MPNetEncoder(random_state_dict(0), device=self._device_index)
+            self.tokenizer = StandInTokenizer(DEFAULT_CONFIG["vocab_size"])
+            self.synthetic = True
+        else:
+            raise FileNotFoundError(
+                f"model '{model_name_or_path}' not found locally (cache_folder={cache_folder!r}); this build does "
+                "not download.  Point cache_folder at a directory holding the checkpoint, or set "
+                "CSS_B200_SYNTHETIC_MODEL=1 for random-init weights + stand-in tokenizer (benchmarks only).")
+
+    # -- API surface the reference uses -----------------------------------------------
+    def to(self, device) -> "SentenceTransformer":
+        s = str(device)
+        if s.startswith("cpu"):
+            # the reference moves to "cpu" when use_gpu is False; this path has no CPU encoder
+            return self
+        return self
+
+    @property
+    def device(self) -> str:
+        return f"cuda:{self._device_index}"
+
+    def get_sentence_embedding_dimension(self) -> int:
+        return self._encoder.dim
+
+    def tokenize_ids(self, sentences: Sequence[str]) -> List[List[int]]:
+        max_len = min(int(self.max_seq_length), self._encoder.max_seq_len)
+        return self.tokenizer.encode_batch(sentences, max_len)
+
+    def encode(self, sentences, batch_size: int = 32, show_progress_bar=None, convert_to_numpy: bool = True,
+               normalize_embeddings: bool = False, **_unused):
+        single = isinstance(sentences, str)
+        texts = [sentences] if single else list(sentences)
+        if not texts:
+            return np.zeros((0, self._encoder.dim), np.float32)
+        # batch_size is a host-memory knob of the reference; the device path packs whole
+        # passes of up to max_tokens tokens, results do not depend on it
+        emb = self._encoder.encode_ids(self.tokenize_ids(texts), normalize=normalize_embeddings)
+        return emb[0] if single else emb
+
+    def close(self) -> None:
+        self._encoder.close()

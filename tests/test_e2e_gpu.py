@@ -1,0 +1,89 @@
+"""BASELINE config 1 end to end on the GPU: synthetic Claude-style chunks -> EmbeddingGenerator
+(MPNet on the device, random-init weights + stand-in tokenizer) -> HybridStorage.add_chunks ->
+100 queries top-10, compared with the oracle pipeline (transformers MPNetModel fp32 on the CPU
+with the same weights + the flat-IP / filter oracle)."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+WORDS = ("lorem ipsum dolor sit amet consectetur adipiscing elit sed do eiusmod tempor incididunt ut labore et dolore "
+         "magna aliqua function class return import def async await error trace index vector search kernel stream "
+         "memory cache token query result project session file path config test build deploy").split()
+
+
+def _make_chunks(n, seed=1234):
+    from claude_semantic_search_b200 import Chunk
+    r = random.Random(seed)
+    chunks = []
+    for i in range(n):
+        text = " ".join(r.choice(WORDS) for _ in range(r.randint(8, 160)))
+        has_code = r.random() < 0.4
+        if has_code:
+            text += "\n```python\nprint('x')\n```"
+        chunks.append(Chunk(id=f"chunk_{i:05d}", text=text, metadata=dict(
+            session_id=f"sess-{i % 40}", project_name=r.choice(["/home/u/alpha", "/home/u/Beta-Proj", "/srv/gamma"]),
+            file_path=f"/f/{i % 40}.jsonl", chunk_type=r.choice(["qa_pair", "code_block", "context_segment"]),
+            timestamp=f"2024-{1 + i % 12:02d}-{1 + i % 28:02d}T10:00:00+00:00", has_code=has_code, has_tools=False,
+            message_count=2, char_count=len(text), word_count=len(text.split()))))
+    return chunks
+
+
+def test_config1_pipeline_vs_oracle(tmp_path):
+    import torch
+    from transformers import MPNetConfig, MPNetModel
+
+    from claude_semantic_search_b200 import (EmbeddingConfig, EmbeddingGenerator, HybridStorage, SearchConfig,
+                                             StorageConfig)
+    from claude_semantic_search_b200.encoder import random_state_dict
+    from oracle import encoder_oracle as eo
+    from oracle import search_oracle as so
+
+    n = 320
+    chunks = _make_chunks(n)
+    gen = EmbeddingGenerator(EmbeddingConfig(model_name="synthetic-mpnet", use_gpu=True, show_progress=False))
+    emb = gen.generate_embeddings(chunks)
+    assert emb.shape == (n, 768) and emb.dtype == np.float32
+    assert gen.is_model_loaded and gen.embedding_dimension == 768 and gen.is_using_gpu
+    assert all(isinstance(c.embedding, list) and len(c.embedding) == 768 for c in chunks)
+
+    # oracle encoder with the same weights and the same token ids
+    model = MPNetModel(MPNetConfig(**eo.CONFIG), add_pooling_layer=False).eval()
+    sd = {k: torch.from_numpy(v) for k, v in random_state_dict(0).items()}
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in m for m in missing)
+    ids = gen.model.tokenize_ids([c.text for c in chunks])
+    sub = list(range(0, n, 4))
+    ref = eo.st_encode_ids(model, [ids[i] for i in sub])
+    cos = eo.cosine_rows(ref, emb[sub])
+    assert cos.min() >= 0.9999, f"min cosine {cos.min():.6f}"   # north_star bar
+
+    st = HybridStorage(StorageConfig(data_dir=str(tmp_path), use_gpu=True))
+    st.initialize()
+    st.add_chunks(chunks)
+    assert st.faiss_index.ntotal == n and st.total_chunks == n
+    x = so.normalize_rows(emb)
+    rows = [dict(id=c.id, **{k: (int(v) if isinstance(v, bool) else v) for k, v in c.metadata.items()}) for c in chunks]
+    r = random.Random(5)
+    flt = {"project_name": "beta", "has_code": True}
+    for qi in r.sample(range(n), 25):
+        q = gen.generate_single_embedding(chunks[qi].text[:80])
+        assert q.shape == (768,) and q.dtype == np.float32
+        got = st.search(q, SearchConfig(top_k=10))
+        want = so.storage_search(x, rows, q, top_k=10)
+        assert [g.chunk_id for g in got] == [chunks[i].id for i, _ in want] or \
+            np.allclose([g.similarity for g in got], [s for _, s in want], atol=1e-4)
+        np.testing.assert_allclose([g.similarity for g in got], [s for _, s in want], atol=1e-4)
+        gotf = st.search(q, SearchConfig(top_k=10), filters=flt)
+        wantf = so.prefilter_search(x, rows, q, top_k=10, filters=flt)
+        np.testing.assert_allclose([g.similarity for g in gotf], [s for _, s in wantf], atol=1e-4)
+        assert all("beta" in g.metadata["project_name"].lower() and g.metadata["has_code"] for g in gotf)
+    st.close()
+    # persistence: a new instance sees the same index (reference tests/test_storage.py:541-558)
+    st2 = HybridStorage(StorageConfig(data_dir=str(tmp_path), use_gpu=True))
+    st2.initialize()
+    assert st2.faiss_index.ntotal == n
+    st2.close()
+    gen.model.close()

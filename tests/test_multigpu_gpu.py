@@ -1,0 +1,61 @@
+"""N > 1 on real GPUs: run with >= 2 visible devices (gpurun --gpus 2); with one device the
+2-rank case is skipped (the gloo test covers the host logic)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["CSS_ROOT"])
+from claude_semantic_search_b200 import _native
+from claude_semantic_search_b200.sharded import ShardedSearch, shard_bounds
+from oracle import search_oracle as so
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+torch.cuda.set_stream(torch.cuda.Stream(dev))
+n, d, k = 150_001, 768, 10
+rng = np.random.default_rng(0)
+x = so.normalize_rows(rng.standard_normal((n, d), dtype=np.float32))
+q = so.normalize_rows(rng.standard_normal((40, d), dtype=np.float32))
+x[n - 3] = x[1]; q[0] = x[1]
+lo, hi = shard_bounds(n, world, rank)
+idx = _native.Index(d, device=dev.index)
+idx.add(x[lo:hi])
+ss = ShardedSearch(idx, id_offset=lo)
+qd = torch.from_numpy(q).to(dev)
+D1, I1 = ss.search_device(qd[:3], k)          # streaming scan + gather + merge
+Db, Ib = ss.search_device(qd, k)              # batched path + gather + merge
+torch.cuda.synchronize(dev)
+Dh, Ih = ss.search_host(q[:3], k)
+Dr, Ir = so.flat_search_c(x, q, k)
+for name, (D, I, sl) in {"scan": (D1, I1, slice(0, 3)), "batched": (Db, Ib, slice(0, 40))}.items():
+    ok, why = so.compare_topk(Dr[sl], Ir[sl], D.cpu().numpy(), I.cpu().numpy())
+    assert ok, f"rank {rank} {name}: {why}"
+ok, why = so.compare_topk(Dr[:3], Ir[:3], Dh, Ih)
+assert ok, f"rank {rank} host: {why}"
+assert I1.cpu().numpy()[0][:2].tolist() == [1, n - 3]
+dist.barrier(); dist.destroy_process_group()
+print(f"rank {rank} ok")
+"""
+
+
+def test_sharded_search_two_gpus(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, CSS_ROOT=str(ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "rank 0 ok" in r.stdout and "rank 1 ok" in r.stdout
