@@ -36,7 +36,7 @@ def cpu_encoder_baseline(n_seq: int = 16):
             "sample": f"{n_seq} chunks x {SEQ_LEN} tokens, batch 16, fp32 transformers MPNetModel + ST pooling on the host"}
 
 
-def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 5, warmup: int = 3):
+def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warmup: int = 3):
     from claude_semantic_search_b200 import _native as native
     from claude_semantic_search_b200.encoder import MPNetEncoder, random_state_dict
     n_seq = int(getattr(args, "encode_seqs", 256))
@@ -53,6 +53,10 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 5, warmu
     for i in range(warmup):
         step(i)
     torch.cuda.synchronize(dev)
+    from bench import ClockSampler
+    sampler = ClockSampler(dev.index)
+    if rank == 0:
+        sampler.start()
     l0 = native.kernel_launch_count()
     if dist is not None:
         dist.barrier()
@@ -65,6 +69,7 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 5, warmu
     if dist is not None:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
     launches = native.kernel_launch_count() - l0
     if dist is not None:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -82,7 +87,7 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 5, warmu
                       "seq_len": SEQ_LEN, "achieved_tflops_per_gpu": tf,
                       "frac_of_bf16_peak": tf / pk["bf16_tflops_sustained"], "peak": pk["bf16_tflops_sustained"],
                       "peak_kind": "sustained bf16 (MEASURED_PEAKS.json)", "flop_per_chunk": FLOP_PER_CHUNK,
-                      "gpu_launches": int(launches),
+                      "gpu_launches": int(launches), "clocks": clocks,
                       "e2e_chunks_per_s": n_seq / t_e2e * world, "h2d_bytes_per_step": int(ids.nbytes + cu.nbytes),
                       "d2h_bytes_per_step": int(emb.nbytes)}}
     if rank == 0 and not getattr(args, "no_cpu", False):

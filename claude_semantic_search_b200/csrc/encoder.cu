@@ -124,14 +124,14 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
     const EncLayer& w = e->layers[l];
     {
       EpiBiasBf16<false>::Params p{e->qkv, w.bqkv, 3 * kHidden};
-      CSS_CHECK((gemm::launch<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
+      CSS_CHECK((gemm::run<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
                                                       e->n_sm, st)));
     }
     attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half, e->ctx);
     CSS_LAUNCHED();
     {
       EpiBiasResidF32::Params p{e->pre, w.bo, e->x, kHidden};
-      CSS_CHECK((gemm::launch<256, EpiBiasResidF32>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
+      CSS_CHECK((gemm::run<256, EpiBiasResidF32>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
                                                    e->n_sm, st)));
     }
     layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln1_w, w.ln1_b, c.layer_norm_eps,
@@ -139,12 +139,12 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
     CSS_LAUNCHED();
     {
       EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn};
-      CSS_CHECK((gemm::launch<256, EpiBiasBf16<true>>(e->x1, kHidden, w.w1, kHidden, T, kFfn, kHidden, 0, p, e->n_sm,
+      CSS_CHECK((gemm::run<256, EpiBiasBf16<true>>(e->x1, kHidden, w.w1, kHidden, T, kFfn, kHidden, 0, p, e->n_sm,
                                                      st)));
     }
     {
       EpiBiasResidF32::Params p{e->pre, w.b2, e->x1, kHidden};
-      CSS_CHECK((gemm::launch<256, EpiBiasResidF32>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
+      CSS_CHECK((gemm::run<256, EpiBiasResidF32>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
     }
     layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln2_w, w.ln2_b, c.layer_norm_eps,
                                                                   e->x);
@@ -435,12 +435,17 @@ int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int
   CSS_CHECK(o32.alloc((size_t)M * N * 4));
   CSS_CUDA(cudaMemsetAsync(o16.p, 0xff, (size_t)M * N * 2, st));
   int rc;
-  if (gelu) {
+  // gelu bit 0: GELU epilogue; bits 1-2 force a kernel: 2 = single-CTA, 4 = 2-CTA pair
+  const int force = gelu & 6;
+  const bool two = force == 4 || (force == 0 && gemm::use_2cta());
+  if (gelu & 1) {
     EpiBiasBf16<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
-    rc = gemm::launch<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+    rc = two ? gemm::launch2<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
+             : gemm::launch<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
   } else {
     EpiBiasBf16<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
-    rc = gemm::launch<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+    rc = two ? gemm::launch2<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
+             : gemm::launch<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
   }
   CSS_CHECK(rc);
   const int64_t n = (int64_t)M * N;

@@ -333,22 +333,28 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restric
 // ------------------------------------------------------------------------
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// Both functors stage the warp's 32 x 32 block through shared memory so that global
+// stores are row-contiguous full sectors (round-1 profile: per-thread row stores cost 32
+// half-written sectors per request and doubled the L2 write traffic).
+//
 // out_bf16[m, n] = acc + bias[n]            (QKV projection)
 // out_bf16[m, n] = gelu(acc + bias[n])      (FFN up-projection)
 template <bool kGelu>
 struct EpiBiasBf16 {
   static constexpr bool kMasksColumns = false;
+  static constexpr int kRowBytes = 80;                 // 64 B of payload + 16 B pad: conflict-free
+  static constexpr int kStageBytes = 32 * kRowBytes;   // per epilogue warp
   struct Params {
     __nv_bfloat16* out;
     const float* bias;
     int ldo;
   };
   const Params& p;
-  __device__ EpiBiasBf16(const Params& p_, int) : p(p_) {}
-  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
-    if (!row_ok) return;
-    uint4* dst = reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + n0);
+  uint8_t* stage;
+  __device__ EpiBiasBf16(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
+  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+    uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
@@ -364,8 +370,21 @@ struct EpiBiasBf16 {
       uint4 o;
       o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
       o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-      dst[g] = o;
+      srow[g] = o;
     }
+    __syncwarp();
+    // 4 lanes per row (4 x 16 B = the row's 64 B), 8 rows per instruction
+    const int piece = lane & 3;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      const int m = m_warp + r;
+      if (m < M) {
+        const uint4 o = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + piece * 16);
+        *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + n0 + piece * 8) = o;
+      }
+    }
+    __syncwarp();
   }
   __device__ __forceinline__ void tile_end(int, int) {}
   __device__ __forceinline__ void finish() {}
@@ -375,6 +394,8 @@ struct EpiBiasBf16 {
 // the LayerNorm kernel consumes out_f32)
 struct EpiBiasResidF32 {
   static constexpr bool kMasksColumns = false;
+  static constexpr int kRowBytes = 144;                // 128 B of payload + 16 B pad
+  static constexpr int kStageBytes = 32 * kRowBytes;
   struct Params {
     float* out;
     const float* bias;
@@ -382,28 +403,38 @@ struct EpiBiasResidF32 {
     int ld;  // leading dimension of out and resid
   };
   const Params& p;
-  __device__ EpiBiasResidF32(const Params& p_, int) : p(p_) {}
-  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
-    if (!row_ok) return;
-    float4* dst = reinterpret_cast<float4*>(p.out + (size_t)m * p.ld + n0);
-    const uint4* r4 = reinterpret_cast<const uint4*>(p.resid + (size_t)m * p.ld + n0);
+  uint8_t* stage;
+  __device__ EpiBiasResidF32(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
+  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+    float4* srow = reinterpret_cast<float4*>(stage + lane * kRowBytes);
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      const uint4 r = __ldg(r4 + g);
-      const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
-      float4 o0, o1;
-      o0.x = __uint_as_float(v[g * 8 + 0]) + ba.x + bf16_lo(r.x);
-      o0.y = __uint_as_float(v[g * 8 + 1]) + ba.y + bf16_hi(r.x);
-      o0.z = __uint_as_float(v[g * 8 + 2]) + ba.z + bf16_lo(r.y);
-      o0.w = __uint_as_float(v[g * 8 + 3]) + ba.w + bf16_hi(r.y);
-      o1.x = __uint_as_float(v[g * 8 + 4]) + bb.x + bf16_lo(r.z);
-      o1.y = __uint_as_float(v[g * 8 + 5]) + bb.y + bf16_hi(r.z);
-      o1.z = __uint_as_float(v[g * 8 + 6]) + bb.z + bf16_lo(r.w);
-      o1.w = __uint_as_float(v[g * 8 + 7]) + bb.w + bf16_hi(r.w);
-      dst[g * 2] = o0;
-      dst[g * 2 + 1] = o1;
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = __ldg(b4 + g);
+      float4 o;
+      o.x = __uint_as_float(v[g * 4 + 0]) + b.x;
+      o.y = __uint_as_float(v[g * 4 + 1]) + b.y;
+      o.z = __uint_as_float(v[g * 4 + 2]) + b.z;
+      o.w = __uint_as_float(v[g * 4 + 3]) + b.w;
+      srow[g] = o;
     }
+    __syncwarp();
+    // 8 lanes per row (8 x 16 B out, 8 x 8 B residual in), 4 rows per instruction
+    const int piece = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3);
+      const int m = m_warp + r;
+      if (m < M) {
+        const size_t g = (size_t)m * p.ld + n0 + piece * 4;
+        const uint2 rr = __ldg(reinterpret_cast<const uint2*>(p.resid + g));
+        float4 o = *reinterpret_cast<const float4*>(stage + r * kRowBytes + piece * 16);
+        o.x += bf16_lo(rr.x); o.y += bf16_hi(rr.x);
+        o.z += bf16_lo(rr.y); o.w += bf16_hi(rr.y);
+        *reinterpret_cast<float4*>(p.out + g) = o;
+      }
+    }
+    __syncwarp();
   }
   __device__ __forceinline__ void tile_end(int, int) {}
   __device__ __forceinline__ void finish() {}

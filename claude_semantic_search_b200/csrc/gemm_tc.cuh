@@ -12,6 +12,7 @@
 // batched search instantiates a per-query threshold filter (search_batched.cu).
 #pragma once
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace css {
 namespace gemm {
@@ -21,15 +22,20 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = (2 + kEpiWarps) * 32;  // 320
 
-template <int BN>
+constexpr int kSmemBudget = 232448;  // 227 KB: the most one CTA may opt in to
+
+template <int BN, int kEpiStageBytes>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + alignment slack
+  static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;  // per-warp output staging
+  static constexpr int kStagesFit = (kSmemBudget - kBarBytes - 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN;  // 512 (BN=256) or 256 (BN=128)
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
 struct Shape {
@@ -39,20 +45,23 @@ struct Shape {
 
 // Epi concept:
 //   struct Epi { struct Params {...};
-//     __device__ Epi(const Params&, int epi_thread /*0..255*/);
-//     __device__ void chunk(int m /*global row*/, bool row_ok, int n0 /*global col of v[0]*/, const uint32_t (&v)[32]);
+//     static constexpr int kStageBytes;   // shared memory per epilogue warp (output staging), may be 0
+//     __device__ Epi(const Params&, int epi_thread /*0..255*/, uint8_t* warp_stage);
+//     // lane i holds row m_warp + i, columns n0 .. n0+31, of the accumulator
+//     __device__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]);
 //     __device__ void tile_end(int m_blk, int n_blk);
 //     __device__ void finish(); };
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                Shape shape, typename Epi::Params ep) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + C::kStages * C::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* sEpi = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + C::kEpiBytes);
   uint64_t* full = bars;                       // [kStages]  TMA -> MMA
   uint64_t* empty = bars + C::kStages;         // [kStages]  MMA -> TMA
   uint64_t* tfull = bars + 2 * C::kStages;     // [2]        MMA -> epilogue
@@ -75,6 +84,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     tc::fence_barrier_init();
   }
+  __syncwarp();
   if (warp == 1) tc::tmem_alloc(tmem_slot, C::kTmemCols);
   tc::tc_fence_before();
   __syncthreads();
@@ -155,7 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int quarter = warp & 3;     // TMEM lane quarter this warp may read
     const int half = ew >> 2;         // column half of the tile
     const int row_in_tile = quarter * 32 + lane;
-    Epi epi(ep, ew * 32 + lane);
+    Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -163,20 +173,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tile_coords(t, mb, nb);
       tc::mbar_wait(tfull + as, aphase);
       tc::tc_fence_after();
-      const int m = mb * BM + row_in_tile;
-      const bool row_ok = m < shape.M;
+      const int m_warp = mb * BM + quarter * 32;  // first row of this warp's 32 rows
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * BN + half * (BN / 2));
-#pragma unroll 1
-      for (int c = 0; c < BN / 2; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(taddr + c, v);
+      const int n_base = nb * BN + half * (BN / 2);
+      constexpr int kChunks = BN / 2 / 32;
+      uint32_t v[2][32];
+      tc::tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
         tc::tmem_ld_wait();
-        epi.chunk(m, row_ok, nb * BN + half * (BN / 2) + c, v);
+        if (c + 1 < kChunks) {
+          tc::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);  // in flight while chunk c is processed
+        } else {
+          // every TMEM read of this accumulator has landed in registers: hand it back early
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_relaxed(tempty + as);
+        }
+        epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(tempty + as);
       epi.tile_end(mb, nb);
       if (++as == 2) {
         as = 0;
@@ -185,6 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     epi.finish();
   }
+  __syncwarp();  // the single-lane roles rejoin their warps before the block-wide barriers
 
   tc::tc_fence_before();
   __syncthreads();
@@ -195,7 +212,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 template <int BN, class Epi>
 int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int m_fastest,
            const typename Epi::Params& ep, int n_sm, cudaStream_t st) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, Epi::kStageBytes>;
   CSS_REQUIRE(M >= 1 && N >= 1 && (N % BN == 0 || Epi::kMasksColumns) && K % BK == 0 && K >= BK,
               "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M, N, K, BN);
   CUtensorMap ta, tb;
@@ -215,6 +232,240 @@ int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, 
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
   CSS_LAUNCHED();
   return CSS_OK;
+}
+
+
+// =====================================================================================
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 A rows and HALF of the B tile
+// (128 of the 256 N rows), so a pair reads (256 + 256) x K operand rows per 256 x 256
+// outputs -- 1.5x less L2->SM traffic per FLOP than the 128 x 256 single-CTA tile, which is
+// L2-bandwidth bound (round-1 profile).  The leader CTA (cluster rank 0) issues every MMA;
+// its `full` barriers collect the TMA bytes of both CTAs; MMA completion is multicast to
+// the `empty` / `tfull` barriers of both; both CTAs' epilogue warps arrive on the leader's
+// `tempty`.  Accumulators: 128 rows x 256 columns x 2 buffers in each CTA's TMEM.
+// =====================================================================================
+template <int BN, int kEpiStageBytes>
+struct Cfg2 {
+  static_assert(BN == 256, "the 2-CTA kernel is built for 256 x 256 tiles");
+  static constexpr int kABytes = BM * BK * 2;          // 128 rows of A per CTA
+  static constexpr int kBBytes = (BN / 2) * BK * 2;    // 128 of the 256 B rows per CTA
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiStageBytes;
+  static constexpr int kStagesFit = (kSmemBudget - kBarBytes - 1024 - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
+  static constexpr int kTmemCols = 2 * BN;
+  static_assert(kStages >= 4, "pipeline too shallow");
+};
+
+template <int BN, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                Shape shape, typename Epi::Params ep) {
+  using C = Cfg2<BN, Epi::kStageBytes>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + C::kStages * C::kABytes;
+  uint8_t* sEpi = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + C::kEpiBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = tc::cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tmap_a);
+    tc::prefetch_tmap(&tmap_b);
+    for (int s = 0; s < C::kStages; ++s) {
+      tc::mbar_init(full + s, 1);    // leader's own arrive.expect_tx; bytes of both CTAs
+      tc::mbar_init(empty + s, 1);   // one multicast commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      tc::mbar_init(tfull + s, 1);
+      tc::mbar_init(tempty + s, 2 * kEpiWarps);  // epilogue warps of both CTAs
+    }
+    tc::fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tc::tmem_alloc_2sm(tmem_slot, C::kTmemCols);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();  // peer barriers are initialised before anyone signals them
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  constexpr int TM = 2 * BM;  // 256 rows per cluster tile
+  const int num_m = (shape.M + TM - 1) / TM;
+  const int num_n = (shape.N + BN - 1) / BN;
+  const int num_tiles = num_m * num_n;
+  const int num_kb = shape.K / BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  auto tile_coords = [&](int t, int& mb, int& nb) {
+    if (shape.m_fastest) {
+      mb = t % num_m;
+      nb = t / num_m;
+    } else {
+      nb = t % num_n;
+      mb = t / num_n;
+    }
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer (both CTAs) =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int mb, nb;
+        tile_coords(t, mb, nb);
+        const int a_row = mb * TM + (int)cta_rank * BM;
+        const int b_row = nb * BN + (int)cta_rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(empty + stage, phase ^ 1);
+          if (leader) tc::mbar_expect_tx(full + stage, 2 * C::kStageBytes);
+          tc::tma_load_2d_2sm(sA + stage * C::kABytes, &tmap_a, full + stage, kb * BK, a_row, tc::kEvictNormal);
+          tc::tma_load_2d_2sm(sB + stage * C::kBBytes, &tmap_b, full + stage, kb * BK, b_row, tc::kEvictNormal);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ===================== MMA issuer (leader CTA only) =====================
+      constexpr uint32_t idesc = tc::make_idesc_bf16_f32(TM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        tc::mbar_wait(tempty + as, aphase ^ 1);
+        tc::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          tc::mbar_wait(full + stage, phase);
+          tc::tc_fence_after();
+          const uint64_t da = tc::make_kmajor_sw128_desc(tc::smem_u32(sA + stage * C::kABytes));
+          const uint64_t db = tc::make_kmajor_sw128_desc(tc::smem_u32(sB + stage * C::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            tc::umma_bf16_2sm(tmem_d, da + k * tc::kDescKStep, db + k * tc::kDescKStep, idesc, (kb | k) != 0);
+          tc::umma_commit_2sm(empty + stage);
+          if (++stage == C::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc::umma_commit_2sm(tfull + as);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    const int row_in_tile = quarter * 32 + lane;
+    Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int mb, nb;
+      tile_coords(t, mb, nb);
+      tc::mbar_wait(tfull + as, aphase);
+      tc::tc_fence_after();
+      const int m_warp = mb * TM + (int)cta_rank * BM + quarter * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                             static_cast<uint32_t>(as * BN + half * (BN / 2));
+      const int n_base = nb * BN + half * (BN / 2);
+      constexpr int kChunks = BN / 2 / 32;
+      uint32_t v[2][32];
+      tc::tmem_ld_32x32(taddr, v[0]);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        tc::tmem_ld_wait();
+        if (c + 1 < kChunks) {
+          tc::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
+        } else {
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive_leader_relaxed(tempty + as);
+        }
+        epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+      }
+      epi.tile_end(mb, nb);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    epi.finish();
+  }
+  __syncwarp();  // the single-lane roles rejoin their warps before the block-wide barriers
+
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::cluster_sync_all();  // nobody exits (or frees TMEM) while the peer may still signal it
+  if (warp == 1) tc::tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+}
+
+// 1 = use the 2-CTA kernel (default), 0 = single-CTA kernel; CSS_GEMM_2CTA overrides.
+inline bool use_2cta() {
+  static const int v = [] {
+    const char* e = getenv("CSS_GEMM_2CTA");
+    return e ? atoi(e) : 1;
+  }();
+  return v != 0;
+}
+
+template <int BN, class Epi>
+int launch2(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int m_fastest,
+            const typename Epi::Params& ep, int n_sm, cudaStream_t st) {
+  using C = Cfg2<BN, Epi::kStageBytes>;
+  CSS_REQUIRE(M >= 1 && N >= 1 && (N % BN == 0 || Epi::kMasksColumns) && K % BK == 0 && K >= BK,
+              "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M, N, K, BN);
+  CUtensorMap ta, tb;
+  CSS_CHECK(encode_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK));
+  CSS_CHECK(encode_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN / 2, BK));
+  auto kern = gemm_tc2_kernel<BN, Epi>;
+  static std::atomic<uint64_t> attr_set{0};
+  int dev = 0;
+  CSS_CUDA(cudaGetDevice(&dev));
+  if (!(attr_set.load(std::memory_order_relaxed) >> (dev & 63) & 1)) {
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_set.fetch_or(uint64_t(1) << (dev & 63), std::memory_order_relaxed);
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
+  int clusters = n_sm / 2;
+  if (tiles < clusters) clusters = tiles;
+  Shape shape{M, N, K, m_fastest};
+  kern<<<2 * clusters, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+// Dispatch used by the encoder and the batched search.
+template <int BN, class Epi>
+int run(const void* A, int lda, const void* B, int ldb, int M, int N, int K, int m_fastest,
+        const typename Epi::Params& ep, int n_sm, cudaStream_t st) {
+  if (use_2cta()) return launch2<BN, Epi>(A, lda, B, ldb, M, N, K, m_fastest, ep, n_sm, st);
+  return launch<BN, Epi>(A, lda, B, ldb, M, N, K, m_fastest, ep, n_sm, st);
 }
 
 }  // namespace gemm

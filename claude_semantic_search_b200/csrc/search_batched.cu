@@ -76,6 +76,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, 
 // ---- 2. GEMM epilogue: threshold filter -------------------------------------------------
 struct EpiSearch {
   static constexpr bool kMasksColumns = true;
+  static constexpr int kStageBytes = 0;
   struct Params {
     const float* thr;       // [nq]
     unsigned* count;        // [nq]
@@ -86,9 +87,10 @@ struct EpiSearch {
     int n_rows;             // rows in this pass
   };
   const Params& p;
-  __device__ EpiSearch(const Params& p_, int) : p(p_) {}
-  __device__ __forceinline__ void chunk(int m, bool row_ok, int n0, const uint32_t (&v)[32]) {
-    if (!row_ok) return;
+  __device__ EpiSearch(const Params& p_, int, uint8_t*) : p(p_) {}
+  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+    const int m = m_warp + lane;
+    if (m >= M) return;
     const float t = __ldg(p.thr + m);
     float mx = __uint_as_float(v[0]);
 #pragma unroll
@@ -359,7 +361,7 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
       ep.mask = mask_dev;
       ep.row0 = (int)r0;
       ep.n_rows = (int)nr;
-      CSS_CHECK((gemm::launch<256, EpiSearch>(st->qb, d, h->xb + (size_t)r0 * d, d, nqc, (int)nr, d,
+      CSS_CHECK((gemm::run<256, EpiSearch>(st->qb, d, h->xb + (size_t)r0 * d, d, nqc, (int)nr, d,
                                              /*m_fastest=*/1, ep, h->n_sm, stream)));
       r0 += nr;
       if (r0 < N) {

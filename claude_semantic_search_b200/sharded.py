@@ -87,23 +87,26 @@ class ShardedSearch:
         return b["D_out"], b["I_out"]
 
     def search_host(self, q: np.ndarray, k: int):
-        """Host buffers in and out (gloo or NCCL group): local search, gather, host merge."""
+        """Host buffers in and out.  NCCL group: the query goes to the device once, the merged
+        list comes back once.  gloo group (CPU tests): host gather + host merge."""
         import torch
         q = np.ascontiguousarray(q, np.float32).reshape(-1, q.shape[-1])
+        if self.local_search is None and self.world > 1 and self.dist.get_backend(self.group) == "nccl":
+            dev = torch.device("cuda", self.index.device)
+            qd = torch.from_numpy(q).to(dev, non_blocking=True)
+            D, I = self.search_device(qd, k)
+            return D.cpu().numpy(), I.cpu().numpy()
         if self.local_search is not None:
             D, I = self.local_search(q, k)
-            I = np.where(I >= 0, I + self.id_offset, -1)
         else:
             D, I = self.index.search(q, k)
-            I = np.where(I >= 0, I + self.id_offset, -1)
+        I = np.where(I >= 0, I + self.id_offset, -1)
         if self.world == 1:
             return D, I
-        backend = self.dist.get_backend(self.group)
-        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-        Dl = torch.from_numpy(np.ascontiguousarray(D)).to(dev)
-        Il = torch.from_numpy(np.ascontiguousarray(I)).to(dev)
+        Dl = torch.from_numpy(np.ascontiguousarray(D))
+        Il = torch.from_numpy(np.ascontiguousarray(I))
         Dg = [torch.empty_like(Dl) for _ in range(self.world)]
         Ig = [torch.empty_like(Il) for _ in range(self.world)]
         self.dist.all_gather(Dg, Dl, group=self.group)
         self.dist.all_gather(Ig, Il, group=self.group)
-        return merge_topk_host(torch.stack(Dg).cpu().numpy(), torch.stack(Ig).cpu().numpy(), k)
+        return merge_topk_host(torch.stack(Dg).numpy(), torch.stack(Ig).numpy(), k)

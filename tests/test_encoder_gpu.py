@@ -31,14 +31,15 @@ def _bf16(a):
 @pytest.mark.parametrize("M,N,K,gelu", [(128, 256, 64, 0), (128, 256, 768, 0), (1, 256, 128, 0), (130, 768, 768, 0),
                                         (1000, 2304, 768, 0), (333, 3072, 768, 1), (777, 768, 3072, 0),
                                         (40000, 768, 768, 0)])
-def test_tcgen05_gemm_vs_fp32(native, M, N, K, gelu):
+@pytest.mark.parametrize("kernel", [2, 4])   # 2 = single-CTA tiles, 4 = 2-CTA (cta_group::2) tiles
+def test_tcgen05_gemm_vs_fp32(native, M, N, K, gelu, kernel):
     import torch
     rng = np.random.default_rng(M + N + K)
     A = rng.standard_normal((M, K), dtype=np.float32)
     B = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
     bias = rng.standard_normal(N).astype(np.float32)
     out = np.empty((M, N), np.float32)
-    native.check(native.load().css_debug_gemm(A.ctypes.data, B.ctypes.data, bias.ctypes.data, M, N, K, gelu, 0,
+    native.check(native.load().css_debug_gemm(A.ctypes.data, B.ctypes.data, bias.ctypes.data, M, N, K, gelu | kernel, 0,
                                               out.ctypes.data))
     ref = torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(B)).double().T + torch.from_numpy(bias).double()
     if gelu:
