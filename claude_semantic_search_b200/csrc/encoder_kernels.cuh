@@ -159,8 +159,8 @@ static __global__ void pool_normalize_kernel(const __nv_bfloat16* __restrict__ x
 // fp32 accumulate).  scores = q.k / 8 + rel_table[h][j - i]; keys >= L do not exist in
 // the packed layout (the reference masks its padded keys with finfo.min -> weight 0).
 // ------------------------------------------------------------------------
-constexpr int kAttnThreads = 128;
-constexpr int kAttnQRows = 64;
+constexpr int kAttnThreads = 256;
+constexpr int kAttnQRows = 128;
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -182,7 +182,7 @@ __device__ __forceinline__ void cp_async_16(uint32_t saddr, const void* g) {
 
 // smem: K [Lp][64] bf16 (128 B rows, 16-byte chunks XOR-swizzled by row & 7), V likewise,
 // rel [2*Lp] fp32 (rel[d + Lp - 1] = bias of relative position d = j - i).
-static __global__ void __launch_bounds__(kAttnThreads)
+static __global__ void __launch_bounds__(kAttnThreads, 2)
 attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
                  const float* __restrict__ rel_table, int rel_half /* table holds d in [-rel_half, rel_half] */,
                  __nv_bfloat16* __restrict__ ctx) {
@@ -238,6 +238,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restric
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  if (q0 + warp * 16 >= L) return;  // this warp's 16 query rows are all past the sequence end
 
   float o[8][4];
 #pragma unroll
@@ -268,7 +269,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restric
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int j = kb + nt * 8 + (lane & 3) * 2 + (e & 1);
-        const int i = qrow + ((e >> 1) << 3);
+        const int i = min(qrow + ((e >> 1) << 3), L - 1);  // rows >= L are never stored
         float v = sc[nt][e] * 0.125f + sRel[j - i + Lp - 1];
         v = (j < L) ? v : -INFINITY;
         sc[nt][e] = v;
@@ -331,7 +332,24 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restric
 // ------------------------------------------------------------------------
 // GEMM epilogue functors (see gemm_tc.cuh for the concept).
 // ------------------------------------------------------------------------
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// GELU with the exact-erf definition (transformers ACT2FN["gelu"]).  erf through Abramowitz &
+// Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the result): two MUFU
+// (rcp, ex2) + ~10 FMA instead of the ~27-instruction erff() -- the FFN up-projection
+// epilogue was ALU-bound on erff in the round-1 profile.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+  const float erf_abs = fmaf(-p, e, 1.f);          // erf(|x| / sqrt 2)
+  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;     // 0.5 x (1 + sign(x) erf_abs)
+}
 
 // Both functors stage the warp's 32 x 32 block through shared memory so that global
 // stores are row-contiguous full sectors (round-1 profile: per-thread row stores cost 32
@@ -386,6 +404,8 @@ struct EpiBiasBf16 {
     }
     __syncwarp();
   }
+  __device__ __forceinline__ void chunk_begin() {}
+  __device__ __forceinline__ void prefetch(int, int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int) {}
   __device__ __forceinline__ void finish() {}
 };
@@ -405,7 +425,25 @@ struct EpiBiasResidF32 {
   const Params& p;
   uint8_t* stage;
   __device__ EpiBiasResidF32(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
+  // Residual rows of the NEXT chunk are requested one chunk ahead (and across tiles, during
+  // the wait for the next accumulator): a DRAM round trip per chunk sat on the critical path
+  // of every tile in the round-1 profile (long-scoreboard stalls on the bf16 unpack).
+  uint2 rr_next[8], rr[8];
+  __device__ __forceinline__ void chunk_begin() {
+#pragma unroll
+    for (int it = 0; it < 8; ++it) rr[it] = rr_next[it];
+  }
+  __device__ __forceinline__ void prefetch(int m_warp, int lane, int M, int n0) {
+    const int piece = lane & 7;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = m_warp + it * 4 + (lane >> 3);
+      rr_next[it] = make_uint2(0u, 0u);
+      if (m < M) rr_next[it] = __ldg(reinterpret_cast<const uint2*>(p.resid + (size_t)m * p.ld + n0 + piece * 4));
+    }
+  }
   __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+    const int piece = lane & 7;
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     float4* srow = reinterpret_cast<float4*>(stage + lane * kRowBytes);
 #pragma unroll
@@ -420,18 +458,15 @@ struct EpiBiasResidF32 {
     }
     __syncwarp();
     // 8 lanes per row (8 x 16 B out, 8 x 8 B residual in), 4 rows per instruction
-    const int piece = lane & 7;
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = it * 4 + (lane >> 3);
       const int m = m_warp + r;
       if (m < M) {
-        const size_t g = (size_t)m * p.ld + n0 + piece * 4;
-        const uint2 rr = __ldg(reinterpret_cast<const uint2*>(p.resid + g));
         float4 o = *reinterpret_cast<const float4*>(stage + r * kRowBytes + piece * 16);
-        o.x += bf16_lo(rr.x); o.y += bf16_hi(rr.x);
-        o.z += bf16_lo(rr.y); o.w += bf16_hi(rr.y);
-        *reinterpret_cast<float4*>(p.out + g) = o;
+        o.x += bf16_lo(rr[it].x); o.y += bf16_hi(rr[it].x);
+        o.z += bf16_lo(rr[it].y); o.w += bf16_hi(rr[it].y);
+        *reinterpret_cast<float4*>(p.out + (size_t)m * p.ld + n0 + piece * 4) = o;
       }
     }
     __syncwarp();

@@ -49,6 +49,11 @@ struct Shape {
 //     __device__ Epi(const Params&, int epi_thread /*0..255*/, uint8_t* warp_stage);
 //     // lane i holds row m_warp + i, columns n0 .. n0+31, of the accumulator
 //     __device__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]);
+//     // prefetch(next) is called one chunk ahead (and across tiles) to start loading whatever
+//     // chunk(next) will need; chunk_begin() runs first so the current chunk can take over
+//     // what the previous prefetch fetched for it
+//     __device__ void chunk_begin();
+//     __device__ void prefetch(int m_warp, int lane, int M, int n0);
 //     __device__ void tile_end(int m_blk, int n_blk);
 //     __device__ void finish(); };
 template <int BN, class Epi>
@@ -168,9 +173,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
+    if (blockIdx.x < num_tiles) {  // operands of the very first chunk (e.g. residual rows) start loading now
+      int mb0, nb0;
+      tile_coords(blockIdx.x, mb0, nb0);
+      epi.prefetch(mb0 * BM + quarter * 32, lane, shape.M, nb0 * BN + half * (BN / 2));
+    }
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       int mb, nb;
       tile_coords(t, mb, nb);
+      // first chunk of the next tile of this CTA (prefetched during the last chunk of this one)
+      int nmb = 0, nnb = 0;
+      const bool has_next_tile = t + (int)gridDim.x < num_tiles;
+      if (has_next_tile) tile_coords(t + gridDim.x, nmb, nnb);
+      const int next_m_warp = nmb * BM + quarter * 32;
+      const int next_n_base = nnb * BN + half * (BN / 2);
       tc::mbar_wait(tfull + as, aphase);
       tc::tc_fence_after();
       const int m_warp = mb * BM + quarter * 32;  // first row of this warp's 32 rows
@@ -191,6 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_relaxed(tempty + as);
         }
+        epi.chunk_begin();
+        if (c + 1 < kChunks) epi.prefetch(m_warp, lane, shape.M, n_base + (c + 1) * 32);
+        else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
         epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
       }
       epi.tile_end(mb, nb);
@@ -385,12 +404,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
+    const int row_off = (int)cta_rank * BM + quarter * 32;
+    if (cluster_id < num_tiles) {
+      int mb0, nb0;
+      tile_coords(cluster_id, mb0, nb0);
+      epi.prefetch(mb0 * TM + row_off, lane, shape.M, nb0 * BN + half * (BN / 2));
+    }
     for (int t = cluster_id; t < num_tiles; t += num_clusters) {
       int mb, nb;
       tile_coords(t, mb, nb);
+      int nmb = 0, nnb = 0;
+      const bool has_next_tile = t + num_clusters < num_tiles;
+      if (has_next_tile) tile_coords(t + num_clusters, nmb, nnb);
+      const int next_m_warp = nmb * TM + row_off;
+      const int next_n_base = nnb * BN + half * (BN / 2);
       tc::mbar_wait(tfull + as, aphase);
       tc::tc_fence_after();
-      const int m_warp = mb * TM + (int)cta_rank * BM + quarter * 32;
+      const int m_warp = mb * TM + row_off;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
                              static_cast<uint32_t>(as * BN + half * (BN / 2));
       const int n_base = nb * BN + half * (BN / 2);
@@ -407,6 +437,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_leader_relaxed(tempty + as);
         }
+        epi.chunk_begin();
+        if (c + 1 < kChunks) epi.prefetch(m_warp, lane, shape.M, n_base + (c + 1) * 32);
+        else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
         epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
       }
       epi.tile_end(mb, nb);

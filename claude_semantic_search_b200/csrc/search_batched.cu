@@ -117,6 +117,8 @@ struct EpiSearch {
       p.ovf_flag[m] = 1;
     }
   }
+  __device__ __forceinline__ void chunk_begin() {}
+  __device__ __forceinline__ void prefetch(int, int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int) {}
   __device__ __forceinline__ void finish() {}
 };
