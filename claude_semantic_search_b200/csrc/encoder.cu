@@ -12,6 +12,7 @@
 //     E5  LayerNorm(pre)                       -> x    bf16 [T, 768]
 //   E7  mean over tokens, L2 normalise         -> out  f32  [n_seq, 768]
 #include "encoder_kernels.cuh"
+#include "attention_tc.cuh"
 #include "gemm_tc.cuh"
 
 #include <algorithm>
@@ -37,6 +38,7 @@ struct css_encoder {
   // weights
   float *word_emb = nullptr, *pos_emb = nullptr, *emb_ln_w = nullptr, *emb_ln_b = nullptr;
   float* rel_table = nullptr;  // [heads][2*rel_half+1]
+  float* rel_max = nullptr;    // [heads] max of each head's table (softmax upper bound)
   int rel_half = 0;
   std::vector<EncLayer> layers;
   std::vector<void*> owned;  // every device allocation, freed on destroy
@@ -119,6 +121,9 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   const size_t attn_smem = (size_t)Lp * 256 + (size_t)2 * Lp * sizeof(float);
   CSS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem));
   const dim3 attn_grid((unsigned)((max_len + kAttnQRows - 1) / kAttnQRows), kHeads, (unsigned)n_seq);
+  // tcgen05 attention (CSS_ATTN_TC=0 selects the mma.sync kernel); longer sequences always take mma.sync
+  static const bool attn_tc_env = [] { const char* v = getenv("CSS_ATTN_TC"); return v ? atoi(v) != 0 : true; }();
+  const bool attn_tc = attn_tc_env && max_len <= kAttnTcMaxLen;
 
   for (int l = 0; l < c.num_layers; ++l) {
     const EncLayer& w = e->layers[l];
@@ -127,8 +132,13 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       CSS_CHECK((gemm::run<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
                                                       e->n_sm, st)));
     }
-    attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half, e->ctx);
-    CSS_LAUNCHED();
+    if (attn_tc) {
+      CSS_CHECK(attention_tc_launch(e->qkv, T, cu_dev, n_seq, max_len, e->rel_table, e->rel_max, e->rel_half, e->ctx,
+                                    e->n_sm, st));
+    } else {
+      attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half, e->ctx);
+      CSS_LAUNCHED();
+    }
     {
       EpiBiasResidF32::Params p{e->pre, w.bo, e->x, kHidden};
       CSS_CHECK((gemm::run<256, EpiBiasResidF32>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
@@ -249,6 +259,14 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
     for (int d = -e->rel_half; d <= e->rel_half; ++d) {
       const int b = css_mpnet_relative_bucket(d, cfg->rel_buckets, cfg->rel_max_distance);
       for (int hh = 0; hh < kHeads; ++hh) table[(size_t)hh * width + d + e->rel_half] = w->rel_bias[(size_t)b * kHeads + hh];
+    }
+    std::vector<float> tmax(kHeads, -INFINITY);
+    for (int hh = 0; hh < kHeads; ++hh)
+      for (int d = 0; d < width; ++d) tmax[hh] = std::max(tmax[hh], table[(size_t)hh * width + d]);
+    if ((rc = enc_alloc(e, &e->rel_max, (size_t)kHeads)) != CSS_OK) return fail(rc);
+    if (cudaMemcpy(e->rel_max, tmax.data(), kHeads * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("rel_max upload failed");
+      return fail(CSS_ERR_CUDA);
     }
     if ((rc = enc_alloc(e, &e->rel_table, table.size())) != CSS_OK) return fail(rc);
     if (cudaMemcpy(e->rel_table, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -479,9 +497,23 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
   const size_t smem = (size_t)Lp * 256 + (size_t)2 * Lp * sizeof(float);
   CSS_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((max_len + kAttnQRows - 1) / kAttnQRows), kHeads, (unsigned)n_seq);
-  attention_kernel<<<grid, kAttnThreads, smem, st>>>((const __nv_bfloat16*)q16.p, (const int32_t*)cud.p,
-                                                     (const float*)reld.p, rel_half, (__nv_bfloat16*)c16.p);
-  CSS_LAUNCHED();
+  const char* tc_env = getenv("CSS_ATTN_TC");
+  if ((tc_env ? atoi(tc_env) != 0 : true) && max_len <= kAttnTcMaxLen) {
+    std::vector<float> tmax(kHeads, -INFINITY);
+    for (int hh = 0; hh < kHeads; ++hh)
+      for (int d = 0; d < 2 * rel_half + 1; ++d) tmax[hh] = std::max(tmax[hh], rel_table[(size_t)hh * (2 * rel_half + 1) + d]);
+    DevBuf maxd;
+    CSS_CHECK(maxd.alloc(kHeads * 4));
+    CSS_CUDA(cudaMemcpy(maxd.p, tmax.data(), kHeads * 4, cudaMemcpyHostToDevice));
+    CSS_CHECK(attention_tc_launch((const __nv_bfloat16*)q16.p, T, (const int32_t*)cud.p, n_seq, max_len,
+                                  (const float*)reld.p, (const float*)maxd.p, rel_half, (__nv_bfloat16*)c16.p,
+                                  sm_count(device), st));
+    CSS_CUDA(cudaStreamSynchronize(st));
+  } else {
+    attention_kernel<<<grid, kAttnThreads, smem, st>>>((const __nv_bfloat16*)q16.p, (const int32_t*)cud.p,
+                                                       (const float*)reld.p, rel_half, (__nv_bfloat16*)c16.p);
+    CSS_LAUNCHED();
+  }
   const int64_t n = (int64_t)T * kHidden;
   bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)c16.p, (float*)c32.p, n);
   CSS_LAUNCHED();

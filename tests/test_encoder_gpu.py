@@ -52,9 +52,11 @@ def test_tcgen05_gemm_vs_fp32(native, M, N, K, gelu, kernel):
 
 
 # ------------------------------------------------------------- attention
-@pytest.mark.parametrize("lens", [[1], [2, 3], [64], [65, 63], [128, 5, 200], [384], [512, 17]])
-def test_attention_vs_fp32(native, lens):
+@pytest.mark.parametrize("tc", ["1", "0"])   # tcgen05 kernel / mma.sync kernel
+@pytest.mark.parametrize("lens", [[1], [2, 3], [64], [65, 63], [128, 5, 200], [384], [129, 448, 300], [512, 17]])
+def test_attention_vs_fp32(native, lens, tc, monkeypatch):
     import torch
+    monkeypatch.setenv("CSS_ATTN_TC", tc)
     rng = np.random.default_rng(sum(lens))
     T = sum(lens)
     cu = np.zeros(len(lens) + 1, np.int32)
