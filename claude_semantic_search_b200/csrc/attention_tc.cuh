@@ -5,7 +5,8 @@
 //               packed qkv activation [T, 2304] (128-byte swizzle)
 //   warp 1      MMA issuer:   S = Q K^T   (tcgen05.mma M128 x N<=256 x K16, fp32 in TMEM cols [0, Lp))
 //                             O = P V     (M128 x N64, V is the MN-major B operand, TMEM cols [448, 512))
-//   warps 2-5   softmax + epilogue, one query row per thread (= one TMEM lane):
+//   warps 2-9   softmax + epilogue: two groups of 4 warps, one query row per thread in each group
+//               (= one TMEM lane); group 0 owns the even 64-key blocks, group 1 the odd ones:
 //               pass 1  row maximum of the raw scores           (tcgen05.ld)
 //               pass 2  p = exp2(s*c + rel[j-i] - m), 64 keys at a time, written as the bf16 A operand of
 //                       the PV product into a double-buffered shared tile -> the PV MMAs of block b run
@@ -22,12 +23,15 @@ namespace css {
 namespace enc {
 
 constexpr int kAttnTcMaxLen = 448;                 // S occupies TMEM columns [0, Lp), O [448, 512)
-constexpr int kAttnTcThreads = 192;                // 6 warps
+constexpr int kAttnTcThreads = 320;                // 10 warps: TMA, MMA, 2 x 4 softmax
 constexpr int kAtQ = 128 * 128;                    // Q tile bytes
 constexpr int kAtKV = kAttnTcMaxLen * 128;         // K / V tile bytes (max)
 constexpr int kAtP = 128 * 128;                    // one P block (128 rows x 64 keys bf16)
-constexpr int kAtRel = 2 * kAttnTcMaxLen * 4;
-constexpr int kAtSmem = kAtQ + 2 * kAtKV + 2 * kAtP + kAtRel + 256 + 1024;
+constexpr int kAtRelStride = 2 * kAttnTcMaxLen;     // floats per head: bias(d) * log2e for d in [-447, 448)
+constexpr int kAtRel = kHeads * kAtRelStride * 4;  // every head's window, staged once per CTA
+constexpr int kAtCuMax = 1024;                     // cu_seqlens entries cached in shared memory
+constexpr int kAtXch = 4 * 128 * 4;                // per-row partial max / sum of the two softmax groups
+constexpr int kAtSmem = kAtQ + 2 * kAtKV + 2 * kAtP + kAtRel + kAtXch + (kAtCuMax + 1) * 4 + 256 + 1024;
 constexpr uint32_t kOCol = 448;
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -67,7 +71,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sV = sK + kAtKV;
   uint8_t* sP = sV + kAtKV;                       // 2 blocks
   float* sRel = reinterpret_cast<float*>(sP + 2 * kAtP);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRel) + kAtRel);
+  float* sXch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sRel) + kAtRel);   // [2][128] max, [2][128] sum
+  int32_t* sCu = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(sXch) + kAtXch);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sCu) + ((kAtCuMax + 1) * 4 + 7) / 8 * 8);
   uint64_t* qk_full = bars + 0;
   uint64_t* qk_empty = bars + 1;
   uint64_t* v_full = bars + 2;
@@ -77,7 +83,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint64_t* o_full = bars + 6;
   uint64_t* p_full = bars + 7;    // [2]
   uint64_t* p_empty = bars + 9;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* o_free = bars + 11;   // all 8 softmax warps have read O of the previous item
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -88,8 +95,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc::mbar_init(v_full, 1);
     tc::mbar_init(v_empty, 1);
     tc::mbar_init(s_full, 1);
-    tc::mbar_init(s_free, 4);
+    tc::mbar_init(s_free, 8);
     tc::mbar_init(o_full, 1);
+    tc::mbar_init(o_free, 8);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(p_full + i, 128);
       tc::mbar_init(p_empty + i, 1);
@@ -98,6 +106,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   __syncwarp();
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
+  // per-CTA constants: every head's bias window (x log2e) and the sequence offsets, so that no
+  // item starts with a chain of dependent global loads (round-1 profile: ~2K cycles per item)
+  for (int x = threadIdx.x; x < kHeads * kAtRelStride; x += kAttnTcThreads) {
+    const int hh = x / kAtRelStride, d = x % kAtRelStride - (kAttnTcMaxLen - 1);
+    const int dc = max(-p.rel_half, min(p.rel_half, d));
+    sRel[x] = p.rel_table[(size_t)hh * (2 * p.rel_half + 1) + p.rel_half + dc] * 1.4426950408889634f;
+  }
+  const bool cu_in_smem = p.n_seq <= kAtCuMax;
+  if (cu_in_smem)
+    for (int x = threadIdx.x; x <= p.n_seq; x += kAttnTcThreads) sCu[x] = p.cu[x];
+  const int32_t* cu = cu_in_smem ? sCu : p.cu;
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -111,7 +130,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       uint32_t it = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int qb = item % p.nqb, h = (item / p.nqb) % kHeads, s = item / (p.nqb * kHeads);
-        const int t0 = p.cu[s], L = p.cu[s + 1] - t0;
+        const int t0 = cu[s], L = cu[s + 1] - t0;
         if (qb * 128 >= L) continue;
         const int Lp = (L + 63) & ~63;
         const int nkb = Lp >> 6;
@@ -130,11 +149,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   } else if (warp == 1) {
     if (lane == 0) {
       // ============================ MMA issuer ============================
-      uint32_t it = 0, g = 0;  // g: running P-block counter (buffer g & 1, use g >> 1)
+      uint32_t it = 0;
+      uint32_t uses[2] = {0, 0};  // how often each P buffer has been consumed (block b uses buffer b & 1)
       const uint32_t idesc_pv = tc::make_idesc_bf16_f32(128, kHeadDim) | (1u << 16);  // B is MN-major
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
         const int qb = item % p.nqb, s = item / (p.nqb * kHeads);
-        const int t0 = p.cu[s], L = p.cu[s + 1] - t0;
+        const int t0 = cu[s], L = cu[s + 1] - t0;
         if (qb * 128 >= L) continue;
         const int Lp = (L + 63) & ~63;
         const int nkb = Lp >> 6;
@@ -153,9 +173,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         tc::umma_commit(qk_empty);
         tc::umma_commit(s_full);
         tc::mbar_wait(v_full, it & 1);
-        for (int b = 0; b < nkb; ++b, ++g) {
-          const uint32_t buf = g & 1;
-          tc::mbar_wait(p_full + buf, (g >> 1) & 1);
+        tc::mbar_wait(o_free, (it & 1) ^ 1);   // the previous item's O has been read out
+        for (int b = 0; b < nkb; ++b) {
+          const uint32_t buf = b & 1;
+          tc::mbar_wait(p_full + buf, uses[buf] & 1);
+          ++uses[buf];
           tc::tc_fence_after();
           const uint64_t dp = tc::make_kmajor_sw128_desc(tc::smem_u32(sP + buf * kAtP));
           const uint64_t dv = make_mnmajor_sw128_desc(tc::smem_u32(sV + b * 8192));
@@ -171,65 +193,79 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
   } else {
     // ============================ softmax + epilogue ============================
+    const int grp = (warp - 2) >> 2;           // 0: even key blocks, 1: odd key blocks
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;         // row of the query block == TMEM lane
-    const int st = threadIdx.x - 64;           // 0..127 among the softmax threads
+    const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    constexpr float kScale = 0.125f * 1.4426950408889634f;   // 1/sqrt(64) * log2(e)
-    uint32_t it = 0, g = 0;
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64) * log2(e)
+    float* sMax = sXch;                        // [2][128]
+    float* sSum = sXch + 256;                  // [2][128]
+    uint32_t it = 0, u = 0;                    // u: uses of this group's P buffer
     for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
       const int qb = item % p.nqb, h = (item / p.nqb) % kHeads, s = item / (p.nqb * kHeads);
-      const int t0 = p.cu[s], L = p.cu[s + 1] - t0;
+      const int t0 = cu[s], L = cu[s + 1] - t0;
       if (qb * 128 >= L) continue;
       const int Lp = (L + 63) & ~63;
       const int nkb = Lp >> 6;
       const int q0 = qb * 128;
       const int i = min(q0 + r, L - 1);        // rows past the end mirror the last row, never stored
-      // relative-position bias window of this head, pre-multiplied by log2(e)
-      {
-        const float* rt = p.rel_table + (size_t)h * (2 * p.rel_half + 1) + p.rel_half;
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // previous item's readers are done
-        for (int x = st; x < 2 * Lp - 1; x += 128) sRel[x] = rt[x - (Lp - 1)] * 1.4426950408889634f;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      const float* rel_i = sRel + (Lp - 1) - i;   // rel_i[j] = bias(j - i) * log2e
+      const float* rel_i = sRel + h * kAtRelStride + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
       tc::mbar_wait(s_full, it & 1);
       tc::tc_fence_after();
-      // ---- pass 1: maximum of the raw scores over the real keys ----
+      // ---- pass 1: maximum of the raw scores over this group's real keys ----
       float mx = -INFINITY;
-      for (int c = 0; c < Lp; c += 32) {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(lane_addr + (uint32_t)c, v);
-        tc::tmem_ld_wait();
-        if (c + 32 <= L) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (c + j < L) mx = fmaxf(mx, __uint_as_float(v[j]));
-        }
-      }
-      // upper bound of the row maximum of (s/8 + bias) in the log2 domain
-      const float m_hat = mx * kScale + __ldg(p.rel_max + h) * 1.4426950408889634f;
-      // ---- pass 2: probabilities, 64 keys per block, as the A operand of P V ----
-      float sum = 0.f;
-      for (int b = 0; b < nkb; ++b, ++g) {
-        const uint32_t buf = g & 1;
-        tc::mbar_wait(p_empty + buf, ((g >> 1) & 1) ^ 1);
-        uint8_t* prow = sP + buf * kAtP + r * 128;
+      for (int b = grp; b < nkb; b += 2) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const int c = b * 64 + hf * 32;
+          if (c >= L) break;
           uint32_t v[32];
           tc::tmem_ld_32x32(lane_addr + (uint32_t)c, v);
           tc::tmem_ld_wait();
-          float pr[32];
+          if (c + 32 <= L) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float e = ex2_approx(fmaf(__uint_as_float(v[j]), kScale, rel_i[c + j] - m_hat));
-            pr[j] = (c + j < L) ? e : 0.f;
-            sum += pr[j];
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c + j < L) mx = fmaxf(mx, __uint_as_float(v[j]));
+          }
+        }
+      }
+      sMax[grp * 128 + r] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mx = fmaxf(mx, sMax[(grp ^ 1) * 128 + r]);
+      // upper bound of the row maximum of (s/8 + bias) in the log2 domain
+      const float m_hat = mx * kScale + __ldg(p.rel_max + h) * kLog2e;
+      // ---- pass 2: probabilities of this group's blocks as the A operand of P V ----
+      float sum = 0.f;
+      for (int b = grp; b < nkb; b += 2, ++u) {
+        tc::mbar_wait(p_empty + grp, (u & 1) ^ 1);
+        uint8_t* prow = sP + grp * kAtP + r * 128;
+        uint32_t vv[2][32];
+        tc::tmem_ld_32x32(lane_addr + (uint32_t)(b * 64), vv[0]);
+        tc::tmem_ld_32x32(lane_addr + (uint32_t)(b * 64 + 32), vv[1]);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c = b * 64 + hf * 32;
+          const uint32_t (&v)[32] = vv[hf];
+          float pr[32];
+          if (c + 32 <= L) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              pr[j] = ex2_approx(fmaf(__uint_as_float(v[j]), kScale, rel_i[c + j] - m_hat));
+              sum += pr[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = ex2_approx(fmaf(__uint_as_float(v[j]), kScale, rel_i[c + j] - m_hat));
+              pr[j] = (c + j < L) ? e : 0.f;
+              sum += pr[j];
+            }
           }
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -244,23 +280,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
         fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core
         tc::tc_fence_before();
-        tc::mbar_arrive(p_full + buf);
+        tc::mbar_arrive(p_full + grp);
       }
-      // S of this item is dead: the next item's Q K^T may overwrite it
+      // S of this item is dead for this warp: the next item's Q K^T may overwrite it once all 8 agree
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(s_free);
-      // ---- epilogue ----
+      sSum[grp * 128 + r] = sum;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float inv = 1.f / (sum + sSum[(grp ^ 1) * 128 + r]);
+      // ---- epilogue: group g writes head-dim columns [32 g, 32 g + 32) ----
       tc::mbar_wait(o_full, it & 1);
       tc::tc_fence_after();
-      const float inv = 1.f / sum;
-      __nv_bfloat16* dst = p.ctx + (size_t)(t0 + q0 + r) * kHidden + h * kHeadDim;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+      {
         uint32_t v[32];
-        tc::tmem_ld_32x32(lane_addr + kOCol + hf * 32, v);
+        tc::tmem_ld_32x32(lane_addr + kOCol + grp * 32, v);
         tc::tmem_ld_wait();
         if (q0 + r < L) {
+          __nv_bfloat16* dst = p.ctx + (size_t)(t0 + q0 + r) * kHidden + h * kHeadDim + grp * 32;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint4 o;
@@ -268,11 +305,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             o.y = pack_bf16(__uint_as_float(v[q4 * 8 + 2]) * inv, __uint_as_float(v[q4 * 8 + 3]) * inv);
             o.z = pack_bf16(__uint_as_float(v[q4 * 8 + 4]) * inv, __uint_as_float(v[q4 * 8 + 5]) * inv);
             o.w = pack_bf16(__uint_as_float(v[q4 * 8 + 6]) * inv, __uint_as_float(v[q4 * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + hf * 32 + q4 * 8) = o;
+            *reinterpret_cast<uint4*>(dst + q4 * 8) = o;
           }
         }
       }
-      tc::tc_fence_before();   // O reads are ordered before the arrivals that let the next P V start
+      tc::tc_fence_before();   // O reads are ordered before the next item's first P V
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(o_free);
       ++it;
     }
   }
