@@ -243,6 +243,10 @@ def main():
     qs_host = qs.cpu().pin_memory()
     stream = torch.cuda.current_stream(dev)
     sp = stream.cuda_stream
+    if args.only == "batched":
+        print(json.dumps(bench_batched(torch, native, dev, idx, qs, pk, world, rank, rows, dist)))
+        idx.close()
+        return
 
     from claude_semantic_search_b200.sharded import ShardedSearch
     id_offset = rank * rows

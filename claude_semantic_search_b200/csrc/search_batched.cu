@@ -3,10 +3,13 @@
 // batch of queries) without materialising the nq x N score matrix.
 //
 //   1. queries -> bf16 A operand; the corpus' bf16 shadow copy (xb) is the B operand.
-//   2. the corpus is swept in passes of geometrically growing size (2K, 8K, 32K ... rows).
+//   2. seed pass over the first 16K rows: the GEMM epilogue keeps only the maximum of every
+//      32-row chunk; the k-th largest of these (k distinct rows) is a valid lower bound of the
+//      k-th best score and becomes the first threshold.  The lists are then cleared.
+//   3. the corpus (from row 0 again) is swept in passes of growing size (128K, 1M, 8M ... rows).
 //      Each pass is one tcgen05 GEMM (gemm_tc.cuh) whose epilogue compares every score with
-//      a per-query threshold and appends (score, row) to the query's candidate list.
-//   3. after each pass a small kernel sorts every list, sets the next threshold to
+//      the per-query threshold and appends (score, row) to the query's candidate list; after
+//      each pass a small kernel sorts every list, sets the next threshold to
 //      (k-th best bf16 score) - 2*eps_q and drops entries below it.
 //   4. the final kernel re-scores the surviving candidates in fp32 with the arithmetic of the
 //      streaming scan (bit-identical scores to the batch-1 path) and writes the top-k.
@@ -21,14 +24,16 @@
 #include "gemm_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace css {
 namespace {
 
 constexpr int kCap = 4096;          // candidate slots per query
 constexpr int kQChunk = 1024;       // queries per sweep
-constexpr int kFirstPassRows = 2048;
-constexpr int kPassGrowth = 4;
+constexpr int kSeedRows = 16384;    // pass 0 ("seed"): only the maximum of every 32-row chunk is kept
+constexpr int kFirstPassRows = 131072;
+constexpr int kPassGrowth = 8;
 constexpr int kSelThreads = 512;
 constexpr int kFallbackSlices = 8;
 
@@ -83,38 +88,77 @@ struct EpiSearch {
     Cand* cand;             // [nq][kCap]
     int* ovf_flag;          // [nq]
     const uint32_t* mask;   // nullable row bitmask (global rows)
-    int row0;               // global row of column 0 of this pass
+    int row0;               // global row of column 0 of this pass (multiple of 32)
     int n_rows;             // rows in this pass
+    int seed;               // 1: keep only the maximum of each 32-row chunk (threshold seeding)
   };
   const Params& p;
   __device__ EpiSearch(const Params& p_, int, uint8_t*) : p(p_) {}
   __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const int m = m_warp + lane;
     if (m >= M) return;
+    if (p.seed) {
+      // chunk-aligned mask word (row0 and n0 are multiples of 32) restricted to real rows
+      uint32_t mw = p.mask ? __ldg(p.mask + ((p.row0 + n0) >> 5)) : 0xffffffffu;
+      const int left = p.n_rows - n0;
+      if (left < 32) mw &= left > 0 ? ((1u << left) - 1u) : 0u;
+      float best = -INFINITY;
+      int bj = -1;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __uint_as_float(v[j]);
+        if (((mw >> j) & 1u) && s > best) {
+          best = s;
+          bj = j;
+        }
+      }
+      if (bj >= 0) offer(m, n0 + bj, best);
+      return;
+    }
     const float t = __ldg(p.thr + m);
-    float mx = __uint_as_float(v[0]);
+    // two-level reject: maxima of the four 8-column groups, then their maximum.  A warp takes
+    // the slow path when ANY of its 32 query rows has a hit, so the slow path itself only
+    // descends into groups that hold one (round-1 profile: flat 32-way checks made the first
+    // sweep pass epilogue-bound).
+    float gm[4];
 #pragma unroll
-    for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+    for (int g = 0; g < 4; ++g) {
+      float a = __uint_as_float(v[g * 8]);
+#pragma unroll
+      for (int j = 1; j < 8; ++j) a = fmaxf(a, __uint_as_float(v[g * 8 + j]));
+      gm[g] = a;
+    }
+    const float mx = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
     if (!(mx >= t)) return;
-    // rare path; fully unrolled so v[] stays in registers (no dynamic indexing)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float s = __uint_as_float(v[j]);
-      if (s >= t) offer(m, n0 + j, s);
+    for (int g = 0; g < 4; ++g) {
+      if (gm[g] >= t) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float s = __uint_as_float(v[g * 8 + j]);
+          if (s >= t) offer(m, n0 + g * 8 + j, s);
+        }
+      }
     }
   }
-  __device__ __noinline__ void offer(int m, int r, float s) {
-    if (r >= p.n_rows) return;
-    const int g = p.row0 + r;
-    if (p.mask && !((__ldg(p.mask + (g >> 5)) >> (g & 31)) & 1u)) return;
-    const unsigned pos = atomicAdd(p.count + m, 1u);
+  // Rare path, kept out of line (and free of `this`, so the functor stays in registers): the
+  // hot loop above stays compact; inlining 32 copies of this body slowed the whole epilogue.
+  __device__ __forceinline__ void offer(int m, int r, float s) {
+    append_hit(p.count, p.cand, p.ovf_flag, p.mask, p.row0, p.n_rows, m, r, s);
+  }
+  __device__ __noinline__ static void append_hit(unsigned* count, Cand* cand, int* ovf_flag, const uint32_t* mask,
+                                                 int row0, int n_rows, int m, int r, float s) {
+    if (r >= n_rows) return;
+    const int g = row0 + r;
+    if (mask && !((__ldg(mask + (g >> 5)) >> (g & 31)) & 1u)) return;
+    const unsigned pos = atomicAdd(count + m, 1u);
     if (pos < (unsigned)kCap) {
       Cand c;
       c.score = s;
       c.row = g;
-      p.cand[(size_t)m * kCap + pos] = c;
+      cand[(size_t)m * kCap + pos] = c;
     } else {
-      p.ovf_flag[m] = 1;
+      ovf_flag[m] = 1;
     }
   }
   __device__ __forceinline__ void chunk_begin() {}
@@ -166,6 +210,7 @@ struct SelectParams {
   int64_t id_offset;
   float* D;
   int64_t* I;
+  int seed;             // 1: this call follows the seed pass -> only the threshold survives
 };
 
 template <bool kFinal>
@@ -214,6 +259,14 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
   __syncthreads();
   const int keep = s_keep;
   if (!kFinal) {
+    if (p.seed) {
+      // the seed candidates are chunk maxima only: the sweep restarts at row 0 and finds them again
+      if (tid == 0) {
+        p.count[qi] = 0;
+        p.thr[qi] = thr;
+      }
+      return;
+    }
     for (int i = tid; i < keep; i += kSelThreads) list[i] = s[i];
     if (tid == 0) {
       p.count[qi] = (unsigned)keep;
@@ -257,6 +310,14 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
     p.D[(size_t)qi * p.k + i] = filled ? s[i].score : -FLT_MAX;
     p.I[(size_t)qi * p.k + i] = filled ? (int64_t)s[i].row + p.id_offset : (int64_t)-1;
   }
+}
+
+// Tuning knobs (rows): CSS_BATCH_SEED_ROWS, CSS_BATCH_FIRST_ROWS override the defaults.
+int64_t env_rows(const char* name, int64_t dflt) {
+  const char* v = getenv(name);
+  if (!v) return dflt;
+  const long long x = atoll(v);
+  return x >= 2048 ? (int64_t)(x / 256 * 256) : dflt;
 }
 
 int ensure_state(css_index* h, int nq) {
@@ -348,23 +409,41 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
     sp.id_offset = id_offset;
     sp.D = D_dev + (size_t)q0 * k;
     sp.I = I_dev + (size_t)q0 * k;
+    sp.seed = 0;
 
+    EpiSearch::Params ep;
+    ep.thr = st->thr;
+    ep.count = st->count;
+    ep.cand = st->cand;
+    ep.ovf_flag = st->ovf_flag;
+    ep.mask = mask_dev;
+    // ---- seed pass: chunk maxima of the first rows -> first threshold ----
+    {
+      static const int64_t seed_dflt = env_rows("CSS_BATCH_SEED_ROWS", kSeedRows);
+      const int64_t seed_rows = std::min<int64_t>(N, std::max<int64_t>(seed_dflt, (int64_t)64 * k));
+      ep.row0 = 0;
+      ep.n_rows = (int)seed_rows;
+      ep.seed = 1;
+      CSS_CHECK((gemm::run<256, EpiSearch>(st->qb, d, h->xb, d, nqc, (int)seed_rows, d, /*m_fastest=*/1, ep, h->n_sm,
+                                          stream)));
+      sp.seed = 1;
+      select_kernel<false><<<(unsigned)nqc, kSelThreads, 0, stream>>>(sp);
+      CSS_LAUNCHED();
+      sp.seed = 0;
+      ep.seed = 0;
+    }
+    // ---- sweep ----
     int64_t r0 = 0;
-    int64_t pass_rows = kFirstPassRows;
+    static const int64_t first_dflt = env_rows("CSS_BATCH_FIRST_ROWS", kFirstPassRows);
+    int64_t pass_rows = first_dflt;
     while (r0 < N) {
       int64_t nr = std::min<int64_t>(pass_rows, N - r0);
       // fold a short tail into this pass
       if (N - (r0 + nr) < nr / 2) nr = N - r0;
-      EpiSearch::Params ep;
-      ep.thr = st->thr;
-      ep.count = st->count;
-      ep.cand = st->cand;
-      ep.ovf_flag = st->ovf_flag;
-      ep.mask = mask_dev;
       ep.row0 = (int)r0;
       ep.n_rows = (int)nr;
       CSS_CHECK((gemm::run<256, EpiSearch>(st->qb, d, h->xb + (size_t)r0 * d, d, nqc, (int)nr, d,
-                                             /*m_fastest=*/1, ep, h->n_sm, stream)));
+                                          /*m_fastest=*/1, ep, h->n_sm, stream)));
       r0 += nr;
       if (r0 < N) {
         select_kernel<false><<<(unsigned)nqc, kSelThreads, 0, stream>>>(sp);
