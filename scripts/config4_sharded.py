@@ -1,0 +1,129 @@
+"""BASELINE configs[3]: exact top-10 over a corpus row-sharded across the GPUs of one box with the
+NCCL top-k merge (100M x 768 = 12.5M rows per GPU on 8 GPUs).  Run under torchrun:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29517 scripts/config4_sharded.py --rows-per-gpu 12500000
+
+Verification at this size (a CPU oracle cannot hold 307 GB): planted needles -- for 64 queries,
+10 rows spread over ALL shards are overwritten with normalise(q + sigma_r * noise) at decreasing
+similarity, so the exact global top-10 (ids and order) is known a priori -- plus agreement of the
+batch-1 (streaming scan) and batch-1024 (tensor-core) paths on every query.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from claude_semantic_search_b200 import _native  # noqa: E402
+from claude_semantic_search_b200.sharded import ShardedSearch  # noqa: E402
+
+D, K = 768, 10
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows-per-gpu", type=int, default=12_500_000)
+    ap.add_argument("--queries", type=int, default=200)
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))
+    rows = args.rows_per_gpu
+    N = rows * world
+    # queries (replicated) and needles (global ids, identical on every rank)
+    gq = torch.Generator(device="cpu").manual_seed(43)
+    q = torch.randn((1024, D), generator=gq)
+    q = (q / q.norm(dim=1, keepdim=True)).to(dev)
+    rng = np.random.default_rng(7)
+    n_needle_q = 64
+    needle_ids = np.sort(rng.choice(N, size=(n_needle_q, K), replace=False), axis=1)
+    rng.shuffle(needle_ids, axis=1)
+    noise = torch.randn((n_needle_q, K, D), generator=gq)
+    noise = noise / noise.norm(dim=2, keepdim=True)
+    sig = (0.05 + 0.05 * torch.arange(K)).view(1, K, 1)
+    needles = q[:n_needle_q].cpu().unsqueeze(1) + sig * noise
+    needles = needles / needles.norm(dim=2, keepdim=True)          # [64, 10, 768], similarity decreasing in r
+
+    idx = _native.Index(D, device=dev.index)
+    idx.reserve(rows)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    sp = torch.cuda.current_stream(dev).cuda_stream
+    lo = rank * rows
+    tile = 250_000
+    t0 = time.perf_counter()
+    for r0 in range(0, rows, tile):
+        nr = min(tile, rows - r0)
+        blk = torch.randn((nr, D), generator=g, device=dev)
+        sel = (needle_ids >= lo + r0) & (needle_ids < lo + r0 + nr)
+        for qi, r in zip(*np.nonzero(sel)):
+            blk[int(needle_ids[qi, r]) - lo - r0] = needles[qi, r].to(dev) * 3.0   # any scale: add() normalises
+        idx.add_device(blk.data_ptr(), nr, normalize=True, stream=sp)
+        torch.cuda.current_stream(dev).synchronize()
+    build_s = time.perf_counter() - t0
+    ss = ShardedSearch(idx, id_offset=lo)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n
+
+    # correctness: batch-1 path on the needle queries, batched path on all 1024
+    I1 = []
+    for i in range(n_needle_q):
+        Dd, Id = ss.search_device(q[i:i + 1], K)
+        I1.append(Id.cpu().numpy()[0].copy())
+    I1 = np.stack(I1)
+    Db, Ib = ss.search_device(q, K)
+    Ib = Ib.cpu().numpy().copy()
+    ok_scan = bool((I1 == needle_ids).all())
+    ok_batched = bool((Ib[:n_needle_q] == needle_ids).all())
+    # timing
+    for i in range(5):
+        ss.search_device(q[i:i + 1], K)
+    ms1 = timed(lambda i: ss.search_device(q[i % 1024:i % 1024 + 1], K), args.queries)
+    ss.search_device(q, K)
+    msb = timed(lambda i: ss.search_device(q, K), 3)
+    if rank == 0:
+        hbm = 6538.3
+        peaks = Path(__file__).resolve().parent.parent / "MEASURED_PEAKS.json"
+        if peaks.exists():
+            hbm = json.loads(peaks.read_text())["hbm_gbs"]
+        gbs = rows * D * 4 / (ms1 * 1e-3) / 1e9
+        print(json.dumps({
+            "workload": f"exact top-10 over {N} x 768 fp32 rows, row-sharded over {world} GPU(s), NCCL gather + merge",
+            "rows_per_gpu": rows, "n_gpus": world, "build_s": build_s,
+            "batch1": {"ms_per_query": ms1, "qps": 1e3 / ms1, "per_gpu_hbm_gbs": gbs, "frac_of_hbm_peak": gbs / hbm,
+                       "aggregate_hbm_gbs": gbs * world},
+            "batch1024": {"ms_per_call": msb, "qps": 1024 / (msb * 1e-3),
+                          "tflops_per_gpu": 2.0 * 1024 * rows * D / (msb * 1e-3) / 1e12},
+            "needles_exact_scan": ok_scan, "needles_exact_batched": ok_batched}))
+    assert ok_scan and ok_batched, (ok_scan, ok_batched)
+    idx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
