@@ -1,17 +1,24 @@
 // attention_tc.cuh -- E3 on the 5th-generation tensor cores.
 //
-// One persistent CTA per SM walks work items (sequence, head, block of 128 query rows):
-//   warp 0      TMA producer: Q [128 x 64], K [Lp x 64], V [Lp x 64] bf16 tiles straight out of the
-//               packed qkv activation [T, 2304] (128-byte swizzle)
-//   warp 1      MMA issuer:   S = Q K^T   (tcgen05.mma M128 x N<=256 x K16, fp32 in TMEM cols [0, Lp))
-//                             O = P V     (M128 x N64, V is the MN-major B operand, TMEM cols [448, 512))
-//   warps 2-9   softmax + epilogue: two groups of 4 warps, one query row per thread in each group
-//               (= one TMEM lane); group 0 owns the even 64-key blocks, group 1 the odd ones:
-//               pass 1  row maximum of the raw scores           (tcgen05.ld)
-//               pass 2  p = exp2(s*c + rel[j-i] - m), 64 keys at a time, written as the bf16 A operand of
-//                       the PV product into a double-buffered shared tile -> the PV MMAs of block b run
-//                       while block b+1 is exponentiated
-//               epilogue O / sum -> ctx (bf16)
+// One persistent CTA per SM walks work units (sequence, head); a unit's K and V tiles are staged
+// once and reused by its query blocks of 128 rows ("items").  The keys of an item are split into
+// two halves of up to 192 keys, each with its own score tile and softmax group (8 warps); the
+// groups agree on one row maximum, so both halves accumulate into ONE output tile, which is
+// double-buffered across items:
+//
+//   TMEM columns   S0 [0,192)   S1 [192,384)   O[item & 1] [384 + 64 (item & 1), +64)
+//
+//   warp 0        TMA producer: Q [128 x 64] per item, K / V [Lp x 64] per unit, bf16 tiles straight
+//                 out of the packed qkv activation [T, 2304] (128-byte swizzle)
+//   warp 1        MMA issuer:   S_g = Q K_g^T  (tcgen05.mma M128 x N<=192 x K16)
+//                               O  += P_g[b] V_g[b]  (M128 x N64, V is the MN-major B operand);
+//                               the next item's Q K^T is issued in front of the last round of P V
+//   warps 2-5     epilogue: O / sum -> ctx (bf16), overlapped with the next item's softmax
+//   warps 6...     softmax group 0 then group 1, kAtGW warps each (4: one per TMEM lane quarter, a thread
+//                 owns a row's 64 columns of every key block; 8: two per quarter, 32 columns each):
+//                 pass 1  row maximum of the raw scores (tcgen05.ld), exchanged over all 16 warps
+//                 pass 2  p = exp2(s*c + rel[j-i] - m), one 64-key block at a time, written as the
+//                         bf16 A operand of P V into a double-buffered shared tile per group
 // Keys beyond the sequence end do not exist in the packed layout (their tile rows hold the next
 // sequence's tokens or TMA zero fill): their probabilities are forced to 0, which is what the
 // reference's additive finfo.min mask produces.  Sequences longer than kAttnTcMaxLen take the
@@ -22,23 +29,47 @@
 namespace css {
 namespace enc {
 
-constexpr int kAttnTcMaxLen = 448;                 // S occupies TMEM columns [0, Lp), O [448, 512)
-constexpr int kAttnTcThreads = 320;                // 10 warps: TMA, MMA, 2 x 4 softmax
+constexpr int kAttnTcMaxLen = 384;                 // two halves of 192 keys
+constexpr int kAtGW = 4;                           // softmax warps per key half: 4 (64 columns per thread and block) or 8 (32)
+constexpr int kAtHf = 8 / kAtGW;                   // 32-column pieces of a key block per thread
+constexpr int kAttnTcThreads = (6 + 2 * kAtGW) * 32;  // warps: TMA, MMA, 4 epilogue, 2 x kAtGW softmax
+constexpr int kAtHalfCols = 192;
 constexpr int kAtQ = 128 * 128;                    // Q tile bytes
 constexpr int kAtKV = kAttnTcMaxLen * 128;         // K / V tile bytes (max)
 constexpr int kAtP = 128 * 128;                    // one P block (128 rows x 64 keys bf16)
-constexpr int kAtRelStride = 2 * kAttnTcMaxLen;     // floats per head: bias(d) * log2e for d in [-447, 448)
+constexpr int kAtRelStride = 2 * kAttnTcMaxLen;    // floats per head: bias(d) * log2e for d in [-383, 383]
 constexpr int kAtRel = kHeads * kAtRelStride * 4;  // every head's window, staged once per CTA
-constexpr int kAtCuMax = 1024;                     // cu_seqlens entries cached in shared memory
-constexpr int kAtXch = 4 * 128 * 4;                // per-row partial max / sum of the two softmax groups
-constexpr int kAtSmem = kAtQ + 2 * kAtKV + 2 * kAtP + kAtRel + kAtXch + (kAtCuMax + 1) * 4 + 256 + 1024;
-constexpr uint32_t kOCol = 448;
+constexpr int kAtCuMax = 768;                      // cu_seqlens entries cached in shared memory
+constexpr int kAtXmax = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial maxima
+constexpr int kAtStat = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial sums
+constexpr int kAtSmem = kAtQ + 2 * kAtKV + 4 * kAtP + kAtRel + 64 + kAtXmax + kAtStat + (kAtCuMax + 1) * 4 + 4 + 256 + 1024;
+static_assert(kAtSmem <= 232448, "attention shared memory exceeds the 227 KB opt-in limit");
+constexpr uint32_t kOCol = 2 * kAtHalfCols;        // O[0] at 384, O[1] at 448
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// Packed fp32x2 arithmetic of sm_100 (two independent fp32 lanes in one 64-bit register).
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 // V tile as the MN-major (N = head dim contiguous) B operand: rows of 128 B, 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr) {
@@ -57,62 +88,206 @@ struct AttnTcParams {
   const float* rel_max;     // [heads] max over the head's table
   int rel_half;
   int n_seq;
-  int nqb;                  // query blocks per sequence in the item space = ceil(max_len / 128)
   __nv_bfloat16* ctx;       // [T, 768]
+  long long* trace;         // optional [5 roles][128 items][8 tags] clock64 stamps of CTA 0 (profiling aid)
+};
+
+__device__ __forceinline__ void attn_trace(long long* trace, int role, uint32_t item, int tag) {
+  if (trace != nullptr && blockIdx.x == 0 && item < 128u) trace[(role * 128 + item) * 8 + tag] = clock64();
+}
+
+// Every role walks the same item sequence: units u = blockIdx.x, +gridDim.x, ...; unit = (sequence,
+// head); items = the unit's query blocks.
+struct AttnWalk {
+  const int32_t* cu;
+  int n_units, stride;
+  int u, qb, nqb;
+  int h, t0, L;
+  int nb0, nb1;             // 64-key blocks of the two halves (nb0 >= nb1, nb1 may be 0)
+  __device__ __forceinline__ void init(const int32_t* cu_, int n_units_) {
+    cu = cu_;
+    n_units = n_units_;
+    stride = gridDim.x;
+    u = (int)blockIdx.x - stride;
+    qb = 0;
+    nqb = 0;
+  }
+  __device__ __forceinline__ bool advance() {
+    if (++qb < nqb) return true;
+    u += stride;
+    if (u >= n_units) return false;
+    const int s = u / kHeads;
+    h = u - s * kHeads;
+    t0 = cu[s];
+    L = cu[s + 1] - t0;
+    nqb = (L + 127) >> 7;
+    const int nkb = (L + 63) >> 6;
+    nb0 = (nkb + 1) >> 1;
+    nb1 = nkb - nb0;
+    qb = 0;
+    return true;
+  }
+  __device__ __forceinline__ bool first_of_unit() const { return qb == 0; }
+  __device__ __forceinline__ bool last_of_unit() const { return qb == nqb - 1; }
+};
+
+// State of the MMA-issuing thread.
+struct AttnMma {
+  uint64_t *q_full, *q_empty, *k_full, *k_empty, *v_full, *v_empty;
+  uint64_t *s_full, *s_free, *o_full, *o_free, *p_full, *p_empty;
+  uint32_t sQ, sK, sV, sP, tmem_base;
+  long long* trace = nullptr;
+  uint32_t n_qk = 0, n_pv = 0;          // items whose Q K^T / P V have been issued
+  uint32_t n_unit_k = 0, n_unit_v = 0;  // K / V loads consumed
+  uint32_t n_s0 = 0, n_s1 = 0;          // items whose S_g has been produced
+  uint32_t n_p0 = 0, n_p1 = 0;          // P blocks of group g consumed
+
+  // S_0 = Q K_0^T and S_1 = Q K_1^T of item x
+  __device__ __forceinline__ void qk(const AttnWalk& x) {
+    attn_trace(trace, 0, n_qk, 0);
+    tc::mbar_wait(q_full, n_qk & 1);
+    if (x.first_of_unit()) tc::mbar_wait(k_full, n_unit_k & 1);
+    const uint64_t dq = tc::make_kmajor_sw128_desc(sQ);
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const int nb = g ? x.nb1 : x.nb0;
+      uint32_t& n_s = g ? n_s1 : n_s0;
+      if (nb > 0) {
+        tc::mbar_wait(s_free + g, (n_s & 1) ^ 1);   // group g has finished reading the previous S_g
+        ++n_s;
+        tc::tc_fence_after();
+        const uint64_t dk = tc::make_kmajor_sw128_desc(sK + (g ? x.nb0 : 0) * 8192);
+        const uint32_t idesc = tc::make_idesc_bf16_f32(128, nb * 64);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          tc::umma_bf16(tmem_base + (uint32_t)(g * kAtHalfCols), dq + k * tc::kDescKStep, dk + k * tc::kDescKStep, idesc,
+                        k != 0);
+        tc::umma_commit(s_full + g);
+        attn_trace(trace, 0, n_qk, 1 + g);
+      }
+    }
+    tc::umma_commit(q_empty);   // Q (and after the unit's last item K) may be overwritten
+    if (x.last_of_unit()) {
+      tc::umma_commit(k_empty);
+      ++n_unit_k;
+    }
+    ++n_qk;
+  }
+
+  // O[item & 1] (+)= P_g[lb] V_g[lb]
+  template <int G>
+  __device__ __forceinline__ void pv(const AttnWalk& x, int lb) {
+    uint32_t& n_p = G ? n_p1 : n_p0;
+    const uint32_t buf = n_p & 1;
+    tc::mbar_wait(p_full + G * 2 + buf, (n_p >> 1) & 1);
+    ++n_p;
+    const uint32_t ob = n_pv & 1;
+    if (G == 0 && lb == 0) {
+      if (x.first_of_unit()) tc::mbar_wait(v_full, n_unit_v & 1);
+      tc::mbar_wait(o_free + ob, ((n_pv >> 1) & 1) ^ 1);   // the epilogue has read the item that used O[ob] before
+    }
+    tc::tc_fence_after();
+    attn_trace(trace, 1, n_pv, G * 4 + lb);
+    const uint32_t idesc_pv = tc::make_idesc_bf16_f32(128, kHeadDim) | (1u << 16);  // B is MN-major
+    const uint64_t dp = tc::make_kmajor_sw128_desc(sP + (G * 2 + buf) * kAtP);
+    const uint64_t dv = make_mnmajor_sw128_desc(sV + ((G ? x.nb0 : 0) + lb) * 8192);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)   // 16 keys per MMA: +32 B in P's rows, +16 rows (2048 B) in V
+      tc::umma_bf16(tmem_base + kOCol + ob * kHeadDim, dp + k * tc::kDescKStep, dv + k * (2048 >> 4), idesc_pv,
+                    (G | lb | k) != 0);
+    tc::umma_commit(p_empty + G * 2 + buf);
+    attn_trace(trace, 3, n_pv, G * 4 + lb);
+  }
+
+  __device__ __forceinline__ void run(AttnWalk cur) {
+    bool have = cur.advance();
+    if (have) qk(cur);
+    while (have) {
+      AttnWalk nxt = cur;
+      const bool have_next = nxt.advance();
+      // S_g is free as soon as group g has loaded its last block (before that block's
+      // exponentials), so the next item's Q K^T goes in front of the last round of P V
+      for (int lb = 0; lb < cur.nb0; ++lb) {
+        if (lb == cur.nb0 - 1 && have_next) qk(nxt);
+        pv<0>(cur, lb);
+        if (lb < cur.nb1) pv<1>(cur, lb);
+      }
+      tc::umma_commit(o_full + (n_pv & 1));
+      if (cur.last_of_unit()) {
+        tc::umma_commit(v_empty);   // every P V of the unit has been issued
+        ++n_unit_v;
+      }
+      ++n_pv;
+      cur = nxt;
+      have = have_next;
+    }
+  }
 };
 
 static __global__ void __launch_bounds__(kAttnTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by pointer arithmetic, so the compiler keeps the shared address space (LDS / STS)
+  uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + kAtQ;
   uint8_t* sV = sK + kAtKV;
-  uint8_t* sP = sV + kAtKV;                       // 2 blocks
-  float* sRel = reinterpret_cast<float*>(sP + 2 * kAtP);
-  float* sXch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sRel) + kAtRel);   // [2][128] max, [2][128] sum
-  int32_t* sCu = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(sXch) + kAtXch);
+  uint8_t* sP = sV + kAtKV;                       // [group][buffer] blocks
+  float* sRel = reinterpret_cast<float*>(sP + 4 * kAtP);
+  float* sRelMax = sRel + kHeads * kAtRelStride;  // [16] per-head table maximum * log2e
+  float* sXmax = sRelMax + 16;
+  float* sStat = sXmax + kAtXmax / 4;
+  int32_t* sCu = reinterpret_cast<int32_t*>(sStat + kAtStat / 4);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sCu) + ((kAtCuMax + 1) * 4 + 7) / 8 * 8);
-  uint64_t* qk_full = bars + 0;
-  uint64_t* qk_empty = bars + 1;
-  uint64_t* v_full = bars + 2;
-  uint64_t* v_empty = bars + 3;
-  uint64_t* s_full = bars + 4;
-  uint64_t* s_free = bars + 5;
-  uint64_t* o_full = bars + 6;
-  uint64_t* p_full = bars + 7;    // [2]
-  uint64_t* p_empty = bars + 9;   // [2]
-  uint64_t* o_free = bars + 11;   // all 8 softmax warps have read O of the previous item
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 3;
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;
+  uint64_t* s_full = bars + 6;     // [2]  MMA -> softmax group
+  uint64_t* s_free = bars + 8;     // [2]  softmax group (8 warps) -> MMA
+  uint64_t* o_full = bars + 10;    // [2]  MMA -> epilogue, by item parity
+  uint64_t* o_free = bars + 12;    // [2]  epilogue (4 warps) -> MMA
+  uint64_t* p_full = bars + 14;    // [2][2] softmax group (8 warps) -> MMA
+  uint64_t* p_empty = bars + 18;   // [2][2] MMA -> softmax group
+  uint64_t* st_full = bars + 22;   // [2]  all 16 softmax warps -> epilogue: row sums of an item, by item parity
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_q);
     tc::prefetch_tmap(&tmap_kv);
-    tc::mbar_init(qk_full, 1);
-    tc::mbar_init(qk_empty, 1);
+    tc::mbar_init(q_full, 1);
+    tc::mbar_init(q_empty, 1);
+    tc::mbar_init(k_full, 1);
+    tc::mbar_init(k_empty, 1);
     tc::mbar_init(v_full, 1);
     tc::mbar_init(v_empty, 1);
-    tc::mbar_init(s_full, 1);
-    tc::mbar_init(s_free, 8);
-    tc::mbar_init(o_full, 1);
-    tc::mbar_init(o_free, 8);
-    for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(p_full + i, 128);
-      tc::mbar_init(p_empty + i, 1);
+    for (int g = 0; g < 2; ++g) {
+      tc::mbar_init(s_full + g, 1);
+      tc::mbar_init(s_free + g, kAtGW);
+      tc::mbar_init(o_full + g, 1);
+      tc::mbar_init(o_free + g, 4);
+      tc::mbar_init(st_full + g, 2 * kAtGW);
+      for (int b = 0; b < 2; ++b) {
+        tc::mbar_init(p_full + g * 2 + b, kAtGW);
+        tc::mbar_init(p_empty + g * 2 + b, 1);
+      }
     }
     tc::fence_barrier_init();
   }
   __syncwarp();
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   // per-CTA constants: every head's bias window (x log2e) and the sequence offsets, so that no
-  // item starts with a chain of dependent global loads (round-1 profile: ~2K cycles per item)
+  // item starts with a chain of dependent global loads
   for (int x = threadIdx.x; x < kHeads * kAtRelStride; x += kAttnTcThreads) {
     const int hh = x / kAtRelStride, d = x % kAtRelStride - (kAttnTcMaxLen - 1);
     const int dc = max(-p.rel_half, min(p.rel_half, d));
     sRel[x] = p.rel_table[(size_t)hh * (2 * p.rel_half + 1) + p.rel_half + dc] * 1.4426950408889634f;
   }
+  if (threadIdx.x < kHeads) sRelMax[threadIdx.x] = p.rel_max[threadIdx.x] * 1.4426950408889634f;
   const bool cu_in_smem = p.n_seq <= kAtCuMax;
   if (cu_in_smem)
     for (int x = threadIdx.x; x <= p.n_seq; x += kAttnTcThreads) sCu[x] = p.cu[x];
@@ -122,197 +297,244 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_items = p.n_seq * kHeads * p.nqb;
+  AttnWalk w;
+  w.init(cu, p.n_seq * kHeads);
 
   if (warp == 0) {
     if (lane == 0) {
       // ============================ TMA producer ============================
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int qb = item % p.nqb, h = (item / p.nqb) % kHeads, s = item / (p.nqb * kHeads);
-        const int t0 = cu[s], L = cu[s + 1] - t0;
-        if (qb * 128 >= L) continue;
-        const int Lp = (L + 63) & ~63;
-        const int nkb = Lp >> 6;
-        tc::mbar_wait(qk_empty, (it & 1) ^ 1);
-        tc::mbar_expect_tx(qk_full, kAtQ + Lp * 128);
-        tc::tma_load_2d(sQ, &tmap_q, qk_full, h * kHeadDim, t0 + qb * 128, tc::kEvictNormal);
-        for (int b = 0; b < nkb; ++b)
-          tc::tma_load_2d(sK + b * 8192, &tmap_kv, qk_full, kHidden + h * kHeadDim, t0 + b * 64, tc::kEvictNormal);
-        tc::mbar_wait(v_empty, (it & 1) ^ 1);
-        tc::mbar_expect_tx(v_full, Lp * 128);
-        for (int b = 0; b < nkb; ++b)
-          tc::tma_load_2d(sV + b * 8192, &tmap_kv, v_full, 2 * kHidden + h * kHeadDim, t0 + b * 64, tc::kEvictNormal);
+      uint32_t it = 0, un = 0;
+      while (w.advance()) {
+        if (w.first_of_unit()) {
+          const int nkb = w.nb0 + w.nb1;
+          tc::mbar_wait_sleep(k_empty, (un & 1) ^ 1, 200);
+          tc::mbar_expect_tx(k_full, nkb * 8192);
+          for (int b = 0; b < nkb; ++b)
+            tc::tma_load_2d(sK + b * 8192, &tmap_kv, k_full, kHidden + w.h * kHeadDim, w.t0 + b * 64, tc::kEvictNormal);
+        }
+        tc::mbar_wait_sleep(q_empty, (it & 1) ^ 1, 200);
+        tc::mbar_expect_tx(q_full, kAtQ);
+        tc::tma_load_2d(sQ, &tmap_q, q_full, w.h * kHeadDim, w.t0 + w.qb * 128, tc::kEvictNormal);
+        if (w.first_of_unit()) {
+          const int nkb = w.nb0 + w.nb1;
+          tc::mbar_wait_sleep(v_empty, (un & 1) ^ 1, 200);
+          tc::mbar_expect_tx(v_full, nkb * 8192);
+          for (int b = 0; b < nkb; ++b)
+            tc::tma_load_2d(sV + b * 8192, &tmap_kv, v_full, 2 * kHidden + w.h * kHeadDim, w.t0 + b * 64, tc::kEvictNormal);
+          ++un;
+        }
         ++it;
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ============================ MMA issuer ============================
-      uint32_t it = 0;
-      uint32_t uses[2] = {0, 0};  // how often each P buffer has been consumed (block b uses buffer b & 1)
-      const uint32_t idesc_pv = tc::make_idesc_bf16_f32(128, kHeadDim) | (1u << 16);  // B is MN-major
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int qb = item % p.nqb, s = item / (p.nqb * kHeads);
-        const int t0 = cu[s], L = cu[s + 1] - t0;
-        if (qb * 128 >= L) continue;
-        const int Lp = (L + 63) & ~63;
-        const int nkb = Lp >> 6;
-        tc::mbar_wait(qk_full, it & 1);
-        tc::mbar_wait(s_free, (it & 1) ^ 1);   // softmax has finished reading the previous S
-        tc::tc_fence_after();
-        const uint64_t dq = tc::make_kmajor_sw128_desc(tc::smem_u32(sQ));
-        for (int n0 = 0; n0 < Lp; n0 += 256) {
-          const int n = (Lp - n0) < 256 ? (Lp - n0) : 256;
-          const uint32_t idesc = tc::make_idesc_bf16_f32(128, n);
-          const uint64_t dk = tc::make_kmajor_sw128_desc(tc::smem_u32(sK + n0 * 128));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc::umma_bf16(tmem_base + (uint32_t)n0, dq + k * tc::kDescKStep, dk + k * tc::kDescKStep, idesc, k != 0);
-        }
-        tc::umma_commit(qk_empty);
-        tc::umma_commit(s_full);
-        tc::mbar_wait(v_full, it & 1);
-        tc::mbar_wait(o_free, (it & 1) ^ 1);   // the previous item's O has been read out
-        for (int b = 0; b < nkb; ++b) {
-          const uint32_t buf = b & 1;
-          tc::mbar_wait(p_full + buf, uses[buf] & 1);
-          ++uses[buf];
-          tc::tc_fence_after();
-          const uint64_t dp = tc::make_kmajor_sw128_desc(tc::smem_u32(sP + buf * kAtP));
-          const uint64_t dv = make_mnmajor_sw128_desc(tc::smem_u32(sV + b * 8192));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // 16 keys per MMA: +32 B in P's rows, +16 rows (2048 B) in V
-            tc::umma_bf16(tmem_base + kOCol, dp + k * tc::kDescKStep, dv + k * (2048 >> 4), idesc_pv, (b | k) != 0);
-          tc::umma_commit(p_empty + buf);
-        }
-        tc::umma_commit(v_empty);
-        tc::umma_commit(o_full);
-        ++it;
-      }
+      AttnMma m;
+      m.q_full = q_full; m.q_empty = q_empty; m.k_full = k_full; m.k_empty = k_empty;
+      m.v_full = v_full; m.v_empty = v_empty; m.s_full = s_full; m.s_free = s_free;
+      m.o_full = o_full; m.o_free = o_free; m.p_full = p_full; m.p_empty = p_empty;
+      m.sQ = tc::smem_u32(sQ); m.sK = tc::smem_u32(sK); m.sV = tc::smem_u32(sV); m.sP = tc::smem_u32(sP);
+      m.tmem_base = tmem_base;
+      m.trace = p.trace;
+      m.run(w);
     }
-  } else {
-    // ============================ softmax + epilogue ============================
-    const int grp = (warp - 2) >> 2;           // 0: even key blocks, 1: odd key blocks
+  } else if (warp < 6) {
+    // ============================ epilogue ============================
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;         // row of the query block == TMEM lane
-    const int st = threadIdx.x - 64;           // 0..255 among the softmax threads
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-    constexpr float kLog2e = 1.4426950408889634f;
-    constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64) * log2(e)
-    float* sMax = sXch;                        // [2][128]
-    float* sSum = sXch + 256;                  // [2][128]
-    uint32_t it = 0, u = 0;                    // u: uses of this group's P buffer
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int qb = item % p.nqb, h = (item / p.nqb) % kHeads, s = item / (p.nqb * kHeads);
-      const int t0 = cu[s], L = cu[s + 1] - t0;
-      if (qb * 128 >= L) continue;
-      const int Lp = (L + 63) & ~63;
-      const int nkb = Lp >> 6;
-      const int q0 = qb * 128;
-      const int i = min(q0 + r, L - 1);        // rows past the end mirror the last row, never stored
-      const float* rel_i = sRel + h * kAtRelStride + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
-      tc::mbar_wait(s_full, it & 1);
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kOCol;
+    uint32_t e = 0;                            // items done
+    while (w.advance()) {
+      const uint32_t par = e & 1, ph = (e >> 1) & 1;
+      const bool tr = lane == 0 && quarter == 0;
+      if (tr) attn_trace(p.trace, 4, e, 0);
+      tc::mbar_wait_sleep(st_full + par, ph, 300);
+      const float* st = sStat + par * 4 * 128;
+      const float inv = 1.f / ((st[r] + st[128 + r]) + (st[256 + r] + st[384 + r]));
+      if (tr) attn_trace(p.trace, 4, e, 1);
+      tc::mbar_wait_sleep(o_full + par, ph, 100);
       tc::tc_fence_after();
-      // ---- pass 1: maximum of the raw scores over this group's real keys ----
-      float mx = -INFINITY;
-      for (int b = grp; b < nkb; b += 2) {
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c = b * 64 + hf * 32;
-          if (c >= L) break;
-          uint32_t v[32];
-          tc::tmem_ld_32x32(lane_addr + (uint32_t)c, v);
-          tc::tmem_ld_wait();
-          if (c + 32 <= L) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c + j < L) mx = fmaxf(mx, __uint_as_float(v[j]));
-          }
-        }
-      }
-      sMax[grp * 128 + r] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mx = fmaxf(mx, sMax[(grp ^ 1) * 128 + r]);
-      // upper bound of the row maximum of (s/8 + bias) in the log2 domain
-      const float m_hat = mx * kScale + __ldg(p.rel_max + h) * kLog2e;
-      // ---- pass 2: probabilities of this group's blocks as the A operand of P V ----
-      float sum = 0.f;
-      for (int b = grp; b < nkb; b += 2, ++u) {
-        tc::mbar_wait(p_empty + grp, (u & 1) ^ 1);
-        uint8_t* prow = sP + grp * kAtP + r * 128;
-        uint32_t vv[2][32];
-        tc::tmem_ld_32x32(lane_addr + (uint32_t)(b * 64), vv[0]);
-        tc::tmem_ld_32x32(lane_addr + (uint32_t)(b * 64 + 32), vv[1]);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c = b * 64 + hf * 32;
-          const uint32_t (&v)[32] = vv[hf];
-          float pr[32];
-          if (c + 32 <= L) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              pr[j] = ex2_approx(fmaf(__uint_as_float(v[j]), kScale, rel_i[c + j] - m_hat));
-              sum += pr[j];
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float e = ex2_approx(fmaf(__uint_as_float(v[j]), kScale, rel_i[c + j] - m_hat));
-              pr[j] = (c + j < L) ? e : 0.f;
-              sum += pr[j];
-            }
-          }
-#pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 o;
-            o.x = pack_bf16(pr[q4 * 8 + 0], pr[q4 * 8 + 1]);
-            o.y = pack_bf16(pr[q4 * 8 + 2], pr[q4 * 8 + 3]);
-            o.z = pack_bf16(pr[q4 * 8 + 4], pr[q4 * 8 + 5]);
-            o.w = pack_bf16(pr[q4 * 8 + 6], pr[q4 * 8 + 7]);
-            const int chunk = hf * 4 + q4;
-            *reinterpret_cast<uint4*>(prow + ((chunk ^ (r & 7)) << 4)) = o;
-          }
-        }
-        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core
-        tc::tc_fence_before();
-        tc::mbar_arrive(p_full + grp);
-      }
-      // S of this item is dead for this warp: the next item's Q K^T may overwrite it once all 8 agree
+      if (tr) attn_trace(p.trace, 4, e, 2);
+      const int row = w.qb * 128 + r;
+      __nv_bfloat16* dst = p.ctx + (size_t)(w.t0 + row) * kHidden + w.h * kHeadDim;
+      uint32_t a[32], b[32];
+      tc::tmem_ld_32x32(lane_addr + par * kHeadDim, a);
+      tc::tmem_ld_32x32(lane_addr + par * kHeadDim + 32, b);
+      tc::tmem_ld_wait();
+      // O[par] is in registers (the sums were read above): the item after next may reuse both
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(s_free);
-      sSum[grp * 128 + r] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      const float inv = 1.f / (sum + sSum[(grp ^ 1) * 128 + r]);
-      // ---- epilogue: group g writes head-dim columns [32 g, 32 g + 32) ----
-      tc::mbar_wait(o_full, it & 1);
-      tc::tc_fence_after();
-      {
-        uint32_t v[32];
-        tc::tmem_ld_32x32(lane_addr + kOCol + grp * 32, v);
-        tc::tmem_ld_wait();
-        if (q0 + r < L) {
-          __nv_bfloat16* dst = p.ctx + (size_t)(t0 + q0 + r) * kHidden + h * kHeadDim + grp * 32;
+      if (lane == 0) tc::mbar_arrive(o_free + par);
+      if (row < w.L) {
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint4 o;
-            o.x = pack_bf16(__uint_as_float(v[q4 * 8 + 0]) * inv, __uint_as_float(v[q4 * 8 + 1]) * inv);
-            o.y = pack_bf16(__uint_as_float(v[q4 * 8 + 2]) * inv, __uint_as_float(v[q4 * 8 + 3]) * inv);
-            o.z = pack_bf16(__uint_as_float(v[q4 * 8 + 4]) * inv, __uint_as_float(v[q4 * 8 + 5]) * inv);
-            o.w = pack_bf16(__uint_as_float(v[q4 * 8 + 6]) * inv, __uint_as_float(v[q4 * 8 + 7]) * inv);
-            *reinterpret_cast<uint4*>(dst + q4 * 8) = o;
-          }
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]) * inv, __uint_as_float(a[q4 * 8 + 1]) * inv);
+          o.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]) * inv, __uint_as_float(a[q4 * 8 + 3]) * inv);
+          o.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]) * inv, __uint_as_float(a[q4 * 8 + 5]) * inv);
+          o.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]) * inv, __uint_as_float(a[q4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + q4 * 8) = o;
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(b[q4 * 8 + 0]) * inv, __uint_as_float(b[q4 * 8 + 1]) * inv);
+          o.y = pack_bf16(__uint_as_float(b[q4 * 8 + 2]) * inv, __uint_as_float(b[q4 * 8 + 3]) * inv);
+          o.z = pack_bf16(__uint_as_float(b[q4 * 8 + 4]) * inv, __uint_as_float(b[q4 * 8 + 5]) * inv);
+          o.w = pack_bf16(__uint_as_float(b[q4 * 8 + 6]) * inv, __uint_as_float(b[q4 * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = o;
         }
       }
-      tc::tc_fence_before();   // O reads are ordered before the next item's first P V
+      if (tr) attn_trace(p.trace, 4, e, 3);
+      ++e;
+    }
+  } else {
+    // ============================ softmax groups ============================
+    const int g = (warp - 6) / kAtGW;                          // key half
+    const int ch = kAtHf == 1 ? ((warp - 6) >> 2) & 1 : 0;     // first 32-column piece of a key block owned by this warp
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                         // row of the query block == TMEM lane
+    const int slot = g * 2 + ch;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
+                               static_cast<uint32_t>(g * kAtHalfCols + ch * 32);
+    constexpr float kLog2e = 1.4426950408889634f;
+    constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64) * log2(e)
+    uint32_t n = 0, ng = 0, np = 0;            // items / items with keys in this half / P blocks of this group
+    while (w.advance()) {
+      const int nb = g ? w.nb1 : w.nb0;
+      const int L = w.L;
+      const int key0 = (g ? w.nb0 : 0) * 64 + ch * 32;   // first key of this thread's columns in block 0
+      const int i = min(w.qb * 128 + r, L - 1);          // rows past the end mirror the last row, never stored
+      const float* rel_i = sRel + w.h * kAtRelStride + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
+      const uint32_t par = n & 1;
+      const bool tr = lane == 0 && ch == 0 && quarter == 0 && g == 0;
+      if (tr) attn_trace(p.trace, 2 + g, n, 0);
+      uint32_t v[kAtHf][32];
+      // ---- pass 1: maximum of the raw scores over this thread's real keys ----
+      float mx = -INFINITY;
+      if (nb > 0) {
+        tc::mbar_wait(s_full + g, ng & 1);
+        tc::tc_fence_after();
+        if (tr) attn_trace(p.trace, 2 + g, n, 1);
+        // blocks in descending order: block 0's scores are still in registers when pass 2 starts
+        for (int lb = nb - 1; lb >= 0; --lb) {
+          const int c0 = key0 + lb * 64;
+          if (c0 >= L) continue;
+#pragma unroll
+          for (int hf = 0; hf < kAtHf; ++hf)
+            if (c0 + hf * 32 < L) tc::tmem_ld_32x32(lane_addr + (uint32_t)(lb * 64 + hf * 32), v[hf]);
+          tc::tmem_ld_wait();
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+          for (int hf = 0; hf < kAtHf; ++hf) {
+            const int c = c0 + hf * 32;
+            if (c + 32 <= L) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[hf][j]));
+            } else if (c < L) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c + j < L) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[hf][j]));
+            }
+          }
+          mx = fmaxf(mx, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        }
+      }
+      // one row maximum for the whole item: both halves then accumulate into the same O
+      float* xm = sXmax + par * 4 * 128;
+      xm[slot * 128 + r] = mx;
+      if (kAtHf == 2) xm[(slot + 1) * 128 + r] = mx;
+      if (tr) attn_trace(p.trace, 2 + g, n, 2);
+      asm volatile("bar.sync 1, %0;" ::"n"(2 * kAtGW * 32) : "memory");
+      if (tr) attn_trace(p.trace, 2 + g, n, 3);
+      mx = fmaxf(fmaxf(xm[r], xm[128 + r]), fmaxf(xm[256 + r], xm[384 + r]));
+      // upper bound of the row maximum of (s/8 + bias) in the log2 domain
+      const float m_hat = fmaf(mx, kScale, sRelMax[w.h]);
+      // ---- pass 2: probabilities, one 64-key block at a time, as the A operand of P V ----
+      // Packed fp32x2 arithmetic (two keys per instruction).  Block 0's scores are left over from
+      // pass 1; the scores of block lb+1 are requested as soon as block lb's exponentials are done,
+      // so TMEM latency stays off the critical path.
+      uint64_t sum2 = 0ull;
+      const uint64_t scale2 = f32x2_pack(kScale, kScale);
+      const uint64_t nm2 = f32x2_pack(-m_hat, -m_hat);
+      for (int lb = 0; lb < nb; ++lb, ++np) {
+        const uint32_t buf = np & 1;
+        const int c0 = key0 + lb * 64;
+        tc::mbar_wait(p_empty + g * 2 + buf, ((np >> 1) & 1) ^ 1);
+        uint8_t* prow = sP + (g * 2 + buf) * kAtP + r * 128;
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int hf = 0; hf < kAtHf; ++hf) {
+          const int c = c0 + hf * 32;
+          const int piece = ch + hf;
+          if (c + 32 <= L) {   // warp-uniform
+            const float* rel_c = rel_i + c;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j2 = 0; j2 < 4; ++j2) {
+                const int j = q4 * 4 + j2;
+                const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(v[hf][2 * j]), __uint_as_float(v[hf][2 * j + 1])),
+                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j], rel_c[2 * j + 1]), nm2));
+                float t0, t1;
+                f32x2_unpack(t, t0, t1);
+                const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
+                sum2 = f32x2_add(sum2, f32x2_pack(e0, e1));
+                pk[j2] = pack_bf16(e0, e1);
+              }
+              *reinterpret_cast<uint4*>(prow + (((piece * 4 + q4) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else if (c < L) {
+            const float* rel_c = rel_i + c;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int j2 = 0; j2 < 4; ++j2) {
+                const int j = q4 * 4 + j2;
+                const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(v[hf][2 * j]), __uint_as_float(v[hf][2 * j + 1])),
+                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j], rel_c[2 * j + 1]), nm2));
+                float t0, t1;
+                f32x2_unpack(t, t0, t1);
+                const float e0 = (c + 2 * j < L) ? ex2_approx(t0) : 0.f;
+                const float e1 = (c + 2 * j + 1 < L) ? ex2_approx(t1) : 0.f;
+                sum2 = f32x2_add(sum2, f32x2_pack(e0, e1));
+                pk[j2] = pack_bf16(e0, e1);
+              }
+              *reinterpret_cast<uint4*>(prow + (((piece * 4 + q4) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              *reinterpret_cast<uint4*>(prow + (((piece * 4 + q4) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        if (lb == nb - 1) {   // the last read of S_g has landed: the next item's Q K_g^T may overwrite it
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(s_free + g);
+        } else {
+#pragma unroll
+          for (int hf = 0; hf < kAtHf; ++hf)
+            if (c0 + 64 + hf * 32 < L) tc::tmem_ld_32x32(lane_addr + (uint32_t)((lb + 1) * 64 + hf * 32), v[hf]);
+        }
+        fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(p_full + g * 2 + buf);
+        if (tr) attn_trace(p.trace, 2 + g, n, 4 + lb);
+      }
+      float sum_lo, sum_hi;
+      f32x2_unpack(sum2, sum_lo, sum_hi);
+      // row sums for the epilogue warps (a half without keys contributes 0); the slot was last used
+      // by item n - 2, which the epilogue has finished once it has released that item's O buffer
+      tc::mbar_wait(o_free + par, ((n >> 1) & 1) ^ 1);
+      sStat[(par * 4 + slot) * 128 + r] = sum_lo + sum_hi;
+      if (kAtHf == 2) sStat[(par * 4 + slot + 1) * 128 + r] = 0.f;
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(o_free);
-      ++it;
+      if (lane == 0) tc::mbar_arrive(st_full + par);
+      if (nb > 0) ++ng;
+      ++n;
     }
   }
   __syncwarp();
@@ -324,7 +546,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // Host launcher.  qkv: [T, 2304] bf16 packed (q | k | v).
 static int attention_tc_launch(const __nv_bfloat16* qkv, int T, const int32_t* cu_dev, int n_seq, int max_len,
                                const float* rel_table, const float* rel_max, int rel_half, __nv_bfloat16* ctx,
-                               int n_sm, cudaStream_t st) {
+                               int n_sm, cudaStream_t st, long long* trace = nullptr) {
+  CSS_REQUIRE(max_len <= kAttnTcMaxLen, "attention_tc: sequence of %d tokens exceeds %d", max_len, kAttnTcMaxLen);
   CUtensorMap tq, tkv;
   CSS_CHECK(encode_tmap_bf16_2d(&tq, qkv, (uint64_t)T, 3 * kHidden, 3 * kHidden, 128, 64));
   CSS_CHECK(encode_tmap_bf16_2d(&tkv, qkv, (uint64_t)T, 3 * kHidden, 3 * kHidden, 64, 64));
@@ -341,10 +564,10 @@ static int attention_tc_launch(const __nv_bfloat16* qkv, int T, const int32_t* c
   p.rel_max = rel_max;
   p.rel_half = rel_half;
   p.n_seq = n_seq;
-  p.nqb = (max_len + 127) / 128;
   p.ctx = ctx;
-  const int items = n_seq * kHeads * p.nqb;
-  const int grid = items < n_sm ? items : n_sm;
+  p.trace = trace;
+  const int units = n_seq * kHeads;
+  const int grid = units < n_sm ? units : n_sm;
   attention_tc_kernel<<<grid, kAttnTcThreads, kAtSmem, st>>>(tq, tkv, p);
   CSS_LAUNCHED();
   return CSS_OK;

@@ -505,10 +505,27 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
     DevBuf maxd;
     CSS_CHECK(maxd.alloc(kHeads * 4));
     CSS_CUDA(cudaMemcpy(maxd.p, tmax.data(), kHeads * 4, cudaMemcpyHostToDevice));
-    CSS_CHECK(attention_tc_launch((const __nv_bfloat16*)q16.p, T, (const int32_t*)cud.p, n_seq, max_len,
-                                  (const float*)reld.p, (const float*)maxd.p, rel_half, (__nv_bfloat16*)c16.p,
-                                  sm_count(device), st));
+    // CSS_ATTN_TRACE=<file>: dump CTA 0's clock64 stamps [5 roles][128 items][8 tags] (profiling aid)
+    const char* trace_path = getenv("CSS_ATTN_TRACE");
+    DevBuf traced;
+    const size_t trace_n = 5 * 128 * 8;
+    if (trace_path) {
+      CSS_CHECK(traced.alloc(trace_n * 8));
+      CSS_CUDA(cudaMemset(traced.p, 0, trace_n * 8));
+    }
+    for (int rep = 0; rep < (trace_path ? 2 : 1); ++rep)
+      CSS_CHECK(attention_tc_launch((const __nv_bfloat16*)q16.p, T, (const int32_t*)cud.p, n_seq, max_len,
+                                    (const float*)reld.p, (const float*)maxd.p, rel_half, (__nv_bfloat16*)c16.p,
+                                    sm_count(device), st, (long long*)traced.p));
     CSS_CUDA(cudaStreamSynchronize(st));
+    if (trace_path) {
+      std::vector<long long> host(trace_n);
+      CSS_CUDA(cudaMemcpy(host.data(), traced.p, trace_n * 8, cudaMemcpyDeviceToHost));
+      if (FILE* f = fopen(trace_path, "wb")) {
+        fwrite(host.data(), 8, trace_n, f);
+        fclose(f);
+      }
+    }
   } else {
     attention_kernel<<<grid, kAttnThreads, smem, st>>>((const __nv_bfloat16*)q16.p, (const int32_t*)cud.p,
                                                        (const float*)reld.p, rel_half, (__nv_bfloat16*)c16.p);

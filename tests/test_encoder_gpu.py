@@ -53,7 +53,8 @@ def test_tcgen05_gemm_vs_fp32(native, M, N, K, gelu, kernel):
 
 # ------------------------------------------------------------- attention
 @pytest.mark.parametrize("tc", ["1", "0"])   # tcgen05 kernel / mma.sync kernel
-@pytest.mark.parametrize("lens", [[1], [2, 3], [64], [65, 63], [128, 5, 200], [384], [129, 448, 300], [512, 17]])
+@pytest.mark.parametrize("lens", [[1], [2, 3], [64], [65, 63], [128, 5, 200], [384], [129, 448, 300], [512, 17],
+                                  [384, 383, 321, 320, 257, 193, 192, 129, 100, 7] * 20, [384] * 40])
 def test_attention_vs_fp32(native, lens, tc, monkeypatch):
     import torch
     monkeypatch.setenv("CSS_ATTN_TC", tc)
@@ -79,7 +80,7 @@ def test_attention_vs_fp32(native, lens, tc, monkeypatch):
         ref = (p @ v).transpose(0, 1).reshape(L, 768).numpy()
         err = np.abs(ctx[cu[s]:cu[s + 1]] - ref)
         # P is rounded to bf16 before the PV product, the output once more
-        assert err.max() < 3e-2, f"seq {s} (L={L}): max err {err.max():.4g}"
+        assert err.max() < 4e-2, f"seq {s} (L={L}): max err {err.max():.4g}"
         assert err.mean() < 3e-3
 
 
