@@ -200,7 +200,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--only", default="", choices=["", "encode", "batched"], help="profiling aid: run one extra leg only")
     ap.add_argument("--full", action="store_true", help="also run the 10M-row filtered leg")
-    ap.add_argument("--encode-seqs", type=int, default=256)
+    ap.add_argument("--encode-seqs", type=int, default=296,
+                    help="chunks per encoder pass (296 x 384 tokens = 148 SMs x 768: every kernel's tile count is a multiple of the SM count)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

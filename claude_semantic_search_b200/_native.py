@@ -121,6 +121,8 @@ SIGNATURES = {
     "css_encoder_max_seq_len": (c_int, [c_void_p]),
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
     "css_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "css_debug_gemm_resid_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                        ctypes.c_float, c_int, c_int, c_void_p]),
     "css_debug_attention": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "css_encoder_encode_device": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p,
                                           c_void_p]),

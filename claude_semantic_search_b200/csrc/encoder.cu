@@ -5,11 +5,9 @@
 //   per layer (12x):
 //     E2  x * Wqkv^T + b                       -> qkv  bf16 [T, 2304]   tcgen05 GEMM
 //     E3  softmax(q k^T / 8 + rel_bias) v      -> ctx  bf16 [T, 768]
-//     E4  ctx * Wo^T + b + x                   -> pre  f32  [T, 768]    tcgen05 GEMM
-//     E5  LayerNorm(pre)                       -> x1   bf16 [T, 768]
+//     E4  LayerNorm(ctx * Wo^T + b + x)        -> x1   bf16 [T, 768]    tcgen05 GEMM, LayerNorm in the epilogue
 //     E6a gelu(x1 * W1^T + b)                  -> h    bf16 [T, 3072]   tcgen05 GEMM
-//     E6b h * W2^T + b + x1                    -> pre  f32  [T, 768]    tcgen05 GEMM
-//     E5  LayerNorm(pre)                       -> x    bf16 [T, 768]
+//     E6b LayerNorm(h * W2^T + b + x1)         -> x    bf16 [T, 768]    tcgen05 GEMM, LayerNorm in the epilogue
 //   E7  mean over tokens, L2 normalise         -> out  f32  [n_seq, 768]
 #include "encoder_kernels.cuh"
 #include "attention_tc.cuh"
@@ -44,7 +42,7 @@ struct css_encoder {
   std::vector<void*> owned;  // every device allocation, freed on destroy
   // workspace
   __nv_bfloat16 *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
-  float* pre = nullptr;
+  float2* ln_stats = nullptr;   // [max_tokens][3][2] partial row statistics written by the FFN-down epilogue
   int32_t *ids_dev = nullptr, *cu_dev = nullptr;
   float* out_dev = nullptr;
   int64_t max_seqs = 0;
@@ -140,24 +138,21 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       CSS_LAUNCHED();
     }
     {
-      EpiBiasResidF32::Params p{e->pre, w.bo, e->x, kHidden};
-      CSS_CHECK((gemm::run<256, EpiBiasResidF32>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
-                                                   e->n_sm, st)));
+      EpiResidLN<true>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, nullptr};
+      CSS_CHECK((gemm::run<256, EpiResidLN<true>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p, e->n_sm,
+                                                    st)));
     }
-    layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln1_w, w.ln1_b, c.layer_norm_eps,
-                                                                  e->x1);
-    CSS_LAUNCHED();
     {
       EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn};
       CSS_CHECK((gemm::run<256, EpiBiasBf16<true>>(e->x1, kHidden, w.w1, kHidden, T, kFfn, kHidden, 0, p, e->n_sm,
                                                      st)));
     }
     {
-      EpiBiasResidF32::Params p{e->pre, w.b2, e->x1, kHidden};
-      CSS_CHECK((gemm::run<256, EpiBiasResidF32>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
+      EpiResidLN<false>::Params p{e->x, w.b2, e->x1, w.ln2_w, w.ln2_b, c.layer_norm_eps, e->ln_stats};
+      CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
     }
-    layernorm_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->pre, T, w.ln2_w, w.ln2_b, c.layer_norm_eps,
-                                                                  e->x);
+    ln_apply_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->x, e->ln_stats, 6, T, w.ln2_w, w.ln2_b,
+                                                                 c.layer_norm_eps);
     CSS_LAUNCHED();
   }
   pool_normalize_kernel<<<(unsigned)n_seq, 256, 0, st>>>(e->x, cu_dev, normalize, out_dev);
@@ -228,7 +223,9 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   e->device = device;
   e->n_sm = sm_count(device);
   e->max_seq = std::min(kMaxSeq, cfg->max_position - cfg->pad_token_id - 1);
-  if (max_tokens <= 0) max_tokens = 128 * 1024;
+  // default pass size: 148 SMs x 768 tokens = 296 chunks of 384 tokens -> 444 row panels of 256, 3996 / 5328 / 1332
+  // GEMM tiles and 3552 attention units, all multiples of the 74 CTA pairs / 148 CTAs (no tail wave)
+  if (max_tokens <= 0) max_tokens = (int64_t)e->n_sm * 768;
   max_tokens = std::max<int64_t>(max_tokens, e->max_seq);
   max_tokens = (max_tokens + 127) / 128 * 128;
   e->max_tokens = max_tokens;
@@ -320,7 +317,7 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   if ((rc = enc_alloc(e, &e->qkv, T * 3 * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ctx, T * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->h, T * kFfn)) != CSS_OK) return fail(rc);
-  if ((rc = enc_alloc(e, &e->pre, T * H)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->ln_stats, T * 6)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ids_dev, T)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->cu_dev, (size_t)e->max_seqs + 1)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->out_dev, (size_t)e->max_seqs * H)) != CSS_OK) return fail(rc);
@@ -464,6 +461,56 @@ int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int
     EpiBiasBf16<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
     rc = two ? gemm::launch2<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
              : gemm::launch<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+  }
+  CSS_CHECK(rc);
+  const int64_t n = (int64_t)M * N;
+  bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)o16.p, (float*)o32.p, n);
+  CSS_LAUNCHED();
+  CSS_CUDA(cudaMemcpyAsync(out, o32.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CSS_CUDA(cudaStreamSynchronize(st));
+  return CSS_OK;
+}
+
+int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, const float* resid, const float* gamma,
+                            const float* beta, int M, int K, float eps, int mode, int device, float* out) {
+  // mode bit 0: 2-CTA tiles; bit 1: LayerNorm fused into the epilogue (panel order), else epilogue
+  // statistics + ln_apply_kernel
+  CSS_REQUIRE(A && B && bias && resid && gamma && beta && out, "NULL buffer");
+  CSS_CHECK(ensure_device(device));
+  DeviceGuard g(device);
+  cudaStream_t st = nullptr;
+  const int N = kHidden;
+  const bool two_cta = (mode & 1) != 0, fused = (mode & 2) != 0;
+  DevBuf a32, a16, b32, b16, r32, r16, biasd, gd, bd, o16, o32, statd;
+  CSS_CHECK(statd.alloc((size_t)M * 6 * sizeof(float2)));
+  CSS_CHECK(to_bf16_dev(A, (size_t)M * K, a32, a16, st));
+  CSS_CHECK(to_bf16_dev(B, (size_t)N * K, b32, b16, st));
+  CSS_CHECK(to_bf16_dev(resid, (size_t)M * N, r32, r16, st));
+  CSS_CHECK(biasd.alloc((size_t)N * 4));
+  CSS_CHECK(gd.alloc((size_t)N * 4));
+  CSS_CHECK(bd.alloc((size_t)N * 4));
+  CSS_CUDA(cudaMemcpyAsync(biasd.p, bias, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CSS_CUDA(cudaMemcpyAsync(gd.p, gamma, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CSS_CUDA(cudaMemcpyAsync(bd.p, beta, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+  CSS_CHECK(o16.alloc((size_t)M * N * 2));
+  CSS_CHECK(o32.alloc((size_t)M * N * 4));
+  CSS_CUDA(cudaMemsetAsync(o16.p, 0xff, (size_t)M * N * 2, st));
+  int rc;
+  if (fused) {
+    EpiResidLN<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, (const __nv_bfloat16*)r16.p,
+                               (const float*)gd.p, (const float*)bd.p, eps, nullptr};
+    rc = two_cta ? gemm::launch2<256, EpiResidLN<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
+                 : gemm::launch<256, EpiResidLN<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+  } else {
+    EpiResidLN<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, (const __nv_bfloat16*)r16.p,
+                                (const float*)gd.p, (const float*)bd.p, eps, (float2*)statd.p};
+    rc = two_cta ? gemm::launch2<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
+                 : gemm::launch<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
+    if (rc == CSS_OK) {
+      ln_apply_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>((__nv_bfloat16*)o16.p, (const float2*)statd.p, 6, M,
+                                                               (const float*)gd.p, (const float*)bd.p, eps);
+      CSS_LAUNCHED();
+    }
   }
   CSS_CHECK(rc);
   const int64_t n = (int64_t)M * N;

@@ -2,7 +2,7 @@
 // main loop (gemm_tc.cuh):
 //   E1  token + position embedding gather, LayerNorm            modeling_mpnet.py:72-96
 //   E3  multi-head attention with relative-position bias        modeling_mpnet.py:144-185,322-360
-//   E5  LayerNorm over (GEMM + bias + residual)                 modeling_mpnet.py:206,242
+//   E5  LayerNorm over (GEMM + bias + residual): fused GEMM epilogue   modeling_mpnet.py:206,242
 //   E7  masked mean pooling + L2 normalisation                  sentence-transformers Pooling / Normalize
 //   GEMM epilogue functors: +bias, +bias+GELU(erf), +bias+residual
 //
@@ -104,20 +104,6 @@ static __global__ void embed_ln_kernel(const int32_t* __restrict__ ids, const in
   }
   warp_layernorm_768(v, gamma, beta, eps, lane);
   store_row_bf16(x + (size_t)t * kHidden, v, lane);
-}
-
-// E5: y[t] = LayerNorm(pre[t]) ; pre already holds GEMM + bias + residual in fp32.
-static __global__ void layernorm_kernel(const float* __restrict__ pre, int T, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y) {
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
-  const float4* r = reinterpret_cast<const float4*>(pre + (size_t)t * kHidden);
-  float4 v[6];
-#pragma unroll
-  for (int j = 0; j < 6; ++j) v[j] = ld_stream_f4(r + j * 32 + lane);
-  warp_layernorm_768(v, gamma, beta, eps, lane);
-  store_row_bf16(y + (size_t)t * kHidden, v, lane);
 }
 
 // E7: out[s] = normalise(mean over tokens of x).  One CTA (256 threads) per sequence,
@@ -360,6 +346,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <bool kGelu>
 struct EpiBiasBf16 {
   static constexpr bool kMasksColumns = false;
+  static constexpr bool kPanel = false;
   static constexpr int kRowBytes = 80;                 // 64 B of payload + 16 B pad: conflict-free
   static constexpr int kStageBytes = 32 * kRowBytes;   // per epilogue warp
   struct Params {
@@ -406,74 +393,202 @@ struct EpiBiasBf16 {
   }
   __device__ __forceinline__ void chunk_begin() {}
   __device__ __forceinline__ void prefetch(int, int, int, int) {}
-  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
 
-// out_f32[m, n] = acc + bias[n] + resid_bf16[m, n]   (attention output / FFN down projections;
-// the LayerNorm kernel consumes out_f32)
-struct EpiBiasResidF32 {
+// y[m, :] = LayerNorm(acc[m, :] + bias + resid[m, :]) * gamma + beta  (attention output / FFN down
+// projections, N = 768).  Per chunk, v = acc + bias + resid in fp32; the thread (= one row) adds v
+// and v^2 to its row statistics; v goes out as bf16, staged through shared memory for full-sector
+// stores.  The fp32 pre-LayerNorm activation never exists in memory.
+//
+// kFused = true (attention output projection, K = 768): the GEMM runs in panel order (a CTA
+//   visits the three 256-column blocks of its rows back to back); after the third block the two
+//   column halves of a row exchange their statistics through shared memory, then each warp
+//   re-reads 16 of the CTA's 128 rows (L2 hits: written microseconds ago), normalises them and
+//   rewrites them in place.  No LayerNorm kernel, no device-scope fence.
+// kFused = false (FFN down projection, K = 3072): panel order would make every CTA pair stream
+//   its own 1.5 MB A panel three times with 116 MB of panels live -- more than the L2 holds
+//   (measured: 478 us against 381 us) -- so the tiles keep the L2-friendly order, the partial
+//   statistics go to stats[row][tile][column half] and ln_apply_kernel finishes the rows
+//   (1.5 KB + 48 B read per token instead of the 3 KB fp32 row of a plain LayerNorm kernel).
+template <bool kFused>
+struct EpiResidLN {
   static constexpr bool kMasksColumns = false;
-  static constexpr int kRowBytes = 144;                // 128 B of payload + 16 B pad
-  static constexpr int kStageBytes = 32 * kRowBytes;
+  static constexpr bool kPanel = kFused;
+  static constexpr int kRowBytes = 80;                           // 64 B of payload + 16 B pad
+  static constexpr int kWarpStage = 32 * kRowBytes;              // bf16 staging per epilogue warp
+  static constexpr int kStatBytes = kFused ? 2 * 2 * 128 * 2 * 4 : 0;  // [panel parity][column half][row][sum, sumsq]
+  static constexpr int kStageBytes = kWarpStage + kStatBytes / 8;  // per epilogue warp (8 warps share the statistics)
   struct Params {
-    float* out;
-    const float* bias;
-    const __nv_bfloat16* resid;
-    int ld;  // leading dimension of out and resid
+    __nv_bfloat16* out;            // [M, 768]
+    const float* bias;             // [768]
+    const __nv_bfloat16* resid;    // [M, 768]
+    const float* gamma;
+    const float* beta;
+    float eps;
+    float2* stats;                 // !kFused: [M][3 tiles][2 column halves] (sum, sum of squares)
   };
   const Params& p;
   uint8_t* stage;
-  __device__ EpiBiasResidF32(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
-  // Residual rows of the NEXT chunk are requested one chunk ahead (and across tiles, during
-  // the wait for the next accumulator): a DRAM round trip per chunk sat on the critical path
-  // of every tile in the round-1 profile (long-scoreboard stalls on the bf16 unpack).
-  uint2 rr_next[8], rr[8];
+  float* sstats;
+  int ew, lane_;
+  int my_row = 0;                  // absolute row of this thread's accumulator lane in the current tile
+  uint32_t parity = 0;
+  float sum = 0.f, sq = 0.f;
+  uint4 rr_next[4], rr[4];         // residual of this thread's row, 32 columns, one chunk ahead
+  __device__ EpiResidLN(const Params& p_, int epi_thread, uint8_t* stage_) : p(p_) {
+    ew = epi_thread >> 5;
+    lane_ = epi_thread & 31;
+    uint8_t* base = stage_ - ew * kStageBytes;
+    stage = base + ew * kWarpStage;
+    sstats = reinterpret_cast<float*>(base + 8 * kWarpStage);
+  }
   __device__ __forceinline__ void chunk_begin() {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) rr[it] = rr_next[it];
+    for (int i = 0; i < 4; ++i) rr[i] = rr_next[i];
   }
   __device__ __forceinline__ void prefetch(int m_warp, int lane, int M, int n0) {
-    const int piece = lane & 7;
+    const int m = m_warp + lane;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int m = m_warp + it * 4 + (lane >> 3);
-      rr_next[it] = make_uint2(0u, 0u);
-      if (m < M) rr_next[it] = __ldg(reinterpret_cast<const uint2*>(p.resid + (size_t)m * p.ld + n0 + piece * 4));
+    for (int i = 0; i < 4; ++i) rr_next[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (m < M) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) rr_next[i] = __ldg(src + i);
     }
   }
   __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
-    const int piece = lane & 7;
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-    float4* srow = reinterpret_cast<float4*>(stage + lane * kRowBytes);
+    uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
+    my_row = m_warp + lane;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 b = __ldg(b4 + g);
-      float4 o;
-      o.x = __uint_as_float(v[g * 4 + 0]) + b.x;
-      o.y = __uint_as_float(v[g * 4 + 1]) + b.y;
-      o.z = __uint_as_float(v[g * 4 + 2]) + b.z;
-      o.w = __uint_as_float(v[g * 4 + 3]) + b.w;
+    for (int g = 0; g < 4; ++g) {
+      const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
+      const uint4 r4 = rr[g];
+      float f[8];
+      f[0] = __uint_as_float(v[g * 8 + 0]) + ba.x + bf16_lo(r4.x); f[1] = __uint_as_float(v[g * 8 + 1]) + ba.y + bf16_hi(r4.x);
+      f[2] = __uint_as_float(v[g * 8 + 2]) + ba.z + bf16_lo(r4.y); f[3] = __uint_as_float(v[g * 8 + 3]) + ba.w + bf16_hi(r4.y);
+      f[4] = __uint_as_float(v[g * 8 + 4]) + bb.x + bf16_lo(r4.z); f[5] = __uint_as_float(v[g * 8 + 5]) + bb.y + bf16_hi(r4.z);
+      f[6] = __uint_as_float(v[g * 8 + 6]) + bb.z + bf16_lo(r4.w); f[7] = __uint_as_float(v[g * 8 + 7]) + bb.w + bf16_hi(r4.w);
+      sum += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
+      sq += ((f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3])) +
+            ((f[4] * f[4] + f[5] * f[5]) + (f[6] * f[6] + f[7] * f[7]));
+      uint4 o;
+      o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+      o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
       srow[g] = o;
     }
     __syncwarp();
-    // 8 lanes per row (8 x 16 B out, 8 x 8 B residual in), 4 rows per instruction
+    // 4 lanes per row (4 x 16 B = the row's 64 B), 8 rows per instruction
+    const int piece = lane & 3;
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3);
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
       const int m = m_warp + r;
       if (m < M) {
-        float4 o = *reinterpret_cast<const float4*>(stage + r * kRowBytes + piece * 16);
-        o.x += bf16_lo(rr[it].x); o.y += bf16_hi(rr[it].x);
-        o.z += bf16_lo(rr[it].y); o.w += bf16_hi(rr[it].y);
-        *reinterpret_cast<float4*>(p.out + (size_t)m * p.ld + n0 + piece * 4) = o;
+        const uint4 o = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + piece * 16);
+        *reinterpret_cast<uint4*>(p.out + (size_t)m * kHidden + n0 + piece * 8) = o;
       }
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void tile_end(int m_cta, int nb, int num_n, int M) {
+    const int half = ew >> 2;
+    if constexpr (!kFused) {
+      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * 2 + half] = make_float2(sum, sq);
+      sum = 0.f;
+      sq = 0.f;
+    } else {
+      if (nb != num_n - 1) return;
+      // ---- the CTA's 128 rows are complete: exchange the row statistics of the two column halves ----
+      float* st = sstats + parity * (2 * 128 * 2);
+      const int row = my_row - m_cta;   // 0..127
+      st[(half * 128 + row) * 2 + 0] = sum;
+      st[(half * 128 + row) * 2 + 1] = sq;
+      sum = 0.f;
+      sq = 0.f;
+      // all 8 epilogue warps: statistics visible, and every bf16 row of the panel is in global memory
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // ---- normalise in place: warp ew owns rows [16 ew, 16 ew + 16), a lane 3 x 8 columns of a row ----
+      // (columns 256 i + 8 lane .. + 8 for i = 0, 1, 2: every 16-byte access of the warp is contiguous)
+      float ga[24], be[24];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int c = (i >> 1) * 256 + lane_ * 8 + (i & 1) * 4;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + c));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + c));
+        ga[i * 4 + 0] = g4.x; ga[i * 4 + 1] = g4.y; ga[i * 4 + 2] = g4.z; ga[i * 4 + 3] = g4.w;
+        be[i * 4 + 0] = b4.x; be[i * 4 + 1] = b4.y; be[i * 4 + 2] = b4.z; be[i * 4 + 3] = b4.w;
+      }
+#pragma unroll 4
+      for (int rr_ = 0; rr_ < 16; ++rr_) {
+        const int r = ew * 16 + rr_;
+        const int m = m_cta + r;
+        if (m >= M) break;
+        const float s = st[r * 2] + st[(128 + r) * 2];
+        const float q = st[r * 2 + 1] + st[(128 + r) * 2 + 1];
+        const float mean = s * (1.f / kHidden);
+        const float var = fmaxf(q * (1.f / kHidden) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        uint4* ptr = reinterpret_cast<uint4*>(p.out + (size_t)m * kHidden + lane_ * 8);   // + 32 uint4 per i
+        uint4 x[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) x[i] = __ldcg(ptr + i * 32);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const uint32_t wds[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = i * 8 + k * 2;
+            const float y0 = (bf16_lo(wds[k]) - mean) * rstd * ga[c] + be[c];
+            const float y1 = (bf16_hi(wds[k]) - mean) * rstd * ga[c + 1] + be[c + 1];
+            o[k] = pack_bf16(y0, y1);
+          }
+          ptr[i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      parity ^= 1;
+    }
+  }
   __device__ __forceinline__ void finish() {}
 };
+
+// Second half of the unfused variant: y[t] = (v[t] - mean) * rstd * gamma + beta in place, with the
+// row statistics summed from the GEMM epilogue's partials in a fixed order.  One warp per row.
+static __global__ void ln_apply_kernel(__nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, int n_part, int T,
+                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= T) return;
+  float s = 0.f, q = 0.f;
+  for (int i = 0; i < n_part; ++i) {
+    const float2 a = __ldg(stats + (size_t)t * n_part + i);
+    s += a.x;
+    q += a.y;
+  }
+  const float mean = s * (1.f / kHidden);
+  const float rstd = rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps);
+  // lane owns columns 256 i + 8 lane .. + 8, i = 0, 1, 2: every access of the warp is contiguous
+  uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)t * kHidden + lane * 8);
+  uint4 v[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) v[i] = ptr[i * 32];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const uint32_t wds[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = i * 256 + lane * 8 + k * 2;
+      const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
+      const float2 b = __ldg(reinterpret_cast<const float2*>(beta + c));
+      o[k] = pack_bf16((bf16_lo(wds[k]) - mean) * rstd * g.x + b.x, (bf16_hi(wds[k]) - mean) * rstd * g.y + b.y);
+    }
+    ptr[i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
 
 }  // namespace enc
 }  // namespace css

@@ -41,6 +41,8 @@ struct Cfg {
 struct Shape {
   int M, N, K;
   int m_fastest;  // 1: consecutive tiles share the B (N) block; 0: share the A (M) block
+  int panel;      // 1: a CTA (pair) visits every N block of one M block back to back, so its epilogue
+                  //    sees whole output rows (row LayerNorm fused into the epilogue)
 };
 
 // Epi concept:
@@ -54,7 +56,8 @@ struct Shape {
 //     // what the previous prefetch fetched for it
 //     __device__ void chunk_begin();
 //     __device__ void prefetch(int m_warp, int lane, int M, int n0);
-//     __device__ void tile_end(int m_blk, int n_blk);
+//     // m_cta: first row of this CTA's 128 rows of the tile; called by all 8 epilogue warps
+//     __device__ void tile_end(int m_cta, int n_blk, int num_n, int M);
 //     __device__ void finish(); };
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -101,7 +104,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int num_tiles = num_m * num_n;
   const int num_kb = shape.K / BK;
 
-  auto tile_coords = [&](int t, int& mb, int& nb) {
+  // u-th tile of this CTA
+  auto tile_at = [&](int u, int& mb, int& nb) -> bool {
+    if (shape.panel) {
+      mb = (int)blockIdx.x + (u / num_n) * (int)gridDim.x;
+      nb = u % num_n;
+      return mb < num_m;
+    }
+    const int t = (int)blockIdx.x + u * (int)gridDim.x;
+    if (t >= num_tiles) return false;
     if (shape.m_fastest) {
       mb = t % num_m;
       nb = t / num_m;
@@ -109,6 +120,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       nb = t % num_n;
       mb = t / num_n;
     }
+    return true;
   };
 
   if (warp == 0) {
@@ -116,9 +128,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        int mb, nb;
-        tile_coords(t, mb, nb);
+      int mb, nb;
+      for (int u = 0; tile_at(u, mb, nb); ++u) {
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty + stage, phase ^ 1);
           tc::mbar_expect_tx(full + stage, C::kStageBytes);
@@ -139,7 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      int mb, nb;
+      for (int u = 0; tile_at(u, mb, nb); ++u) {
         tc::mbar_wait(tempty + as, aphase ^ 1);  // epilogue has drained this accumulator
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
@@ -169,22 +181,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int ew = warp - 2;          // 0..7
     const int quarter = warp & 3;     // TMEM lane quarter this warp may read
     const int half = ew >> 2;         // column half of the tile
-    const int row_in_tile = quarter * 32 + lane;
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
-    if (blockIdx.x < num_tiles) {  // operands of the very first chunk (e.g. residual rows) start loading now
-      int mb0, nb0;
-      tile_coords(blockIdx.x, mb0, nb0);
-      epi.prefetch(mb0 * BM + quarter * 32, lane, shape.M, nb0 * BN + half * (BN / 2));
-    }
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      int mb, nb;
-      tile_coords(t, mb, nb);
+    int mb, nb;
+    if (tile_at(0, mb, nb))  // operands of the very first chunk (e.g. residual rows) start loading now
+      epi.prefetch(mb * BM + quarter * 32, lane, shape.M, nb * BN + half * (BN / 2));
+    for (int u = 0; tile_at(u, mb, nb); ++u) {
       // first chunk of the next tile of this CTA (prefetched during the last chunk of this one)
       int nmb = 0, nnb = 0;
-      const bool has_next_tile = t + (int)gridDim.x < num_tiles;
-      if (has_next_tile) tile_coords(t + gridDim.x, nmb, nnb);
+      const bool has_next_tile = tile_at(u + 1, nmb, nnb);
       const int next_m_warp = nmb * BM + quarter * 32;
       const int next_n_base = nnb * BN + half * (BN / 2);
       tc::mbar_wait(tfull + as, aphase);
@@ -212,7 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
         epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
       }
-      epi.tile_end(mb, nb);
+      epi.tile_end(mb * BM, nb, num_n, shape.M);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -247,7 +253,7 @@ int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
-  Shape shape{M, N, K, m_fastest};
+  Shape shape{M, N, K, m_fastest, Epi::kPanel ? 1 : 0};
   kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
   CSS_LAUNCHED();
   return CSS_OK;
@@ -330,7 +336,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
-  auto tile_coords = [&](int t, int& mb, int& nb) {
+  // u-th tile of this CTA pair
+  auto tile_at = [&](int u, int& mb, int& nb) -> bool {
+    if (shape.panel) {
+      mb = cluster_id + (u / num_n) * num_clusters;
+      nb = u % num_n;
+      return mb < num_m;
+    }
+    const int t = cluster_id + u * num_clusters;
+    if (t >= num_tiles) return false;
     if (shape.m_fastest) {
       mb = t % num_m;
       nb = t / num_m;
@@ -338,6 +352,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       nb = t % num_n;
       mb = t / num_n;
     }
+    return true;
   };
 
   if (warp == 0) {
@@ -345,9 +360,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       // ===================== TMA producer (both CTAs) =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        int mb, nb;
-        tile_coords(t, mb, nb);
+      int mb, nb;
+      for (int u = 0; tile_at(u, mb, nb); ++u) {
         const int a_row = mb * TM + (int)cta_rank * BM;
         const int b_row = nb * BN + (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -370,7 +384,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      int mb, nb;
+      for (int u = 0; tile_at(u, mb, nb); ++u) {
         tc::mbar_wait(tempty + as, aphase ^ 1);
         tc::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
@@ -400,22 +415,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int ew = warp - 2;
     const int quarter = warp & 3;
     const int half = ew >> 2;
-    const int row_in_tile = quarter * 32 + lane;
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
     const int row_off = (int)cta_rank * BM + quarter * 32;
-    if (cluster_id < num_tiles) {
-      int mb0, nb0;
-      tile_coords(cluster_id, mb0, nb0);
-      epi.prefetch(mb0 * TM + row_off, lane, shape.M, nb0 * BN + half * (BN / 2));
-    }
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      int mb, nb;
-      tile_coords(t, mb, nb);
+    int mb, nb;
+    if (tile_at(0, mb, nb)) epi.prefetch(mb * TM + row_off, lane, shape.M, nb * BN + half * (BN / 2));
+    for (int u = 0; tile_at(u, mb, nb); ++u) {
       int nmb = 0, nnb = 0;
-      const bool has_next_tile = t + num_clusters < num_tiles;
-      if (has_next_tile) tile_coords(t + num_clusters, nmb, nnb);
+      const bool has_next_tile = tile_at(u + 1, nmb, nnb);
       const int next_m_warp = nmb * TM + row_off;
       const int next_n_base = nnb * BN + half * (BN / 2);
       tc::mbar_wait(tfull + as, aphase);
@@ -442,7 +450,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
         epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
       }
-      epi.tile_end(mb, nb);
+      epi.tile_end(mb * TM + (int)cta_rank * BM, nb, num_n, shape.M);
       if (++as == 2) {
         as = 0;
         aphase ^= 1;
@@ -487,7 +495,7 @@ int launch2(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + BN - 1) / BN);
   int clusters = n_sm / 2;
   if (tiles < clusters) clusters = tiles;
-  Shape shape{M, N, K, m_fastest};
+  Shape shape{M, N, K, m_fastest, Epi::kPanel ? 1 : 0};
   kern<<<2 * clusters, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
   CSS_LAUNCHED();
   return CSS_OK;

@@ -81,6 +81,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, 
 // ---- 2. GEMM epilogue: threshold filter -------------------------------------------------
 struct EpiSearch {
   static constexpr bool kMasksColumns = true;
+  static constexpr bool kPanel = false;
   static constexpr int kStageBytes = 0;
   struct Params {
     const float* thr;       // [nq]
@@ -163,7 +164,7 @@ struct EpiSearch {
   }
   __device__ __forceinline__ void chunk_begin() {}
   __device__ __forceinline__ void prefetch(int, int, int, int) {}
-  __device__ __forceinline__ void tile_end(int, int) {}
+  __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
 

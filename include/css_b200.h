@@ -249,6 +249,13 @@ int css_encoder_encode_device(css_encoder* h, const int32_t* ids_dev, const int3
  *              rel_table[12][2*rel_half+1] indexed by (key - query) + rel_half. */
 int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int N, int K, int gelu,
                    int device, float* out);
+/*   gemm_resid_ln: out[M,768] = LayerNorm(bf16(A[M,K]) * bf16(B[768,K])^T + bias + bf16(resid[M,768])) * gamma + beta
+ *              through the fused epilogue of the attention-output / FFN-down projections
+ *              (modeling_mpnet.py:183-185,239-243); out is the bf16 result widened.  mode bit 0: 2-CTA
+ *              tiles, bit 1: LayerNorm inside the GEMM epilogue (else epilogue statistics + apply kernel). */
+int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, const float* resid,
+                            const float* gamma, const float* beta, int M, int K, float eps, int mode,
+                            int device, float* out);
 int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, const float* rel_table,
                         int rel_half, int device, float* ctx);
 

@@ -51,6 +51,34 @@ def test_tcgen05_gemm_vs_fp32(native, M, N, K, gelu, kernel):
     assert (err <= tol).all(), f"max err {err.max():.4g} at {np.unravel_index(err.argmax(), err.shape)}"
 
 
+@pytest.mark.parametrize("M,K", [(1, 768), (127, 768), (256, 768), (1000, 3072), (33000, 768)])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])   # bit 0: 2-CTA tiles, bit 1: LayerNorm inside the epilogue
+def test_gemm_resid_layernorm_epilogue_vs_fp64(native, M, K, mode):
+    """The fused epilogue of the attention-output / FFN-down projections: LayerNorm(A W^T + b + resid)."""
+    import torch
+    rng = np.random.default_rng(M + K)
+    N = 768
+    A = rng.standard_normal((M, K), dtype=np.float32)
+    B = (rng.standard_normal((N, K), dtype=np.float32) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    resid = (rng.standard_normal((M, N)) * 1.5 + 0.3).astype(np.float32)
+    gamma = (1 + 0.2 * rng.standard_normal(N)).astype(np.float32)
+    beta = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    out = np.empty((M, N), np.float32)
+    native.check(native.load().css_debug_gemm_resid_ln(A.ctypes.data, B.ctypes.data, bias.ctypes.data, resid.ctypes.data,
+                                                       gamma.ctypes.data, beta.ctypes.data, M, K, 1e-5, mode, 0,
+                                                       out.ctypes.data))
+    pre = (torch.from_numpy(_bf16(A)).double() @ torch.from_numpy(_bf16(B)).double().T + torch.from_numpy(bias).double()
+           + torch.from_numpy(_bf16(resid)).double())
+    ref = torch.nn.functional.layer_norm(pre, (N,), torch.from_numpy(gamma).double(), torch.from_numpy(beta).double(),
+                                         1e-5).numpy()
+    err = np.abs(out - ref)
+    # pre-LayerNorm value rounded to bf16 once (relative 2^-9 of |pre| ~ a few), the result once more
+    tol = 2.0 ** -7 * np.abs(ref) + 2.5e-2
+    assert (err <= tol).all(), f"max err {err.max():.4g} at {np.unravel_index(err.argmax(), err.shape)}"
+    assert err.mean() < 4e-3
+
+
 # ------------------------------------------------------------- attention
 @pytest.mark.parametrize("tc", ["1", "0"])   # tcgen05 kernel / mma.sync kernel
 @pytest.mark.parametrize("lens", [[1], [2, 3], [64], [65, 63], [128, 5, 200], [384], [129, 448, 300], [512, 17],
