@@ -111,6 +111,7 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   const css_mpnet_config& c = e->cfg;
   const int warps_per_block = 8;
   const unsigned row_blocks = (unsigned)((T + warps_per_block - 1) / warps_per_block);
+  const unsigned ln_blocks = (unsigned)((T + 8 * kLnApplyRows - 1) / (8 * kLnApplyRows));
   embed_ln_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(ids_dev, cu_dev, n_seq, T, e->word_emb, e->pos_emb,
                                                                c.vocab_size, c.max_position, c.pad_token_id,
                                                                e->emb_ln_w, e->emb_ln_b, c.layer_norm_eps, e->x);
@@ -122,6 +123,8 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   // tcgen05 attention (CSS_ATTN_TC=0 selects the mma.sync kernel); longer sequences always take mma.sync
   static const bool attn_tc_env = [] { const char* v = getenv("CSS_ATTN_TC"); return v ? atoi(v) != 0 : true; }();
   const bool attn_tc = attn_tc_env && max_len <= kAttnTcMaxLen;
+  // CSS_LN_FUSED=1: LayerNorm inside the attention-output GEMM epilogue (panel order); 0: epilogue statistics + apply kernel
+  static const bool ln_fused = [] { const char* v = getenv("CSS_LN_FUSED"); return v ? atoi(v) != 0 : true; }();
 
   for (int l = 0; l < c.num_layers; ++l) {
     const EncLayer& w = e->layers[l];
@@ -137,10 +140,17 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half, e->ctx);
       CSS_LAUNCHED();
     }
-    {
+    if (ln_fused) {
       EpiResidLN<true>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, nullptr};
       CSS_CHECK((gemm::run<256, EpiResidLN<true>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p, e->n_sm,
                                                     st)));
+    } else {
+      EpiResidLN<false>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, e->ln_stats};
+      CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p, e->n_sm,
+                                                     st)));
+      ln_apply_kernel<<<ln_blocks, 256, 0, st>>>(e->x1, e->ln_stats, T, w.ln1_w, w.ln1_b,
+                                                                   c.layer_norm_eps);
+      CSS_LAUNCHED();
     }
     {
       EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn};
@@ -151,7 +161,7 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       EpiResidLN<false>::Params p{e->x, w.b2, e->x1, w.ln2_w, w.ln2_b, c.layer_norm_eps, e->ln_stats};
       CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
     }
-    ln_apply_kernel<<<row_blocks, warps_per_block * 32, 0, st>>>(e->x, e->ln_stats, 6, T, w.ln2_w, w.ln2_b,
+    ln_apply_kernel<<<ln_blocks, 256, 0, st>>>(e->x, e->ln_stats, T, w.ln2_w, w.ln2_b,
                                                                  c.layer_norm_eps);
     CSS_LAUNCHED();
   }
@@ -507,7 +517,7 @@ int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, c
     rc = two_cta ? gemm::launch2<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
                  : gemm::launch<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
     if (rc == CSS_OK) {
-      ln_apply_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>((__nv_bfloat16*)o16.p, (const float2*)statd.p, 6, M,
+      ln_apply_kernel<<<(unsigned)((M + 8 * kLnApplyRows - 1) / (8 * kLnApplyRows)), 256, 0, st>>>((__nv_bfloat16*)o16.p, (const float2*)statd.p, M,
                                                                (const float*)gd.p, (const float*)bd.p, eps);
       CSS_LAUNCHED();
     }

@@ -409,7 +409,7 @@ struct EpiBiasBf16 {
   const Params& p;
   uint8_t* stage;
   __device__ EpiBiasBf16(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
-  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(int, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
 #pragma unroll
@@ -443,8 +443,7 @@ struct EpiBiasBf16 {
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void chunk_begin() {}
-  __device__ __forceinline__ void prefetch(int, int, int, int) {}
+  __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
@@ -487,8 +486,8 @@ struct EpiResidLN {
   int ew, lane_;
   int my_row = 0;                  // absolute row of this thread's accumulator lane in the current tile
   uint32_t parity = 0;
-  float sum = 0.f, sq = 0.f;
-  uint4 rr_next[4], rr[4];         // residual of this thread's row, 32 columns, one chunk ahead
+  uint64_t sum2 = 0ull, sq2 = 0ull;   // row statistics, two interleaved partial sums each (fp32x2)
+  uint4 rr[4][4];                  // residual of this thread's row: the 4 x 32 columns of a tile, requested one tile ahead
   __device__ EpiResidLN(const Params& p_, int epi_thread, uint8_t* stage_) : p(p_) {
     ew = epi_thread >> 5;
     lane_ = epi_thread & 31;
@@ -496,40 +495,42 @@ struct EpiResidLN {
     stage = base + ew * kWarpStage;
     sstats = reinterpret_cast<float*>(base + 8 * kWarpStage);
   }
-  __device__ __forceinline__ void chunk_begin() {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rr[i] = rr_next[i];
-  }
-  __device__ __forceinline__ void prefetch(int m_warp, int lane, int M, int n0) {
+  // A DRAM round trip per chunk sat on the critical path of every tile when the residual was
+  // requested one chunk ahead (tensor pipe 30 % active in the K = 768 projection): the request now
+  // leads by a whole tile.
+  __device__ __forceinline__ void prefetch(int slot, int m_warp, int lane, int M, int n0) {
     const int m = m_warp + lane;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rr_next[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = 0; i < 4; ++i) rr[slot][i] = make_uint4(0u, 0u, 0u, 0u);
     if (m < M) {
       const uint4* src = reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) rr_next[i] = __ldg(src + i);
+      for (int i = 0; i < 4; ++i) rr[slot][i] = __ldg(src + i);
     }
   }
-  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
     my_row = m_warp + lane;
+    // packed fp32x2 arithmetic: two columns per FADD2 / FFMA2
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
-      const uint4 r4 = rr[g];
-      float f[8];
-      f[0] = __uint_as_float(v[g * 8 + 0]) + ba.x + bf16_lo(r4.x); f[1] = __uint_as_float(v[g * 8 + 1]) + ba.y + bf16_hi(r4.x);
-      f[2] = __uint_as_float(v[g * 8 + 2]) + ba.z + bf16_lo(r4.y); f[3] = __uint_as_float(v[g * 8 + 3]) + ba.w + bf16_hi(r4.y);
-      f[4] = __uint_as_float(v[g * 8 + 4]) + bb.x + bf16_lo(r4.z); f[5] = __uint_as_float(v[g * 8 + 5]) + bb.y + bf16_hi(r4.z);
-      f[6] = __uint_as_float(v[g * 8 + 6]) + bb.z + bf16_lo(r4.w); f[7] = __uint_as_float(v[g * 8 + 7]) + bb.w + bf16_hi(r4.w);
-      sum += ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + f[7]));
-      sq += ((f[0] * f[0] + f[1] * f[1]) + (f[2] * f[2] + f[3] * f[3])) +
-            ((f[4] * f[4] + f[5] * f[5]) + (f[6] * f[6] + f[7] * f[7]));
-      uint4 o;
-      o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
-      o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
-      srow[g] = o;
+      const uint4 r4 = rr[slot][g];
+      const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+      const uint64_t bias2[4] = {f32x2_pack(ba.x, ba.y), f32x2_pack(ba.z, ba.w), f32x2_pack(bb.x, bb.y), f32x2_pack(bb.z, bb.w)};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t acc2 = f32x2_pack(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
+        const uint64_t f2 = f32x2_add(f32x2_add(acc2, bias2[k]), f32x2_pack(bf16_lo(rw[k]), bf16_hi(rw[k])));
+        sum2 = f32x2_add(sum2, f2);
+        sq2 = f32x2_fma(f2, f2, sq2);
+        float f0, f1;
+        f32x2_unpack(f2, f0, f1);
+        o[k] = pack_bf16(f0, f1);
+      }
+      srow[g] = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncwarp();
     // 4 lanes per row (4 x 16 B = the row's 64 B), 8 rows per instruction
@@ -548,18 +549,24 @@ struct EpiResidLN {
   __device__ __forceinline__ void tile_end(int m_cta, int nb, int num_n, int M) {
     const int half = ew >> 2;
     if constexpr (!kFused) {
-      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * 2 + half] = make_float2(sum, sq);
-      sum = 0.f;
-      sq = 0.f;
+      float s0, s1, q0, q1;
+      f32x2_unpack(sum2, s0, s1);
+      f32x2_unpack(sq2, q0, q1);
+      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * 2 + half] = make_float2(s0 + s1, q0 + q1);
+      sum2 = 0ull;
+      sq2 = 0ull;
     } else {
       if (nb != num_n - 1) return;
       // ---- the CTA's 128 rows are complete: exchange the row statistics of the two column halves ----
       float* st = sstats + parity * (2 * 128 * 2);
       const int row = my_row - m_cta;   // 0..127
-      st[(half * 128 + row) * 2 + 0] = sum;
-      st[(half * 128 + row) * 2 + 1] = sq;
-      sum = 0.f;
-      sq = 0.f;
+      float s0, s1, q0, q1;
+      f32x2_unpack(sum2, s0, s1);
+      f32x2_unpack(sq2, q0, q1);
+      st[(half * 128 + row) * 2 + 0] = s0 + s1;
+      st[(half * 128 + row) * 2 + 1] = q0 + q1;
+      sum2 = 0ull;
+      sq2 = 0ull;
       // all 8 epilogue warps: statistics visible, and every bf16 row of the panel is in global memory
       asm volatile("bar.sync 1, 256;" ::: "memory");
       // ---- normalise in place: warp ew owns rows [16 ew, 16 ew + 16), a lane 3 x 8 columns of a row ----
@@ -608,37 +615,59 @@ struct EpiResidLN {
 };
 
 // Second half of the unfused variant: y[t] = (v[t] - mean) * rstd * gamma + beta in place, with the
-// row statistics summed from the GEMM epilogue's partials in a fixed order.  One warp per row.
-static __global__ void ln_apply_kernel(__nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, int n_part, int T,
-                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
+// row statistics summed from the GEMM epilogue's partials in a fixed order.  A warp owns
+// kLnApplyRows consecutive rows and requests all of them before touching any (HBM-bound:
+// 1.5 KB read + 1.5 KB written per row, so bytes in flight are what matters).
+constexpr int kLnApplyRows = 4;
+static __global__ void __launch_bounds__(256)
+ln_apply_kernel(__nv_bfloat16* __restrict__ x, const float2* __restrict__ stats, int T,
+                const float* __restrict__ gamma, const float* __restrict__ beta, float eps) {
   const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= T) return;
-  float s = 0.f, q = 0.f;
-  for (int i = 0; i < n_part; ++i) {
-    const float2 a = __ldg(stats + (size_t)t * n_part + i);
-    s += a.x;
-    q += a.y;
-  }
-  const float mean = s * (1.f / kHidden);
-  const float rstd = rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps);
+  const int t0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kLnApplyRows;
+  if (t0 >= T) return;
   // lane owns columns 256 i + 8 lane .. + 8, i = 0, 1, 2: every access of the warp is contiguous
-  uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)t * kHidden + lane * 8);
-  uint4 v[3];
+  uint4 v[kLnApplyRows][3];
+  float4 sp[kLnApplyRows][3];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) v[i] = ptr[i * 32];
+  for (int j = 0; j < kLnApplyRows; ++j) {
+    const int t = min(t0 + j, T - 1);
+    const uint4* ptr = reinterpret_cast<const uint4*>(x + (size_t)t * kHidden + lane * 8);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const uint32_t wds[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-    uint32_t o[4];
+    for (int i = 0; i < 3; ++i) v[j][i] = ptr[i * 32];
+    // 6 partials (3 tiles x 2 column halves) = 48 B per row
+    const float4* s4 = reinterpret_cast<const float4*>(stats + (size_t)t * 6);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = i * 256 + lane * 8 + k * 2;
-      const float2 g = __ldg(reinterpret_cast<const float2*>(gamma + c));
-      const float2 b = __ldg(reinterpret_cast<const float2*>(beta + c));
-      o[k] = pack_bf16((bf16_lo(wds[k]) - mean) * rstd * g.x + b.x, (bf16_hi(wds[k]) - mean) * rstd * g.y + b.y);
+    for (int i = 0; i < 3; ++i) sp[j][i] = __ldg(s4 + i);
+  }
+  float g[24], b[24];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (i >> 1) * 256 + lane * 8 + (i & 1) * 4;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    g[i * 4 + 0] = g4.x; g[i * 4 + 1] = g4.y; g[i * 4 + 2] = g4.z; g[i * 4 + 3] = g4.w;
+    b[i * 4 + 0] = b4.x; b[i * 4 + 1] = b4.y; b[i * 4 + 2] = b4.z; b[i * 4 + 3] = b4.w;
+  }
+#pragma unroll
+  for (int j = 0; j < kLnApplyRows; ++j) {
+    const int t = t0 + j;
+    if (t >= T) break;
+    const float s = ((sp[j][0].x + sp[j][0].z) + (sp[j][1].x + sp[j][1].z)) + (sp[j][2].x + sp[j][2].z);
+    const float q = ((sp[j][0].y + sp[j][0].w) + (sp[j][1].y + sp[j][1].w)) + (sp[j][2].y + sp[j][2].w);
+    const float mean = s * (1.f / kHidden);
+    const float rstd = rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps);
+    uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)t * kHidden + lane * 8);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const uint32_t wds[4] = {v[j][i].x, v[j][i].y, v[j][i].z, v[j][i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = i * 8 + k * 2;
+        o[k] = pack_bf16((bf16_lo(wds[k]) - mean) * rstd * g[c] + b[c], (bf16_hi(wds[k]) - mean) * rstd * g[c + 1] + b[c + 1]);
+      }
+      ptr[i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
     }
-    ptr[i * 32] = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 

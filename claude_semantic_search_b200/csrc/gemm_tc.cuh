@@ -50,12 +50,12 @@ struct Shape {
 //     static constexpr int kStageBytes;   // shared memory per epilogue warp (output staging), may be 0
 //     __device__ Epi(const Params&, int epi_thread /*0..255*/, uint8_t* warp_stage);
 //     // lane i holds row m_warp + i, columns n0 .. n0+31, of the accumulator
-//     __device__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]);
-//     // prefetch(next) is called one chunk ahead (and across tiles) to start loading whatever
-//     // chunk(next) will need; chunk_begin() runs first so the current chunk can take over
-//     // what the previous prefetch fetched for it
-//     __device__ void chunk_begin();
-//     __device__ void prefetch(int m_warp, int lane, int M, int n0);
+//     __device__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]);
+//     // prefetch(slot, ...) is called one whole TILE ahead: right after chunk(slot, ...) of the
+//     // current tile, with the coordinates of the same chunk of this CTA's next tile (and for
+//     // every chunk of the first tile before the loop), so that operands the epilogue reads
+//     // from global memory (residual rows) have a tile's worth of time to arrive
+//     __device__ void prefetch(int slot, int m_warp, int lane, int M, int n0);
 //     // m_cta: first row of this CTA's 128 rows of the tile; called by all 8 epilogue warps
 //     __device__ void tile_end(int m_cta, int n_blk, int num_n, int M);
 //     __device__ void finish(); };
@@ -185,8 +185,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     int mb, nb;
-    if (tile_at(0, mb, nb))  // operands of the very first chunk (e.g. residual rows) start loading now
-      epi.prefetch(mb * BM + quarter * 32, lane, shape.M, nb * BN + half * (BN / 2));
+    if (tile_at(0, mb, nb)) {  // operands of the first tile (e.g. residual rows) start loading now
+#pragma unroll
+      for (int c = 0; c < BN / 2 / 32; ++c)
+        epi.prefetch(c, mb * BM + quarter * 32, lane, shape.M, nb * BN + half * (BN / 2) + c * 32);
+    }
     for (int u = 0; tile_at(u, mb, nb); ++u) {
       // first chunk of the next tile of this CTA (prefetched during the last chunk of this one)
       int nmb = 0, nnb = 0;
@@ -213,10 +216,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_relaxed(tempty + as);
         }
-        epi.chunk_begin();
-        if (c + 1 < kChunks) epi.prefetch(m_warp, lane, shape.M, n_base + (c + 1) * 32);
-        else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
-        epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        if (has_next_tile) epi.prefetch(c, next_m_warp, lane, shape.M, next_n_base + c * 32);
       }
       epi.tile_end(mb * BM, nb, num_n, shape.M);
       if (++as == 2) {
@@ -420,7 +421,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t aphase = 0;
     const int row_off = (int)cta_rank * BM + quarter * 32;
     int mb, nb;
-    if (tile_at(0, mb, nb)) epi.prefetch(mb * TM + row_off, lane, shape.M, nb * BN + half * (BN / 2));
+    if (tile_at(0, mb, nb)) {
+#pragma unroll
+      for (int c = 0; c < BN / 2 / 32; ++c)
+        epi.prefetch(c, mb * TM + row_off, lane, shape.M, nb * BN + half * (BN / 2) + c * 32);
+    }
     for (int u = 0; tile_at(u, mb, nb); ++u) {
       int nmb = 0, nnb = 0;
       const bool has_next_tile = tile_at(u + 1, nmb, nnb);
@@ -445,10 +450,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_leader_relaxed(tempty + as);
         }
-        epi.chunk_begin();
-        if (c + 1 < kChunks) epi.prefetch(m_warp, lane, shape.M, n_base + (c + 1) * 32);
-        else if (has_next_tile) epi.prefetch(next_m_warp, lane, shape.M, next_n_base);
-        epi.chunk(m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        if (has_next_tile) epi.prefetch(c, next_m_warp, lane, shape.M, next_n_base + c * 32);
       }
       epi.tile_end(mb * TM + (int)cta_rank * BM, nb, num_n, shape.M);
       if (++as == 2) {

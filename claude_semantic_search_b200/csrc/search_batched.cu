@@ -95,7 +95,7 @@ struct EpiSearch {
   };
   const Params& p;
   __device__ EpiSearch(const Params& p_, int, uint8_t*) : p(p_) {}
-  __device__ __forceinline__ void chunk(int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(int, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const int m = m_warp + lane;
     if (m >= M) return;
     if (p.seed) {
@@ -162,8 +162,7 @@ struct EpiSearch {
       ovf_flag[m] = 1;
     }
   }
-  __device__ __forceinline__ void chunk_begin() {}
-  __device__ __forceinline__ void prefetch(int, int, int, int) {}
+  __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
