@@ -34,6 +34,9 @@ D = 768
 K = 10
 ROWS = 1_000_000
 BYTES_PER_ROW = D * 4  # 3072 B per corpus row per batch-1 query
+# DRAM traffic of one scan_topk_kernel launch from the committed ncu --set full capture
+# (profiles/r1_ncu_kernels_summary.txt: 3.072071 GB read + 4.0 MB written), keyed by rows per GPU.
+NCU_SCAN_TRAFFIC = {1_000_000: 3_072_071_000 + 4_015_872}
 
 
 def peaks():
@@ -331,7 +334,10 @@ def main():
                        "l2": "corpus (3.07 GB) >> 126 MB L2, no flush needed",
                        "exchange": "none" if world == 1 else "2 x ncclAllGather (k x 4 B + k x 8 B per rank) + merge kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_source": pk["source"],
+                         "frac": achieved / pk["hbm_gbs"], "traffic": NCU_SCAN_TRAFFIC.get(rows),
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                           "(profiles/r1_ncu_kernels_summary.txt)" if rows in NCU_SCAN_TRAFFIC else None,
+                         "peak_source": pk["source"],
                          "kernel": "scan_topk_kernel", "kernel_ms": ms_scan,
                          "algorithmic_bytes_per_launch": rows * BYTES_PER_ROW},
             "cpu_baseline": cpu_base,

@@ -97,6 +97,9 @@ def main():
     I1 = np.stack(I1)
     Db, Ib = ss.search_device(q, K)
     Ib = Ib.cpu().numpy().copy()
+    # the two search paths agree on queries without needles too (same fp32 re-score arithmetic)
+    I2 = np.stack([ss.search_device(q[i:i + 1], K)[1].cpu().numpy()[0].copy() for i in range(n_needle_q, n_needle_q + 32)])
+    paths_agree = bool((I2 == Ib[n_needle_q:n_needle_q + 32]).all())
     ok_scan = bool((I1 == needle_ids).all())
     ok_batched = bool((Ib[:n_needle_q] == needle_ids).all())
     # timing
@@ -118,8 +121,9 @@ def main():
                        "aggregate_hbm_gbs": gbs * world},
             "batch1024": {"ms_per_call": msb, "qps": 1024 / (msb * 1e-3),
                           "tflops_per_gpu": 2.0 * 1024 * rows * D / (msb * 1e-3) / 1e12},
-            "needles_exact_scan": ok_scan, "needles_exact_batched": ok_batched}))
-    assert ok_scan and ok_batched, (ok_scan, ok_batched)
+            "needles_exact_scan": ok_scan, "needles_exact_batched": ok_batched,
+            "scan_and_batched_paths_agree_32_queries": paths_agree}))
+    assert ok_scan and ok_batched and paths_agree, (ok_scan, ok_batched, paths_agree)
     idx.close()
     if world > 1:
         dist.destroy_process_group()
