@@ -370,12 +370,13 @@ def bench_filtered(torch, native, dev, pk, rows=10_000_000, n_queries=200):
     order = rng.permutation(200)
     mass = np.bincount(proj, minlength=200) / rows
     allowed, acc = [], 0.0
-    for p_ in order:
-        if acc >= 0.5:
-            break
-        allowed.append(int(p_))
-        acc += mass[p_]
-    flt = native.Filter().add_range(4, 100, 100 + 182).add_set(1, allowed, 200).add_range(5, 1, 1)
+    for p_ in order:                      # ~50 % of the rows, never overshooting by a heavy project
+        if acc + mass[p_] <= 0.505:
+            allowed.append(int(p_))
+            acc += mass[p_]
+    # date window sized so that window x project x has_code = 5.0 % (5.0 +- 0.2 %)
+    days = int(round(0.05 / (acc * float(has_code.mean())) * 731))
+    flt = native.Filter().add_range(4, 100, 100 + days - 1).add_set(1, allowed, 200).add_range(5, 1, 1)
     words, n_pass = idx.filter_mask(flt)
     sel = n_pass / rows
     q = np.random.default_rng(43).standard_normal((n_queries, D)).astype(np.float32)

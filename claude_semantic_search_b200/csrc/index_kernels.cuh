@@ -212,6 +212,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
   float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
   __shared__ int s_is_last;
+  __shared__ unsigned short s_rows[kScanWarps][32 * kRowsPerUnit];   // filtered scan: selected rows of a window
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -249,6 +250,40 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       }
     }
     const int nu = (int)min((int64_t)32, u_end - ub);
+    if (mask8 != nullptr) {
+      // Filtered scan: compact the selected rows of the 256-row window into a per-warp list first,
+      // so that every score_rows call carries kRowsPerGroup distinct rows whatever the selectivity
+      // (unit by unit, a 5 % filter left one useful row -- and three duplicate loads -- per call).
+      const int cnt = __popc(mb);
+      int pos = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, pos, o);
+        if (lane >= o) pos += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, pos, 31);
+      pos -= cnt;
+      unsigned mm = mb;
+      while (mm) {
+        const int b = __ffs(mm) - 1;
+        mm &= mm - 1;
+        s_rows[warp][pos++] = (unsigned short)(lane * kRowsPerUnit + b);
+      }
+      __syncwarp();
+      const int64_t base = ub * kRowsPerUnit;
+      for (int g0 = 0; g0 < total; g0 += kRowsPerGroup) {
+        int64_t r[kRowsPerGroup];
+#pragma unroll
+        for (int i = 0; i < kRowsPerGroup; ++i) r[i] = base + s_rows[warp][min(g0 + i, total - 1)];
+        float acc[kRowsPerGroup];
+        score_rows<METRIC, D768>(p, qreg, q_s, r, lane, acc);
+#pragma unroll
+        for (int i = 0; i < kRowsPerGroup; ++i)
+          if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
+      }
+      __syncwarp();
+      continue;
+    }
     for (int j = 0; j < nu; ++j) {
       unsigned m = __shfl_sync(0xffffffffu, mb, j);
       const int64_t row0 = (ub + j) * kRowsPerUnit;
