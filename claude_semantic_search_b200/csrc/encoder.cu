@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <map>
 #include <vector>
 
 using namespace css;
@@ -48,6 +49,13 @@ struct css_encoder {
   int64_t max_seqs = 0;
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
+  // Single-query latency path: the 62 launches of one forward pass over one short
+  // sequence are captured once per (token bucket, normalize) into a CUDA graph and replayed.
+  struct QueryGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::map<int, QueryGraph> query_graphs;
   std::mutex mu;
 };
 
@@ -167,6 +175,54 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   }
   pool_normalize_kernel<<<(unsigned)n_seq, 256, 0, st>>>(e->x, cu_dev, normalize, out_dev);
   CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+// Token bucket of the single-query graph path (0: not served by a graph).
+int query_bucket(int T) {
+  static const bool enabled = [] { const char* v = getenv("CSS_QUERY_GRAPH"); return v ? atoi(v) != 0 : true; }();
+  if (!enabled || T > kAttnTcMaxLen) return 0;
+  for (int b : {32, 64, 128, 256, 384})
+    if (T <= b) return b;
+  return 0;
+}
+
+// One sequence of <= 384 tokens already in e->ids_dev / e->cu_dev: replay (or first capture) the graph
+// of a forward pass over `bucket` token rows.  Rows past the sequence end hold stale finite values;
+// every kernel is row-wise (GEMM, LayerNorm) or bounded by cu_seqlens (attention, pooling), so they
+// never reach the result.
+int forward_query_graph(css_encoder* e, int bucket, int normalize, cudaStream_t st) {
+  const int key = bucket * 2 + (normalize ? 1 : 0);
+  auto it = e->query_graphs.find(key);
+  if (it == e->query_graphs.end()) {
+    const int64_t l0 = g_launches.load(std::memory_order_relaxed);
+    CSS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    const int rc = forward(e, e->ids_dev, e->cu_dev, 1, bucket, bucket, normalize, e->out_dev, st);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    if (rc != CSS_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess || !graph) {
+      (void)cudaGetLastError();
+      set_error("graph capture of the query path failed: %s", cudaGetErrorString(ce));
+      return CSS_ERR_CUDA;
+    }
+    css_encoder::QueryGraph qg;
+    const cudaError_t ie = cudaGraphInstantiate(&qg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(ie));
+      return CSS_ERR_CUDA;
+    }
+    qg.launches = g_launches.load(std::memory_order_relaxed) - l0;
+    g_launches.store(l0, std::memory_order_relaxed);   // counted per replay below
+    it = e->query_graphs.emplace(key, qg).first;
+  }
+  CSS_CUDA(cudaGraphLaunch(it->second.exec, st));
+  g_launches.fetch_add(it->second.launches, std::memory_order_relaxed);
   return CSS_OK;
 }
 
@@ -331,6 +387,13 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   if ((rc = enc_alloc(e, &e->ids_dev, T)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->cu_dev, (size_t)e->max_seqs + 1)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->out_dev, (size_t)e->max_seqs * H)) != CSS_OK) return fail(rc);
+  // the graph path runs whole token buckets: rows past a query's end must hold finite values
+  cudaMemsetAsync(e->x, 0, T * H * 2, e->stream);
+  cudaMemsetAsync(e->x1, 0, T * H * 2, e->stream);
+  cudaMemsetAsync(e->qkv, 0, T * 3 * H * 2, e->stream);
+  cudaMemsetAsync(e->ctx, 0, T * H * 2, e->stream);
+  cudaMemsetAsync(e->h, 0, T * kFfn * 2, e->stream);
+  cudaMemsetAsync(e->ids_dev, 0, T * 4, e->stream);
   if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
     set_error("encoder initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
     return fail(CSS_ERR_CUDA);
@@ -344,6 +407,8 @@ int css_encoder_destroy(css_encoder* e) {
   {
     DeviceGuard g(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (auto& kv : e->query_graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     for (void* p : e->owned) cudaFree(p);
     if (e->pinned) cudaFreeHost(e->pinned);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -407,7 +472,9 @@ int css_encoder_encode(css_encoder* e, const int32_t* ids_host, const int32_t* c
     for (int i = 0; i <= ns; ++i) cu_pin[i] = cu_seqlens_host[s0 + i] - base;
     CSS_CUDA(cudaMemcpyAsync(e->ids_dev, pin, ids_bytes, cudaMemcpyHostToDevice, st));
     CSS_CUDA(cudaMemcpyAsync(e->cu_dev, cu_pin, cu_bytes, cudaMemcpyHostToDevice, st));
-    CSS_CHECK(forward(e, e->ids_dev, e->cu_dev, ns, T, max_len, normalize, e->out_dev, st));
+    const int bucket = (n_seq == 1) ? query_bucket(T) : 0;
+    if (bucket) CSS_CHECK(forward_query_graph(e, bucket, normalize, st));
+    else CSS_CHECK(forward(e, e->ids_dev, e->cu_dev, ns, T, max_len, normalize, e->out_dev, st));
     CSS_CUDA(cudaMemcpyAsync(pin + out_off, e->out_dev, out_bytes, cudaMemcpyDeviceToHost, st));
     CSS_CUDA(cudaStreamSynchronize(st));
     memcpy(out_host + (size_t)s0 * H, pin + out_off, out_bytes);

@@ -171,6 +171,27 @@ def test_encoder_ragged_batch_vs_oracle(native):
     enc.close()
 
 
+def test_single_query_graph_path_matches_batch_path(native):
+    """a single short sequence is served by a captured CUDA graph over a token
+    bucket (32 / 64 / 128 / 256 / 384 rows); it must return exactly what the batch path returns."""
+    from claude_semantic_search_b200.encoder import MPNetEncoder
+    from oracle import encoder_oracle as eo
+    lengths = [1, 5, 31, 32, 33, 64, 100, 128, 129, 256, 300, 384]
+    seqs = eo.synthetic_ids(len(lengths), lengths, seed=21)
+    model = eo.build_model(seed=0, perturb=True, num_layers=3)
+    enc = MPNetEncoder.from_hf_model(model)
+    batch = enc.encode_ids(seqs)                      # n_seq > 1: plain launches
+    want = eo.st_encode_ids(model, seqs, batch_size=16)
+    assert eo.cosine_rows(want, batch).min() >= COS_MIN
+    for rep in range(2):                              # first call captures, second replays
+        for i, q in enumerate(seqs):
+            one = enc.encode_ids([q])
+            np.testing.assert_array_equal(one[0], batch[i], err_msg=f"L={lengths[i]} rep={rep}")
+    raw = enc.encode_ids([seqs[4]], normalize=False)  # separate graph per normalize flag
+    np.testing.assert_allclose(raw[0] / np.linalg.norm(raw[0]), batch[4], atol=2e-6)
+    enc.close()
+
+
 def test_encoder_errors(native):
     from claude_semantic_search_b200.encoder import MPNetEncoder
     from oracle import encoder_oracle as eo
