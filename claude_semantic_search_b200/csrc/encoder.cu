@@ -43,7 +43,7 @@ struct css_encoder {
   std::vector<void*> owned;  // every device allocation, freed on destroy
   // workspace
   __nv_bfloat16 *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
-  float2* ln_stats = nullptr;   // [max_tokens][3][2] partial row statistics written by the FFN-down epilogue
+  float2* ln_stats = nullptr;   // [max_tokens][3][4] partial row statistics written by the FFN-down epilogue
   int32_t *ids_dev = nullptr, *cu_dev = nullptr;
   float* out_dev = nullptr;
   int64_t max_seqs = 0;
@@ -383,7 +383,7 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   if ((rc = enc_alloc(e, &e->qkv, T * 3 * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ctx, T * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->h, T * kFfn)) != CSS_OK) return fail(rc);
-  if ((rc = enc_alloc(e, &e->ln_stats, T * 6)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->ln_stats, T * 3 * kGemmEpiColSplit)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ids_dev, T)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->cu_dev, (size_t)e->max_seqs + 1)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->out_dev, (size_t)e->max_seqs * H)) != CSS_OK) return fail(rc);
@@ -559,7 +559,7 @@ int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, c
   const int N = kHidden;
   const bool two_cta = (mode & 1) != 0, fused = (mode & 2) != 0;
   DevBuf a32, a16, b32, b16, r32, r16, biasd, gd, bd, o16, o32, statd;
-  CSS_CHECK(statd.alloc((size_t)M * 6 * sizeof(float2)));
+  CSS_CHECK(statd.alloc((size_t)M * 3 * kGemmEpiColSplit * sizeof(float2)));
   CSS_CHECK(to_bf16_dev(A, (size_t)M * K, a32, a16, st));
   CSS_CHECK(to_bf16_dev(B, (size_t)N * K, b32, b16, st));
   CSS_CHECK(to_bf16_dev(resid, (size_t)M * N, r32, r16, st));

@@ -399,6 +399,7 @@ template <bool kGelu>
 struct EpiBiasBf16 {
   static constexpr bool kMasksColumns = false;
   static constexpr bool kPanel = false;
+  static constexpr bool kResidPrefetch = false;
   static constexpr int kRowBytes = 80;                 // 64 B of payload + 16 B pad: conflict-free
   static constexpr int kStageBytes = 32 * kRowBytes;   // per epilogue warp
   struct Params {
@@ -444,6 +445,7 @@ struct EpiBiasBf16 {
     __syncwarp();
   }
   __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
+  __device__ __forceinline__ void prefetch_none() {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
@@ -467,10 +469,14 @@ template <bool kFused>
 struct EpiResidLN {
   static constexpr bool kMasksColumns = false;
   static constexpr bool kPanel = kFused;
+  static constexpr bool kResidPrefetch = true;   // the TMA producer pulls the residual tile into L2 ahead of the epilogue
   static constexpr int kRowBytes = 80;                           // 64 B of payload + 16 B pad
-  static constexpr int kWarpStage = 32 * kRowBytes;              // bf16 staging per epilogue warp
-  static constexpr int kStatBytes = kFused ? 2 * 2 * 128 * 2 * 4 : 0;  // [panel parity][column half][row][sum, sumsq]
-  static constexpr int kStageBytes = kWarpStage + kStatBytes / 8;  // per epilogue warp (8 warps share the statistics)
+  static constexpr int kSlotBytes = 32 * kRowBytes;              // one 32 x 32 bf16 block (residual in, result out)
+  static constexpr int kWarpStage = 2 * kSlotBytes;              // per epilogue warp: one slot per chunk of its column slice
+  static constexpr int kSplit = kGemmEpiColSplit;              // column slices of a tile, one epilogue warp each
+  static constexpr int kWarps = kGemmEpiWarps;
+  static constexpr int kStatBytes = kFused ? 2 * kSplit * 128 * 2 * 4 : 0;  // [panel parity][column slice][row][sum, sumsq]
+  static constexpr int kStageBytes = kWarpStage + kStatBytes / kWarps;  // per epilogue warp (the warps share the statistics)
   struct Params {
     __nv_bfloat16* out;            // [M, 768]
     const float* bias;             // [768]
@@ -478,8 +484,9 @@ struct EpiResidLN {
     const float* gamma;
     const float* beta;
     float eps;
-    float2* stats;                 // !kFused: [M][3 tiles][2 column halves] (sum, sum of squares)
+    float2* stats;                 // !kFused: [M][3 tiles][4 column slices] (sum, sum of squares)
   };
+  static const void* resid_ptr(const Params& q) { return q.resid; }
   const Params& p;
   uint8_t* stage;
   float* sstats;
@@ -487,36 +494,49 @@ struct EpiResidLN {
   int my_row = 0;                  // absolute row of this thread's accumulator lane in the current tile
   uint32_t parity = 0;
   uint64_t sum2 = 0ull, sq2 = 0ull;   // row statistics, two interleaved partial sums each (fp32x2)
-  uint4 rr[4][4];                  // residual of this thread's row: the 4 x 32 columns of a tile, requested one tile ahead
   __device__ EpiResidLN(const Params& p_, int epi_thread, uint8_t* stage_) : p(p_) {
     ew = epi_thread >> 5;
     lane_ = epi_thread & 31;
     uint8_t* base = stage_ - ew * kStageBytes;
     stage = base + ew * kWarpStage;
-    sstats = reinterpret_cast<float*>(base + 8 * kWarpStage);
+    sstats = reinterpret_cast<float*>(base + kWarps * kWarpStage);
   }
-  // A DRAM round trip per chunk sat on the critical path of every tile when the residual was
-  // requested one chunk ahead (tensor pipe 30 % active in the K = 768 projection): the request now
-  // leads by a whole tile.
+  // The residual block of chunk `slot` of this CTA's NEXT tile is copied asynchronously
+  // (cp.async, 16 B per lane, 4 lanes x 16 B = the 64 B a row contributes, 8 rows per instruction)
+  // straight into the slot that the current tile's chunk has just finished with: a tile ahead, with
+  // no registers held.  Holding the prefetch in registers made ptxas spill in-flight loads, i.e.
+  // wait for them on the spot (ncu: the STL stalls on the long scoreboard) -- the K = 768 projection
+  // then ran at 180 us against 98 us without the residual.
   __device__ __forceinline__ void prefetch(int slot, int m_warp, int lane, int M, int n0) {
-    const int m = m_warp + lane;
+    const int piece = lane & 3;
+    const uint32_t dst0 = tc::smem_u32(stage + slot * kSlotBytes) + piece * 16;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) rr[slot][i] = make_uint4(0u, 0u, 0u, 0u);
-    if (m < M) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) rr[slot][i] = __ldg(src + i);
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      const int m = m_warp + r;
+      const __nv_bfloat16* src = p.resid + (size_t)min(m, M - 1) * kHidden + n0 + piece * 8;   // rows >= M are never stored
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + r * kRowBytes), "l"(src) : "memory");
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  __device__ __forceinline__ void prefetch_none() { asm volatile("cp.async.commit_group;" ::: "memory"); }
   __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+    uint8_t* blk = stage + slot * kSlotBytes;
+    // the copy into this slot was committed one tile ago; the only younger group is the other chunk's
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    uint4 rrow[4];   // this thread's row: 32 residual values
+#pragma unroll
+    for (int g = 0; g < 4; ++g) rrow[g] = *reinterpret_cast<const uint4*>(blk + lane * kRowBytes + g * 16);
+    __syncwarp();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-    uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
+    uint4* srow = reinterpret_cast<uint4*>(blk + lane * kRowBytes);
     my_row = m_warp + lane;
     // packed fp32x2 arithmetic: two columns per FADD2 / FFMA2
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
-      const uint4 r4 = rr[slot][g];
+      const uint4 r4 = rrow[g];
       const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
       const uint64_t bias2[4] = {f32x2_pack(ba.x, ba.y), f32x2_pack(ba.z, ba.w), f32x2_pack(bb.x, bb.y), f32x2_pack(bb.z, bb.w)};
       uint32_t o[4];
@@ -524,8 +544,10 @@ struct EpiResidLN {
       for (int k = 0; k < 4; ++k) {
         const uint64_t acc2 = f32x2_pack(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
         const uint64_t f2 = f32x2_add(f32x2_add(acc2, bias2[k]), f32x2_pack(bf16_lo(rw[k]), bf16_hi(rw[k])));
+#if !(defined(CSS_EPI_EXP) && (CSS_EPI_EXP & 2))
         sum2 = f32x2_add(sum2, f2);
         sq2 = f32x2_fma(f2, f2, sq2);
+#endif
         float f0, f1;
         f32x2_unpack(f2, f0, f1);
         o[k] = pack_bf16(f0, f1);
@@ -540,36 +562,36 @@ struct EpiResidLN {
       const int r = it * 8 + (lane >> 2);
       const int m = m_warp + r;
       if (m < M) {
-        const uint4 o = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + piece * 16);
+        const uint4 o = *reinterpret_cast<const uint4*>(blk + r * kRowBytes + piece * 16);
         *reinterpret_cast<uint4*>(p.out + (size_t)m * kHidden + n0 + piece * 8) = o;
       }
     }
     __syncwarp();
   }
   __device__ __forceinline__ void tile_end(int m_cta, int nb, int num_n, int M) {
-    const int half = ew >> 2;
+    const int colq = ew >> 2;
     if constexpr (!kFused) {
       float s0, s1, q0, q1;
       f32x2_unpack(sum2, s0, s1);
       f32x2_unpack(sq2, q0, q1);
-      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * 2 + half] = make_float2(s0 + s1, q0 + q1);
+      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * kSplit + colq] = make_float2(s0 + s1, q0 + q1);
       sum2 = 0ull;
       sq2 = 0ull;
     } else {
       if (nb != num_n - 1) return;
       // ---- the CTA's 128 rows are complete: exchange the row statistics of the two column halves ----
-      float* st = sstats + parity * (2 * 128 * 2);
+      float* st = sstats + parity * (kSplit * 128 * 2);
       const int row = my_row - m_cta;   // 0..127
       float s0, s1, q0, q1;
       f32x2_unpack(sum2, s0, s1);
       f32x2_unpack(sq2, q0, q1);
-      st[(half * 128 + row) * 2 + 0] = s0 + s1;
-      st[(half * 128 + row) * 2 + 1] = q0 + q1;
+      st[(colq * 128 + row) * 2 + 0] = s0 + s1;
+      st[(colq * 128 + row) * 2 + 1] = q0 + q1;
       sum2 = 0ull;
       sq2 = 0ull;
-      // all 8 epilogue warps: statistics visible, and every bf16 row of the panel is in global memory
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      // ---- normalise in place: warp ew owns rows [16 ew, 16 ew + 16), a lane 3 x 8 columns of a row ----
+      // all epilogue warps: statistics visible, and every bf16 row of the panel is in global memory
+      asm volatile("bar.sync 1, %0;" ::"n"(kWarps * 32) : "memory");
+      // ---- normalise in place: warp ew owns 128 / kWarps rows, a lane 3 x 8 columns of a row ----
       // (columns 256 i + 8 lane .. + 8 for i = 0, 1, 2: every 16-byte access of the warp is contiguous)
       float ga[24], be[24];
 #pragma unroll
@@ -580,13 +602,18 @@ struct EpiResidLN {
         ga[i * 4 + 0] = g4.x; ga[i * 4 + 1] = g4.y; ga[i * 4 + 2] = g4.z; ga[i * 4 + 3] = g4.w;
         be[i * 4 + 0] = b4.x; be[i * 4 + 1] = b4.y; be[i * 4 + 2] = b4.z; be[i * 4 + 3] = b4.w;
       }
+      constexpr int kRowsPerWarp = 128 / kWarps;
 #pragma unroll 4
-      for (int rr_ = 0; rr_ < 16; ++rr_) {
-        const int r = ew * 16 + rr_;
+      for (int rr_ = 0; rr_ < kRowsPerWarp; ++rr_) {
+        const int r = ew * kRowsPerWarp + rr_;
         const int m = m_cta + r;
         if (m >= M) break;
-        const float s = st[r * 2] + st[(128 + r) * 2];
-        const float q = st[r * 2 + 1] + st[(128 + r) * 2 + 1];
+        float s = 0.f, q = 0.f;
+#pragma unroll
+        for (int c = 0; c < kSplit; ++c) {
+          s += st[(c * 128 + r) * 2];
+          q += st[(c * 128 + r) * 2 + 1];
+        }
         const float mean = s * (1.f / kHidden);
         const float var = fmaxf(q * (1.f / kHidden) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + p.eps);
@@ -627,17 +654,18 @@ ln_apply_kernel(__nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
   if (t0 >= T) return;
   // lane owns columns 256 i + 8 lane .. + 8, i = 0, 1, 2: every access of the warp is contiguous
   uint4 v[kLnApplyRows][3];
-  float4 sp[kLnApplyRows][3];
+  constexpr int kPart4 = 3 * kGemmEpiColSplit / 2;   // float4s holding a row's 3 x 4 (sum, sumsq) partials
+  float4 sp[kLnApplyRows][kPart4];
 #pragma unroll
   for (int j = 0; j < kLnApplyRows; ++j) {
     const int t = min(t0 + j, T - 1);
     const uint4* ptr = reinterpret_cast<const uint4*>(x + (size_t)t * kHidden + lane * 8);
 #pragma unroll
     for (int i = 0; i < 3; ++i) v[j][i] = ptr[i * 32];
-    // 6 partials (3 tiles x 2 column halves) = 48 B per row
-    const float4* s4 = reinterpret_cast<const float4*>(stats + (size_t)t * 6);
+    // 12 partials (3 tiles x 4 column slices) = 96 B per row
+    const float4* s4 = reinterpret_cast<const float4*>(stats + (size_t)t * (2 * kPart4));
 #pragma unroll
-    for (int i = 0; i < 3; ++i) sp[j][i] = __ldg(s4 + i);
+    for (int i = 0; i < kPart4; ++i) sp[j][i] = __ldg(s4 + i);
   }
   float g[24], b[24];
 #pragma unroll
@@ -652,8 +680,12 @@ ln_apply_kernel(__nv_bfloat16* __restrict__ x, const float2* __restrict__ stats,
   for (int j = 0; j < kLnApplyRows; ++j) {
     const int t = t0 + j;
     if (t >= T) break;
-    const float s = ((sp[j][0].x + sp[j][0].z) + (sp[j][1].x + sp[j][1].z)) + (sp[j][2].x + sp[j][2].z);
-    const float q = ((sp[j][0].y + sp[j][0].w) + (sp[j][1].y + sp[j][1].w)) + (sp[j][2].y + sp[j][2].w);
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kPart4; ++i) {   // fixed order: results are run-to-run identical
+      s += sp[j][i].x + sp[j][i].z;
+      q += sp[j][i].y + sp[j][i].w;
+    }
     const float mean = s * (1.f / kHidden);
     const float rstd = rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps);
     uint4* ptr = reinterpret_cast<uint4*>(x + (size_t)t * kHidden + lane * 8);

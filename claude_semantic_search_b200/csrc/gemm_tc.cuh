@@ -5,7 +5,7 @@
 //   C    : fp32 accumulators in TMEM (2 x BN columns, double-buffered so the epilogue of
 //          tile i overlaps the main loop of tile i+1)
 //   roles: warp 0 = TMA producer (1 thread), warp 1 = MMA issuer (1 thread) + TMEM owner,
-//          warps 2..9 = epilogue (TMEM -> registers -> Epi functor -> global)
+//          warps 2..17 = epilogue (TMEM -> registers -> Epi functor -> global)
 //
 // One CTA per SM, tiles of 128 x BN visited round-robin.  The epilogue is a template
 // parameter: the encoder instantiates bias / bias+GELU / bias+residual writers, the
@@ -19,8 +19,9 @@ namespace gemm {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;
-constexpr int kThreads = (2 + kEpiWarps) * 32;  // 320
+constexpr int kEpiWarps = kGemmEpiWarps;          // 16
+constexpr int kColSplit = kGemmEpiColSplit;      // 4 column slices of BN / 4
+constexpr int kThreads = (2 + kEpiWarps) * 32;   // 576
 
 constexpr int kSmemBudget = 232448;  // 227 KB: the most one CTA may opt in to
 
@@ -35,7 +36,7 @@ struct Cfg {
   static constexpr int kStages = kStagesFit > 6 ? 6 : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN;  // 512 (BN=256) or 256 (BN=128)
-  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kStages >= 2, "pipeline too shallow");  // fallback kernel (CSS_GEMM_2CTA=0); the 2-CTA kernel keeps >= 4
 };
 
 struct Shape {
@@ -48,7 +49,7 @@ struct Shape {
 // Epi concept:
 //   struct Epi { struct Params {...};
 //     static constexpr int kStageBytes;   // shared memory per epilogue warp (output staging), may be 0
-//     __device__ Epi(const Params&, int epi_thread /*0..255*/, uint8_t* warp_stage);
+//     __device__ Epi(const Params&, int epi_thread /*0..511*/, uint8_t* warp_stage);
 //     // lane i holds row m_warp + i, columns n0 .. n0+31, of the accumulator
 //     __device__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]);
 //     // prefetch(slot, ...) is called one whole TILE ahead: right after chunk(slot, ...) of the
@@ -56,13 +57,16 @@ struct Shape {
 //     // every chunk of the first tile before the loop), so that operands the epilogue reads
 //     // from global memory (residual rows) have a tile's worth of time to arrive
 //     __device__ void prefetch(int slot, int m_warp, int lane, int M, int n0);
+//     __device__ void prefetch_none();   // called instead when this CTA has no next tile
+//   static constexpr bool kResidPrefetch: the TMA producer pulls the tile of Params::resid ([M, N] bf16)
+//     that the epilogue of the NEXT tile will read into L2 (cp.async.bulk.prefetch.tensor)
 //     // m_cta: first row of this CTA's 128 rows of the tile; called by all 8 epilogue warps
 //     __device__ void tile_end(int m_cta, int n_blk, int num_n, int M);
 //     __device__ void finish(); };
 template <int BN, class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               Shape shape, typename Epi::Params ep) {
+               const __grid_constant__ CUtensorMap tmap_r, Shape shape, typename Epi::Params ep) {
   using C = Cfg<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,7 +133,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int mb, nb;
+      if constexpr (Epi::kResidPrefetch) {
+        if (tile_at(0, mb, nb))
+          for (int j = 0; j < BN / 64; ++j) tc::tma_prefetch_l2_2d(&tmap_r, nb * BN + j * 64, mb * BM);
+      }
       for (int u = 0; tile_at(u, mb, nb); ++u) {
+        if constexpr (Epi::kResidPrefetch) {   // residual rows of the next tile -> L2, two mainloops before they are read
+          int pmb, pnb;
+          if (tile_at(u + 1, pmb, pnb))
+            for (int j = 0; j < BN / 64; ++j) tc::tma_prefetch_l2_2d(&tmap_r, pnb * BN + j * 64, pmb * BM);
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           tc::mbar_wait(empty + stage, phase ^ 1);
           tc::mbar_expect_tx(full + stage, C::kStageBytes);
@@ -178,46 +191,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else {
     // ===================== epilogue =====================
-    const int ew = warp - 2;          // 0..7
+    const int ew = warp - 2;          // 0..15
     const int quarter = warp & 3;     // TMEM lane quarter this warp may read
-    const int half = ew >> 2;         // column half of the tile
+    const int colq = ew >> 2;         // column slice of the tile
+    constexpr int kCols = BN / kColSplit;
+    constexpr int kChunks = kCols / 32;
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
     int mb, nb;
     if (tile_at(0, mb, nb)) {  // operands of the first tile (e.g. residual rows) start loading now
 #pragma unroll
-      for (int c = 0; c < BN / 2 / 32; ++c)
-        epi.prefetch(c, mb * BM + quarter * 32, lane, shape.M, nb * BN + half * (BN / 2) + c * 32);
+      for (int c = 0; c < kChunks; ++c)
+        epi.prefetch(c, mb * BM + quarter * 32, lane, shape.M, nb * BN + colq * kCols + c * 32);
     }
     for (int u = 0; tile_at(u, mb, nb); ++u) {
-      // first chunk of the next tile of this CTA (prefetched during the last chunk of this one)
+      // same chunk of the next tile of this CTA (requested a tile ahead)
       int nmb = 0, nnb = 0;
       const bool has_next_tile = tile_at(u + 1, nmb, nnb);
       const int next_m_warp = nmb * BM + quarter * 32;
-      const int next_n_base = nnb * BN + half * (BN / 2);
+      const int next_n_base = nnb * BN + colq * kCols;
       tc::mbar_wait(tfull + as, aphase);
       tc::tc_fence_after();
       const int m_warp = mb * BM + quarter * 32;  // first row of this warp's 32 rows
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(as * BN + half * (BN / 2));
-      const int n_base = nb * BN + half * (BN / 2);
-      constexpr int kChunks = BN / 2 / 32;
-      uint32_t v[2][32];
-      tc::tmem_ld_32x32(taddr, v[0]);
+                             static_cast<uint32_t>(as * BN + colq * kCols);
+      const int n_base = nb * BN + colq * kCols;
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
+        uint32_t v[32];   // one chunk at a time: with four warps per sub-partition the others cover the TMEM latency
+        tc::tmem_ld_32x32(taddr + c * 32, v);
         tc::tmem_ld_wait();
-        if (c + 1 < kChunks) {
-          tc::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);  // in flight while chunk c is processed
-        } else {
+        if (c == kChunks - 1) {
           // every TMEM read of this accumulator has landed in registers: hand it back early
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_relaxed(tempty + as);
         }
-        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v);
         if (has_next_tile) epi.prefetch(c, next_m_warp, lane, shape.M, next_n_base + c * 32);
+        else epi.prefetch_none();
       }
       epi.tile_end(mb * BM, nb, num_n, shape.M);
       if (++as == 2) {
@@ -241,9 +254,12 @@ int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, 
   using C = Cfg<BN, Epi::kStageBytes>;
   CSS_REQUIRE(M >= 1 && N >= 1 && (N % BN == 0 || Epi::kMasksColumns) && K % BK == 0 && K >= BK,
               "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M, N, K, BN);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tr;
   CSS_CHECK(encode_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK));
   CSS_CHECK(encode_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN, BK));
+  tr = ta;
+  if constexpr (Epi::kResidPrefetch)
+    CSS_CHECK(encode_tmap_bf16_2d(&tr, Epi::resid_ptr(ep), (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64));
   auto kern = gemm_tc_kernel<BN, Epi>;
   static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
   int dev = 0;
@@ -255,7 +271,7 @@ int launch(const void* A, int lda, const void* B, int ldb, int M, int N, int K, 
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < n_sm ? tiles : n_sm;
   Shape shape{M, N, K, m_fastest, Epi::kPanel ? 1 : 0};
-  kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
+  kern<<<grid, kThreads, C::kSmemBytes, st>>>(ta, tb, tr, shape, ep);
   CSS_LAUNCHED();
   return CSS_OK;
 }
@@ -289,7 +305,7 @@ struct Cfg2 {
 template <int BN, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                Shape shape, typename Epi::Params ep) {
+                const __grid_constant__ CUtensorMap tmap_r, Shape shape, typename Epi::Params ep) {
   using C = Cfg2<BN, Epi::kStageBytes>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -362,7 +378,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       int mb, nb;
+      if constexpr (Epi::kResidPrefetch) {
+        if (tile_at(0, mb, nb))
+          for (int j = 0; j < BN / 64; ++j) tc::tma_prefetch_l2_2d(&tmap_r, nb * BN + j * 64, mb * TM + (int)cta_rank * BM);
+      }
       for (int u = 0; tile_at(u, mb, nb); ++u) {
+        if constexpr (Epi::kResidPrefetch) {   // this CTA's residual rows of the next tile -> L2
+          int pmb, pnb;
+          if (tile_at(u + 1, pmb, pnb))
+            for (int j = 0; j < BN / 64; ++j)
+              tc::tma_prefetch_l2_2d(&tmap_r, pnb * BN + j * 64, pmb * TM + (int)cta_rank * BM);
+        }
         const int a_row = mb * TM + (int)cta_rank * BM;
         const int b_row = nb * BN + (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -413,9 +439,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
   } else {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    const int ew = warp - 2;
+    const int ew = warp - 2;          // 0..15
     const int quarter = warp & 3;
-    const int half = ew >> 2;
+    const int colq = ew >> 2;
+    constexpr int kCols = BN / kColSplit;
+    constexpr int kChunks = kCols / 32;
     Epi epi(ep, ew * 32 + lane, sEpi + ew * Epi::kStageBytes);
     int as = 0;
     uint32_t aphase = 0;
@@ -423,35 +451,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     int mb, nb;
     if (tile_at(0, mb, nb)) {
 #pragma unroll
-      for (int c = 0; c < BN / 2 / 32; ++c)
-        epi.prefetch(c, mb * TM + row_off, lane, shape.M, nb * BN + half * (BN / 2) + c * 32);
+      for (int c = 0; c < kChunks; ++c)
+        epi.prefetch(c, mb * TM + row_off, lane, shape.M, nb * BN + colq * kCols + c * 32);
     }
     for (int u = 0; tile_at(u, mb, nb); ++u) {
       int nmb = 0, nnb = 0;
       const bool has_next_tile = tile_at(u + 1, nmb, nnb);
       const int next_m_warp = nmb * TM + row_off;
-      const int next_n_base = nnb * BN + half * (BN / 2);
+      const int next_n_base = nnb * BN + colq * kCols;
       tc::mbar_wait(tfull + as, aphase);
       tc::tc_fence_after();
       const int m_warp = mb * TM + row_off;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) +
-                             static_cast<uint32_t>(as * BN + half * (BN / 2));
-      const int n_base = nb * BN + half * (BN / 2);
-      constexpr int kChunks = BN / 2 / 32;
-      uint32_t v[2][32];
-      tc::tmem_ld_32x32(taddr, v[0]);
+                             static_cast<uint32_t>(as * BN + colq * kCols);
+      const int n_base = nb * BN + colq * kCols;
 #pragma unroll
       for (int c = 0; c < kChunks; ++c) {
+        uint32_t v[32];
+        tc::tmem_ld_32x32(taddr + c * 32, v);
         tc::tmem_ld_wait();
-        if (c + 1 < kChunks) {
-          tc::tmem_ld_32x32(taddr + (c + 1) * 32, v[(c + 1) & 1]);
-        } else {
+        if (c == kChunks - 1) {
           tc::tc_fence_before();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive_leader_relaxed(tempty + as);
         }
-        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v[c & 1]);
+        epi.chunk(c, m_warp, lane, shape.M, n_base + c * 32, v);
         if (has_next_tile) epi.prefetch(c, next_m_warp, lane, shape.M, next_n_base + c * 32);
+        else epi.prefetch_none();
       }
       epi.tile_end(mb * TM + (int)cta_rank * BM, nb, num_n, shape.M);
       if (++as == 2) {
@@ -484,9 +510,12 @@ int launch2(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   using C = Cfg2<BN, Epi::kStageBytes>;
   CSS_REQUIRE(M >= 1 && N >= 1 && (N % BN == 0 || Epi::kMasksColumns) && K % BK == 0 && K >= BK,
               "gemm shape M=%d N=%d K=%d unsupported (BN=%d)", M, N, K, BN);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tr;
   CSS_CHECK(encode_tmap_bf16_2d(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, BM, BK));
   CSS_CHECK(encode_tmap_bf16_2d(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, BN / 2, BK));
+  tr = ta;
+  if constexpr (Epi::kResidPrefetch)
+    CSS_CHECK(encode_tmap_bf16_2d(&tr, Epi::resid_ptr(ep), (uint64_t)M, (uint64_t)N, (uint64_t)N, BM, 64));
   auto kern = gemm_tc2_kernel<BN, Epi>;
   static std::atomic<uint64_t> attr_set{0};
   int dev = 0;
@@ -499,7 +528,7 @@ int launch2(const void* A, int lda, const void* B, int ldb, int M, int N, int K,
   int clusters = n_sm / 2;
   if (tiles < clusters) clusters = tiles;
   Shape shape{M, N, K, m_fastest, Epi::kPanel ? 1 : 0};
-  kern<<<2 * clusters, kThreads, C::kSmemBytes, st>>>(ta, tb, shape, ep);
+  kern<<<2 * clusters, kThreads, C::kSmemBytes, st>>>(ta, tb, tr, shape, ep);
   CSS_LAUNCHED();
   return CSS_OK;
 }

@@ -82,6 +82,7 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, 
 struct EpiSearch {
   static constexpr bool kMasksColumns = true;
   static constexpr bool kPanel = false;
+  static constexpr bool kResidPrefetch = false;
   static constexpr int kStageBytes = 0;
   struct Params {
     const float* thr;       // [nq]
@@ -163,6 +164,7 @@ struct EpiSearch {
     }
   }
   __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
+  __device__ __forceinline__ void prefetch_none() {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };

@@ -112,6 +112,11 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Pull a tile into L2 only (no shared memory, no LSU traffic): issued by the TMA producer thread.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---- TMEM -----------------------------------------------------------------------
 // Whole-warp calls.  ncols: power of two in [32, 512].
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
@@ -261,6 +266,13 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
 }
 
 }  // namespace tc
+
+// Epilogue warps of the GEMM kernels (gemm_tc.cuh): 16 = four per SM sub-partition.  A warp owns 32
+// accumulator rows (its TMEM lane quarter, warp % 4) x a quarter of the tile's columns.  With 8 warps
+// (two per sub-partition) the epilogues were latency-bound: tensor pipe 30 % (K = 768 + LayerNorm) and
+// 72 % (GELU) active with neither the issue slots nor the XU pipe saturated.
+constexpr int kGemmEpiWarps = 16;
+constexpr int kGemmEpiColSplit = kGemmEpiWarps / 4;   // column slices of a tile
 
 // ---- host: tensor-map encoding through the driver entry point (libcuda is not linked) ----
 // 2-D row-major bf16 matrix [rows, cols]; box = {box_cols (innermost), box_rows}; 128B swizzle.
