@@ -37,13 +37,8 @@ constexpr int kAtHalfCols = 192;
 constexpr int kAtQ = 128 * 128;                    // Q tile bytes
 constexpr int kAtKV = kAttnTcMaxLen * 128;         // K / V tile bytes (max)
 constexpr int kAtP = 128 * 128;                    // one P block (128 rows x 64 keys bf16)
-// Relative-position bias of the current head, x log2e, for d = key - query in [-383, 383], as FOUR copies
-// shifted by 0..3 elements (copy s holds T[x + s]) so that a row's 32 consecutive biases -- whose first
-// element sits at a per-lane alignment -- are read with 128-bit shared loads: scalar LDS.32 per key
-// was the bottleneck of the softmax (scripts/micro/softmax_mix.cu: 1119 -> 653 cycles per 64 keys).
-// Double-buffered by unit parity; the softmax threads refill it when the head changes.
-constexpr int kAtRelCopy = 2 * kAttnTcMaxLen + 8;  // floats per copy: 776, i.e. copies start 8 banks apart
-constexpr int kAtRel = 2 * 4 * kAtRelCopy * 4;     // [unit parity][shift][x]
+constexpr int kAtRelStride = 2 * kAttnTcMaxLen;    // floats per head: bias(d) * log2e for d in [-383, 383]
+constexpr int kAtRel = kHeads * kAtRelStride * 4;  // every head's window, staged once per CTA
 constexpr int kAtCuMax = 768;                      // cu_seqlens entries cached in shared memory
 constexpr int kAtXmax = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial maxima
 constexpr int kAtStat = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial sums
@@ -221,7 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sV = sK + kAtKV;
   uint8_t* sP = sV + kAtKV;                       // [group][buffer] blocks
   float* sRel = reinterpret_cast<float*>(sP + 4 * kAtP);
-  float* sRelMax = sRel + 2 * 4 * kAtRelCopy;     // [16] per-head table maximum * log2e
+  float* sRelMax = sRel + kHeads * kAtRelStride;  // [16] per-head table maximum * log2e
   float* sXmax = sRelMax + 16;
   float* sStat = sXmax + kAtXmax / 4;
   int32_t* sCu = reinterpret_cast<int32_t*>(sStat + kAtStat / 4);
@@ -266,8 +261,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
   __syncwarp();
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
-  // per-CTA constants: the heads' bias maxima and the sequence offsets, so that no item starts with a
-  // chain of dependent global loads
+  // per-CTA constants: every head's bias window (x log2e) and the sequence offsets, so that no
+  // item starts with a chain of dependent global loads
+  for (int x = threadIdx.x; x < kHeads * kAtRelStride; x += kAttnTcThreads) {
+    const int hh = x / kAtRelStride, d = x % kAtRelStride - (kAttnTcMaxLen - 1);
+    const int dc = max(-p.rel_half, min(p.rel_half, d));
+    sRel[x] = p.rel_table[(size_t)hh * (2 * p.rel_half + 1) + p.rel_half + dc] * 1.4426950408889634f;
+  }
   if (threadIdx.x < kHeads) sRelMax[threadIdx.x] = p.rel_max[threadIdx.x] * 1.4426950408889634f;
   const bool cu_in_smem = p.n_seq <= kAtCuMax;
   if (cu_in_smem)
@@ -381,25 +381,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64) * log2(e)
     uint32_t n = 0, ng = 0, np = 0;            // items / items with keys in this half / P blocks of this group
-    uint32_t nu = 0, nu_next = 0;              // units started
     while (w.advance()) {
       const int nb = g ? w.nb1 : w.nb0;
       const int L = w.L;
       const int key0 = (g ? w.nb0 : 0) * 64 + ch * 32;   // first key of this thread's columns in block 0
       const int i = min(w.qb * 128 + r, L - 1);          // rows past the end mirror the last row, never stored
-      // bias table of this unit's head: refilled by the softmax threads at the unit's first item (the
-      // barrier between pass 1 and pass 2 publishes it; the buffer was last read two units ago)
-      float* relbuf = sRel + (nu & 1) * (4 * kAtRelCopy);
-      if (w.first_of_unit()) {
-        const float* src = p.rel_table + (size_t)w.h * (2 * p.rel_half + 1) + p.rel_half;
-        for (int x = threadIdx.x - 6 * 32; x < 4 * kAtRelCopy; x += 2 * kAtGW * 32) {
-          const int sft = x / kAtRelCopy, xx = x - sft * kAtRelCopy;
-          const int d = max(-p.rel_half, min(p.rel_half, xx + sft - (kAttnTcMaxLen - 1)));   // key - query
-          relbuf[x] = __ldg(src + d) * 1.4426950408889634f;
-        }
-      }
-      if (w.last_of_unit()) ++nu_next;
-      const int rel_o = (kAttnTcMaxLen - 1) - i;   // bias(j - i) * log2e = T[rel_o + j]
+      const float* rel_i = sRel + w.h * kAtRelStride + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
       const uint32_t par = n & 1;
       const bool tr = lane == 0 && ch == 0 && quarter == 0 && g == 0;
       if (tr) attn_trace(p.trace, 2 + g, n, 0);
@@ -461,20 +448,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         for (int hf = 0; hf < kAtHf; ++hf) {
           const int c = c0 + hf * 32;
           const int piece = ch + hf;
-          // 32 consecutive biases from the copy whose shift makes them 16-byte aligned
-          const int ro = rel_o + c;
-          const float4* rel4 = reinterpret_cast<const float4*>(relbuf + (ro & 3) * kAtRelCopy + (ro & ~3));
           if (c + 32 <= L) {   // warp-uniform
+            const float* rel_c = rel_i + c;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               uint32_t pk[4];
-              const float4 ra = rel4[q4 * 2], rb = rel4[q4 * 2 + 1];
-              const float rel_c[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
               for (int j2 = 0; j2 < 4; ++j2) {
                 const int j = q4 * 4 + j2;
                 const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(v[hf][2 * j]), __uint_as_float(v[hf][2 * j + 1])),
-                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j2], rel_c[2 * j2 + 1]), nm2));
+                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j], rel_c[2 * j + 1]), nm2));
                 float t0, t1;
                 f32x2_unpack(t, t0, t1);
                 const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
@@ -484,16 +467,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
               *reinterpret_cast<uint4*>(prow + (((piece * 4 + q4) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           } else if (c < L) {
+            const float* rel_c = rel_i + c;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               uint32_t pk[4];
-              const float4 ra = rel4[q4 * 2], rb = rel4[q4 * 2 + 1];
-              const float rel_c[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #pragma unroll
               for (int j2 = 0; j2 < 4; ++j2) {
                 const int j = q4 * 4 + j2;
                 const uint64_t t = f32x2_fma(f32x2_pack(__uint_as_float(v[hf][2 * j]), __uint_as_float(v[hf][2 * j + 1])),
-                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j2], rel_c[2 * j2 + 1]), nm2));
+                                             scale2, f32x2_add(f32x2_pack(rel_c[2 * j], rel_c[2 * j + 1]), nm2));
                 float t0, t1;
                 f32x2_unpack(t, t0, t1);
                 const float e0 = (c + 2 * j < L) ? ex2_approx(t0) : 0.f;
@@ -534,7 +516,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (lane == 0) tc::mbar_arrive(st_full + par);
       if (nb > 0) ++ng;
       ++n;
-      nu = nu_next;
     }
   }
   __syncwarp();

@@ -470,8 +470,12 @@ struct EpiResidLN {
   static constexpr bool kMasksColumns = false;
   static constexpr bool kPanel = kFused;
   static constexpr bool kResidPrefetch = true;   // the TMA producer pulls the residual tile into L2 ahead of the epilogue
-  static constexpr int kRowBytes = 80;                           // 64 B of payload + 16 B pad
-  static constexpr int kSlotBytes = 32 * kRowBytes;              // one 32 x 32 bf16 block (residual in, result out)
+  // one 32 x 32 bf16 block (residual in, result out): rows of 64 B, no padding; the 16-byte piece g of
+  // row r sits at position g ^ ((r >> 1) & 3), which makes both access patterns conflict-free (lane = row
+  // for the arithmetic, 4 lanes per row for the copies) and keeps the epilogue at 4 KB per warp, i.e.
+  // five pipeline stages for the main loop instead of four
+  static constexpr int kRowBytes = 64;
+  static constexpr int kSlotBytes = 32 * kRowBytes;
   static constexpr int kWarpStage = 2 * kSlotBytes;              // per epilogue warp: one slot per chunk of its column slice
   static constexpr int kSplit = kGemmEpiColSplit;              // column slices of a tile, one epilogue warp each
   static constexpr int kWarps = kGemmEpiWarps;
@@ -494,6 +498,7 @@ struct EpiResidLN {
   int my_row = 0;                  // absolute row of this thread's accumulator lane in the current tile
   uint32_t parity = 0;
   uint64_t sum2 = 0ull, sq2 = 0ull;   // row statistics, two interleaved partial sums each (fp32x2)
+  static __device__ __forceinline__ int slot_off(int r, int g) { return r * kRowBytes + ((g ^ ((r >> 1) & 3)) << 4); }
   __device__ EpiResidLN(const Params& p_, int epi_thread, uint8_t* stage_) : p(p_) {
     ew = epi_thread >> 5;
     lane_ = epi_thread & 31;
@@ -509,13 +514,13 @@ struct EpiResidLN {
   // then ran at 180 us against 98 us without the residual.
   __device__ __forceinline__ void prefetch(int slot, int m_warp, int lane, int M, int n0) {
     const int piece = lane & 3;
-    const uint32_t dst0 = tc::smem_u32(stage + slot * kSlotBytes) + piece * 16;
+    const uint32_t dst0 = tc::smem_u32(stage + slot * kSlotBytes);
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
       const int r = it * 8 + (lane >> 2);
       const int m = m_warp + r;
       const __nv_bfloat16* src = p.resid + (size_t)min(m, M - 1) * kHidden + n0 + piece * 8;   // rows >= M are never stored
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + r * kRowBytes), "l"(src) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + slot_off(r, piece)), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -527,10 +532,9 @@ struct EpiResidLN {
     __syncwarp();
     uint4 rrow[4];   // this thread's row: 32 residual values
 #pragma unroll
-    for (int g = 0; g < 4; ++g) rrow[g] = *reinterpret_cast<const uint4*>(blk + lane * kRowBytes + g * 16);
+    for (int g = 0; g < 4; ++g) rrow[g] = *reinterpret_cast<const uint4*>(blk + slot_off(lane, g));
     __syncwarp();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
-    uint4* srow = reinterpret_cast<uint4*>(blk + lane * kRowBytes);
     my_row = m_warp + lane;
     // packed fp32x2 arithmetic: two columns per FADD2 / FFMA2
 #pragma unroll
@@ -552,7 +556,7 @@ struct EpiResidLN {
         f32x2_unpack(f2, f0, f1);
         o[k] = pack_bf16(f0, f1);
       }
-      srow[g] = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(blk + slot_off(lane, g)) = make_uint4(o[0], o[1], o[2], o[3]);
     }
     __syncwarp();
     // 4 lanes per row (4 x 16 B = the row's 64 B), 8 rows per instruction
@@ -562,7 +566,7 @@ struct EpiResidLN {
       const int r = it * 8 + (lane >> 2);
       const int m = m_warp + r;
       if (m < M) {
-        const uint4 o = *reinterpret_cast<const uint4*>(blk + r * kRowBytes + piece * 16);
+        const uint4 o = *reinterpret_cast<const uint4*>(blk + slot_off(r, piece));
         *reinterpret_cast<uint4*>(p.out + (size_t)m * kHidden + n0 + piece * 8) = o;
       }
     }
