@@ -25,6 +25,11 @@ struct EncLayer {
   __nv_bfloat16 *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   float *ln1_w = nullptr, *ln1_b = nullptr, *ln2_w = nullptr, *ln2_b = nullptr;
+  // LayerNorm-folded pipeline (EpiBiasBf16<., true>): weights scaled by the gamma of the LayerNorm that
+  // feeds them, their column sums c and the constants d = b + W beta.  wqkv_f folds the PREVIOUS layer's
+  // output LayerNorm (layer 0 has none: its input is the embedding LayerNorm's output).
+  __nv_bfloat16 *wqkv_f = nullptr, *w1_f = nullptr;
+  float *cqkv = nullptr, *dqkv = nullptr, *c1 = nullptr, *d1 = nullptr;
 };
 
 struct css_encoder {
@@ -43,7 +48,8 @@ struct css_encoder {
   std::vector<void*> owned;  // every device allocation, freed on destroy
   // workspace
   __nv_bfloat16 *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
-  float2* ln_stats = nullptr;   // [max_tokens][3][4] partial row statistics written by the FFN-down epilogue
+  float2* ln_stats = nullptr;   // [max_tokens][3][4] partial row statistics written by the EpiResidLN epilogues
+  float2 *mr1 = nullptr, *mr2 = nullptr;   // [max_tokens] (mean, rstd) of the attention / output LayerNorm inputs
   int32_t *ids_dev = nullptr, *cu_dev = nullptr;
   float* out_dev = nullptr;
   int64_t max_seqs = 0;
@@ -94,6 +100,33 @@ int upload_bf16_into(css_encoder* e, __nv_bfloat16* dst, const float* src, size_
   return CSS_OK;
 }
 
+float bf16_round_host(float x) {   // round-to-nearest-even to bf16, as __float2bfloat16_rn
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// W [N, K] (nn.Linear layout), LayerNorm (gamma, beta) [K] feeding it, bias b [N]:
+//   Wf = W * gamma (per input column), c[n] = sum_k bf16(Wf[n, k]), d[n] = b[n] + sum_k beta[k] W[n, k]
+void fold_layernorm(const float* W, const float* b, const float* gamma, const float* beta, size_t N, size_t K,
+                    float* Wf, float* c, float* d) {
+  for (size_t n = 0; n < N; ++n) {
+    double cs = 0.0, ds = b[n];
+    for (size_t k = 0; k < K; ++k) {
+      const float wf = W[n * K + k] * gamma[k];
+      Wf[n * K + k] = wf;
+      cs += (double)bf16_round_host(wf);
+      ds += (double)beta[k] * (double)W[n * K + k];
+    }
+    c[n] = (float)cs;
+    d[n] = (float)ds;
+  }
+}
+
 int ensure_pinned(css_encoder* e, size_t bytes) {
   if (bytes <= e->pinned_bytes) return CSS_OK;
   if (e->pinned) {
@@ -134,11 +167,64 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   // CSS_LN_FUSED=1: LayerNorm inside the attention-output GEMM epilogue (panel order); 0 (default, measured
   // 127 + 61 us against 196 us): epilogue statistics + apply kernel
   static const bool ln_fused = [] { const char* v = getenv("CSS_LN_FUSED"); return v ? atoi(v) != 0 : false; }();
+  // CSS_LN_FOLD=1 (default): no normalised activation is ever materialised -- the projections emit the
+  // pre-LayerNorm value + row statistics, the consuming GEMMs fold the LayerNorm into their weights /
+  // epilogue, the residual adds rebuild LN(.) in fp32.  0: ln_apply_kernel after each projection.
+  static const bool ln_fold = [] { const char* v = getenv("CSS_LN_FOLD"); return v ? atoi(v) != 0 : true; }();
+  if (ln_fold) {
+    const unsigned fin_blocks = (unsigned)((T + 255) / 256);
+    for (int l = 0; l < c.num_layers; ++l) {
+      const EncLayer& w = e->layers[l];
+      const EncLayer* prev = l > 0 ? &e->layers[l - 1] : nullptr;
+      if (l == 0) {   // e->x holds the embedding LayerNorm's output
+        EpiBiasBf16<false>::Params p{e->qkv, w.bqkv, 3 * kHidden, nullptr, nullptr};
+        CSS_CHECK((gemm::run<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
+                                                        e->n_sm, st)));
+      } else {        // e->x holds the previous layer's pre-LayerNorm output, mr2 its row statistics
+        EpiBiasBf16<false, true>::Params p{e->qkv, w.dqkv, 3 * kHidden, w.cqkv, e->mr2};
+        CSS_CHECK((gemm::run<256, EpiBiasBf16<false, true>>(e->x, kHidden, w.wqkv_f, kHidden, T, 3 * kHidden, kHidden,
+                                                              0, p, e->n_sm, st)));
+      }
+      if (attn_tc) {
+        CSS_CHECK(attention_tc_launch(e->qkv, T, cu_dev, n_seq, max_len, e->rel_table, e->rel_max, e->rel_half,
+                                      e->ctx, e->n_sm, st));
+      } else {
+        attention_kernel<<<attn_grid, kAttnThreads, attn_smem, st>>>(e->qkv, cu_dev, e->rel_table, e->rel_half,
+                                                                     e->ctx);
+        CSS_LAUNCHED();
+      }
+      {
+        EpiResidLN<false>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, e->ln_stats,
+                                    prev ? e->mr2 : nullptr, prev ? prev->ln2_w : nullptr, prev ? prev->ln2_b : nullptr};
+        CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p,
+                                                       e->n_sm, st)));
+      }
+      ln_stats_finalize_kernel<<<fin_blocks, 256, 0, st>>>(e->ln_stats, T, c.layer_norm_eps, e->mr1);
+      CSS_LAUNCHED();
+      {
+        EpiBiasBf16<true, true>::Params p{e->h, w.d1, kFfn, w.c1, e->mr1};
+        CSS_CHECK((gemm::run<256, EpiBiasBf16<true, true>>(e->x1, kHidden, w.w1_f, kHidden, T, kFfn, kHidden, 0, p,
+                                                             e->n_sm, st)));
+      }
+      {
+        EpiResidLN<false>::Params p{e->x, w.b2, e->x1, w.ln2_w, w.ln2_b, c.layer_norm_eps, e->ln_stats,
+                                    e->mr1, w.ln1_w, w.ln1_b};
+        CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
+      }
+      ln_stats_finalize_kernel<<<fin_blocks, 256, 0, st>>>(e->ln_stats, T, c.layer_norm_eps, e->mr2);
+      CSS_LAUNCHED();
+    }
+    const EncLayer& last = e->layers[c.num_layers - 1];
+    pool_normalize_ln_kernel<<<(unsigned)n_seq, 256, 0, st>>>(e->x, e->mr2, last.ln2_w, last.ln2_b, cu_dev, normalize,
+                                                              out_dev);
+    CSS_LAUNCHED();
+    return CSS_OK;
+  }
 
   for (int l = 0; l < c.num_layers; ++l) {
     const EncLayer& w = e->layers[l];
     {
-      EpiBiasBf16<false>::Params p{e->qkv, w.bqkv, 3 * kHidden};
+      EpiBiasBf16<false>::Params p{e->qkv, w.bqkv, 3 * kHidden, nullptr, nullptr};
       CSS_CHECK((gemm::run<256, EpiBiasBf16<false>>(e->x, kHidden, w.wqkv, kHidden, T, 3 * kHidden, kHidden, 0, p,
                                                       e->n_sm, st)));
     }
@@ -150,11 +236,11 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       CSS_LAUNCHED();
     }
     if (ln_fused) {
-      EpiResidLN<true>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, nullptr};
+      EpiResidLN<true>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, nullptr, nullptr, nullptr, nullptr};
       CSS_CHECK((gemm::run<256, EpiResidLN<true>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p, e->n_sm,
                                                     st)));
     } else {
-      EpiResidLN<false>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, e->ln_stats};
+      EpiResidLN<false>::Params p{e->x1, w.bo, e->x, w.ln1_w, w.ln1_b, c.layer_norm_eps, e->ln_stats, nullptr, nullptr, nullptr};
       CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->ctx, kHidden, w.wo, kHidden, T, kHidden, kHidden, 0, p, e->n_sm,
                                                      st)));
       ln_apply_kernel<<<ln_blocks, 256, 0, st>>>(e->x1, e->ln_stats, T, w.ln1_w, w.ln1_b,
@@ -162,12 +248,12 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
       CSS_LAUNCHED();
     }
     {
-      EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn};
+      EpiBiasBf16<true>::Params p{e->h, w.b1, kFfn, nullptr, nullptr};
       CSS_CHECK((gemm::run<256, EpiBiasBf16<true>>(e->x1, kHidden, w.w1, kHidden, T, kFfn, kHidden, 0, p, e->n_sm,
                                                      st)));
     }
     {
-      EpiResidLN<false>::Params p{e->x, w.b2, e->x1, w.ln2_w, w.ln2_b, c.layer_norm_eps, e->ln_stats};
+      EpiResidLN<false>::Params p{e->x, w.b2, e->x1, w.ln2_w, w.ln2_b, c.layer_norm_eps, e->ln_stats, nullptr, nullptr, nullptr};
       CSS_CHECK((gemm::run<256, EpiResidLN<false>>(e->h, kFfn, w.w2, kFfn, T, kHidden, kFfn, 0, p, e->n_sm, st)));
     }
     ln_apply_kernel<<<ln_blocks, 256, 0, st>>>(e->x, e->ln_stats, T, w.ln2_w, w.ln2_b,
@@ -372,6 +458,37 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
     if ((rc = upload_f32(e, &d.ln1_b, s.ln1_b, H)) != CSS_OK) return fail(rc);
     if ((rc = upload_f32(e, &d.ln2_w, s.ln2_w, H)) != CSS_OK) return fail(rc);
     if ((rc = upload_f32(e, &d.ln2_b, s.ln2_b, H)) != CSS_OK) return fail(rc);
+    // LayerNorm-folded copies: FFN up-projection with this layer's attention LayerNorm, QKV projection
+    // with the previous layer's output LayerNorm
+    {
+      std::vector<float> wf((size_t)kFfn * H), cc(kFfn), dd(kFfn);
+      fold_layernorm(s.ffn1_w, s.ffn1_b, s.ln1_w, s.ln1_b, kFfn, H, wf.data(), cc.data(), dd.data());
+      if ((rc = enc_alloc(e, &d.w1_f, (size_t)kFfn * H)) != CSS_OK) return fail(rc);
+      if ((rc = upload_bf16_into(e, d.w1_f, wf.data(), (size_t)kFfn * H, stage)) != CSS_OK) return fail(rc);
+      if ((rc = upload_f32(e, &d.c1, cc.data(), kFfn)) != CSS_OK) return fail(rc);
+      if ((rc = upload_f32(e, &d.d1, dd.data(), kFfn)) != CSS_OK) return fail(rc);
+      if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+        set_error("weight upload failed");
+        return fail(CSS_ERR_CUDA);
+      }
+      if (l > 0) {
+        const css_mpnet_layer& pl = w->layers[l - 1];
+        std::vector<float> cq(3 * H), dq(3 * H);
+        if ((rc = enc_alloc(e, &d.wqkv_f, 3 * H * H)) != CSS_OK) return fail(rc);
+        const float* ws[3] = {s.q_w, s.k_w, s.v_w};
+        const float* bs[3] = {s.q_b, s.k_b, s.v_b};
+        for (int j = 0; j < 3; ++j) {
+          fold_layernorm(ws[j], bs[j], pl.ln2_w, pl.ln2_b, H, H, wf.data(), cq.data() + j * H, dq.data() + j * H);
+          if ((rc = upload_bf16_into(e, d.wqkv_f + (size_t)j * H * H, wf.data(), H * H, stage)) != CSS_OK) return fail(rc);
+        }
+        if ((rc = upload_f32(e, &d.cqkv, cq.data(), 3 * H)) != CSS_OK) return fail(rc);
+        if ((rc = upload_f32(e, &d.dqkv, dq.data(), 3 * H)) != CSS_OK) return fail(rc);
+        if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+          set_error("weight upload failed");
+          return fail(CSS_ERR_CUDA);
+        }
+      }
+    }
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
       set_error("weight upload failed");
       return fail(CSS_ERR_CUDA);
@@ -385,6 +502,10 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   if ((rc = enc_alloc(e, &e->ctx, T * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->h, T * kFfn)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ln_stats, T * 3 * kGemmEpiColSplit)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->mr1, T)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->mr2, T)) != CSS_OK) return fail(rc);
+  cudaMemsetAsync(e->mr1, 0, T * sizeof(float2), e->stream);
+  cudaMemsetAsync(e->mr2, 0, T * sizeof(float2), e->stream);
   if ((rc = enc_alloc(e, &e->ids_dev, T)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->cu_dev, (size_t)e->max_seqs + 1)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->out_dev, (size_t)e->max_seqs * H)) != CSS_OK) return fail(rc);
@@ -532,11 +653,11 @@ int css_debug_gemm(const float* A, const float* B, const float* bias, int M, int
   const int force = gelu & 6;
   const bool two = force == 4 || (force == 0 && gemm::use_2cta());
   if (gelu & 1) {
-    EpiBiasBf16<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
+    EpiBiasBf16<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N, nullptr, nullptr};
     rc = two ? gemm::launch2<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
              : gemm::launch<256, EpiBiasBf16<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
   } else {
-    EpiBiasBf16<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N};
+    EpiBiasBf16<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, N, nullptr, nullptr};
     rc = two ? gemm::launch2<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
              : gemm::launch<256, EpiBiasBf16<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
   }
@@ -576,12 +697,12 @@ int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, c
   int rc;
   if (fused) {
     EpiResidLN<true>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, (const __nv_bfloat16*)r16.p,
-                               (const float*)gd.p, (const float*)bd.p, eps, nullptr};
+                               (const float*)gd.p, (const float*)bd.p, eps, nullptr, nullptr, nullptr, nullptr};
     rc = two_cta ? gemm::launch2<256, EpiResidLN<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
                  : gemm::launch<256, EpiResidLN<true>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
   } else {
     EpiResidLN<false>::Params p{(__nv_bfloat16*)o16.p, (const float*)biasd.p, (const __nv_bfloat16*)r16.p,
-                                (const float*)gd.p, (const float*)bd.p, eps, (float2*)statd.p};
+                                (const float*)gd.p, (const float*)bd.p, eps, (float2*)statd.p, nullptr, nullptr, nullptr};
     rc = two_cta ? gemm::launch2<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st)
                  : gemm::launch<256, EpiResidLN<false>>(a16.p, K, b16.p, K, M, N, K, 0, p, sm_count(device), st);
     if (rc == CSS_OK) {

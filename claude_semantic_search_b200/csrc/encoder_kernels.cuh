@@ -130,6 +130,42 @@ static __global__ void embed_ln_kernel(const int32_t* __restrict__ ids, const in
   store_row_bf16(x + (size_t)t * kHidden, v, lane);
 }
 
+// E7 for the LayerNorm-folded pipeline: x holds the pre-LayerNorm activation of the last projection;
+// mean_t LN(x_t) = gamma * mean_t((x_t - mu_t) rstd_t) + beta.
+static __global__ void pool_normalize_ln_kernel(const __nv_bfloat16* __restrict__ x, const float2* __restrict__ mr,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const int32_t* __restrict__ cu, int normalize, float* __restrict__ out) {
+  const int s = blockIdx.x;
+  const int t0 = cu[s], t1 = cu[s + 1];
+  const int c = threadIdx.x;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int t = t0; t < t1; ++t) {
+    const __nv_bfloat16* r = x + (size_t)t * kHidden;
+    const float2 m = __ldg(mr + t);
+    a0 += (__bfloat162float(r[c]) - m.x) * m.y;
+    a1 += (__bfloat162float(r[c + 256]) - m.x) * m.y;
+    a2 += (__bfloat162float(r[c + 512]) - m.x) * m.y;
+  }
+  const float denom = fmaxf((float)(t1 - t0), 1e-9f);  // Pooling: clamp(sum(mask), min=1e-9)
+  a0 = a0 / denom * gamma[c] + beta[c];
+  a1 = a1 / denom * gamma[c + 256] + beta[c + 256];
+  a2 = a2 / denom * gamma[c + 512] + beta[c + 512];
+  if (normalize) {
+    __shared__ float red[8];
+    float ss = a0 * a0 + a1 * a1 + a2 * a2;
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float nrm = fmaxf(sqrtf(tot), 1e-12f);  // F.normalize(p=2, eps=1e-12)
+    a0 /= nrm; a1 /= nrm; a2 /= nrm;
+  }
+  float* o = out + (size_t)s * kHidden;
+  o[c] = a0; o[c + 256] = a1; o[c + 512] = a2;
+}
+
 // E7: out[s] = normalise(mean over tokens of x).  One CTA (256 threads) per sequence,
 // thread c owns columns c, c+256, c+512.
 static __global__ void pool_normalize_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ cu,
@@ -395,7 +431,13 @@ __device__ __forceinline__ uint64_t gelu_erf_x2(uint64_t x2) {
 //
 // out_bf16[m, n] = acc + bias[n]            (QKV projection)
 // out_bf16[m, n] = gelu(acc + bias[n])      (FFN up-projection)
-template <bool kGelu>
+//
+// kFold: the A operand is the PRE-LayerNorm activation v (bf16) of the producing projection and the
+// LayerNorm is folded into this GEMM:  LN(v) W^T + b = rstd_m (v (W gamma)^T - mu_m c_n) + d_n  with
+// c_n = sum_k (W gamma)[n, k] and d_n = b_n + sum_k beta_k W[n, k] prepared at load time (the weight
+// operand is W gamma, `bias` carries d, `colsum` carries c) and (mu_m, rstd_m) from
+// ln_stats_finalize_kernel.  The normalised activation is never written to or read from memory.
+template <bool kGelu, bool kFold = false>
 struct EpiBiasBf16 {
   static constexpr bool kMasksColumns = false;
   static constexpr bool kPanel = false;
@@ -404,23 +446,44 @@ struct EpiBiasBf16 {
   static constexpr int kStageBytes = 32 * kRowBytes;   // per epilogue warp
   struct Params {
     __nv_bfloat16* out;
-    const float* bias;
+    const float* bias;     // b, or d when kFold
     int ldo;
+    const float* colsum;   // kFold: c [N]
+    const float2* mr;      // kFold: (mean, rstd) per row [M]
   };
   const Params& p;
   uint8_t* stage;
+  float2 mr_cur = make_float2(0.f, 1.f), mr_next = make_float2(0.f, 1.f);
   __device__ EpiBiasBf16(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
-  __device__ __forceinline__ void chunk(int, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
+    if constexpr (kFold) {
+      if (slot == 0) mr_cur = mr_next;   // this tile's row statistics, requested a tile ahead
+    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
       float f[8];
+      if constexpr (kFold) {
+        const float4* c4 = reinterpret_cast<const float4*>(p.colsum + n0);
+        const float4 ca = __ldg(c4 + g * 2), cb = __ldg(c4 + g * 2 + 1);
+        // y = rstd acc + (d - rstd mu c), two columns per FFMA2
+        const uint64_t rs2 = f32x2_pack(mr_cur.y, mr_cur.y);
+        const uint64_t nb2 = f32x2_pack(-mr_cur.x * mr_cur.y, -mr_cur.x * mr_cur.y);
+        const uint64_t c2[4] = {f32x2_pack(ca.x, ca.y), f32x2_pack(ca.z, ca.w), f32x2_pack(cb.x, cb.y), f32x2_pack(cb.z, cb.w)};
+        const uint64_t d2[4] = {f32x2_pack(ba.x, ba.y), f32x2_pack(ba.z, ba.w), f32x2_pack(bb.x, bb.y), f32x2_pack(bb.z, bb.w)};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t acc2 = f32x2_pack(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
+          f32x2_unpack(f32x2_fma(rs2, acc2, f32x2_fma(nb2, c2[k], d2[k])), f[2 * k], f[2 * k + 1]);
+        }
+      } else {
       f[0] = __uint_as_float(v[g * 8 + 0]) + ba.x; f[1] = __uint_as_float(v[g * 8 + 1]) + ba.y;
       f[2] = __uint_as_float(v[g * 8 + 2]) + ba.z; f[3] = __uint_as_float(v[g * 8 + 3]) + ba.w;
       f[4] = __uint_as_float(v[g * 8 + 4]) + bb.x; f[5] = __uint_as_float(v[g * 8 + 5]) + bb.y;
       f[6] = __uint_as_float(v[g * 8 + 6]) + bb.z; f[7] = __uint_as_float(v[g * 8 + 7]) + bb.w;
+      }
       if constexpr (kGelu) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) f32x2_unpack(gelu_erf_x2(f32x2_pack(f[2 * i], f[2 * i + 1])), f[2 * i], f[2 * i + 1]);
@@ -444,11 +507,34 @@ struct EpiBiasBf16 {
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
+  __device__ __forceinline__ void prefetch(int slot, int m_warp, int lane, int M, int) {
+    if constexpr (kFold) {
+      if (slot == 0) mr_next = __ldg(p.mr + min(m_warp + lane, M - 1));
+    }
+  }
   __device__ __forceinline__ void prefetch_none() {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
+
+// (mean, rstd) of every row from the partial statistics the EpiResidLN epilogue leaves behind
+// (fixed summation order: results are run-to-run identical).
+static __global__ void ln_stats_finalize_kernel(const float2* __restrict__ parts, int T, float eps,
+                                                float2* __restrict__ mr) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T) return;
+  constexpr int kPart4 = 3 * kGemmEpiColSplit / 2;
+  const float4* s4 = reinterpret_cast<const float4*>(parts + (size_t)t * (2 * kPart4));
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kPart4; ++i) {
+    const float4 a = __ldg(s4 + i);
+    s += a.x + a.z;
+    q += a.y + a.w;
+  }
+  const float mean = s * (1.f / kHidden);
+  mr[t] = make_float2(mean, rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps));
+}
 
 // y[m, :] = LayerNorm(acc[m, :] + bias + resid[m, :]) * gamma + beta  (attention output / FFN down
 // projections, N = 768).  Per chunk, v = acc + bias + resid in fp32; the thread (= one row) adds v
@@ -489,6 +575,12 @@ struct EpiResidLN {
     const float* beta;
     float eps;
     float2* stats;                 // !kFused: [M][3 tiles][4 column slices] (sum, sum of squares)
+    // LayerNorm-folded pipeline: `resid` holds the PRE-LayerNorm activation of the previous
+    // projection and the residual is LN(resid) = (resid - mean) * rstd * rgamma + rbeta, rebuilt here
+    // in fp32 (rmr == nullptr: `resid` is the residual itself)
+    const float2* rmr;             // (mean, rstd) per row of `resid`
+    const float* rgamma;
+    const float* rbeta;
   };
   static const void* resid_ptr(const Params& q) { return q.resid; }
   const Params& p;
@@ -498,6 +590,7 @@ struct EpiResidLN {
   int my_row = 0;                  // absolute row of this thread's accumulator lane in the current tile
   uint32_t parity = 0;
   uint64_t sum2 = 0ull, sq2 = 0ull;   // row statistics, two interleaved partial sums each (fp32x2)
+  float2 mr_cur = make_float2(0.f, 1.f), mr_next = make_float2(0.f, 1.f);
   static __device__ __forceinline__ int slot_off(int r, int g) { return r * kRowBytes + ((g ^ ((r >> 1) & 3)) << 4); }
   __device__ EpiResidLN(const Params& p_, int epi_thread, uint8_t* stage_) : p(p_) {
     ew = epi_thread >> 5;
@@ -523,6 +616,7 @@ struct EpiResidLN {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + slot_off(r, piece)), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    if (p.rmr != nullptr && slot == 0) mr_next = __ldg(p.rmr + min(m_warp + lane, M - 1));
   }
   __device__ __forceinline__ void prefetch_none() { asm volatile("cp.async.commit_group;" ::: "memory"); }
   __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
@@ -536,6 +630,9 @@ struct EpiResidLN {
     __syncwarp();
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     my_row = m_warp + lane;
+    const bool rebuild = p.rmr != nullptr;   // kernel-uniform
+    if (rebuild && slot == 0) mr_cur = mr_next;
+    const uint64_t rs2 = f32x2_pack(mr_cur.y, mr_cur.y), nb2 = f32x2_pack(-mr_cur.x * mr_cur.y, -mr_cur.x * mr_cur.y);
     // packed fp32x2 arithmetic: two columns per FADD2 / FFMA2
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
@@ -543,11 +640,21 @@ struct EpiResidLN {
       const uint4 r4 = rrow[g];
       const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
       const uint64_t bias2[4] = {f32x2_pack(ba.x, ba.y), f32x2_pack(ba.z, ba.w), f32x2_pack(bb.x, bb.y), f32x2_pack(bb.z, bb.w)};
+      uint64_t g2[4], be2[4];
+      if (rebuild) {
+        const float4* g4 = reinterpret_cast<const float4*>(p.rgamma + n0);
+        const float4* e4 = reinterpret_cast<const float4*>(p.rbeta + n0);
+        const float4 ga = __ldg(g4 + g * 2), gb = __ldg(g4 + g * 2 + 1), ea = __ldg(e4 + g * 2), eb = __ldg(e4 + g * 2 + 1);
+        g2[0] = f32x2_pack(ga.x, ga.y); g2[1] = f32x2_pack(ga.z, ga.w); g2[2] = f32x2_pack(gb.x, gb.y); g2[3] = f32x2_pack(gb.z, gb.w);
+        be2[0] = f32x2_pack(ea.x, ea.y); be2[1] = f32x2_pack(ea.z, ea.w); be2[2] = f32x2_pack(eb.x, eb.y); be2[3] = f32x2_pack(eb.z, eb.w);
+      }
       uint32_t o[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const uint64_t acc2 = f32x2_pack(__uint_as_float(v[g * 8 + 2 * k]), __uint_as_float(v[g * 8 + 2 * k + 1]));
-        const uint64_t f2 = f32x2_add(f32x2_add(acc2, bias2[k]), f32x2_pack(bf16_lo(rw[k]), bf16_hi(rw[k])));
+        uint64_t res2 = f32x2_pack(bf16_lo(rw[k]), bf16_hi(rw[k]));
+        if (rebuild) res2 = f32x2_fma(f32x2_fma(res2, rs2, nb2), g2[k], be2[k]);   // LN(resid) = ((v - mu) rstd) gamma + beta
+        const uint64_t f2 = f32x2_add(f32x2_add(acc2, bias2[k]), res2);
 #if !(defined(CSS_EPI_EXP) && (CSS_EPI_EXP & 2))
         sum2 = f32x2_add(sum2, f2);
         sq2 = f32x2_fma(f2, f2, sq2);
