@@ -13,7 +13,8 @@
 //   warp 1        MMA issuer:   S_g = Q K_g^T  (tcgen05.mma M128 x N<=192 x K16)
 //                               O  += P_g[b] V_g[b]  (M128 x N64, V is the MN-major B operand);
 //                               the next item's Q K^T is issued in front of the last round of P V
-//   warps 2-5     epilogue: O / sum -> ctx (bf16), overlapped with the next item's softmax
+//   warps 2-5     epilogue: O / sum -> bf16 tile in shared memory -> one TMA store into ctx, overlapped with
+//                 the next item's softmax
 //   warps 6...     softmax group 0 then group 1, kAtGW warps each (4: one per TMEM lane quarter, a thread
 //                 owns a row's 64 columns of every key block; 8: two per quarter, 32 columns each):
 //                 pass 1  row maximum of the raw scores (tcgen05.ld), exchanged over all 16 warps
@@ -37,12 +38,13 @@ constexpr int kAtHalfCols = 192;
 constexpr int kAtQ = 128 * 128;                    // Q tile bytes
 constexpr int kAtKV = kAttnTcMaxLen * 128;         // K / V tile bytes (max)
 constexpr int kAtP = 128 * 128;                    // one P block (128 rows x 64 keys bf16)
-constexpr int kAtRelStride = 2 * kAttnTcMaxLen;    // floats per head: bias(d) * log2e for d in [-383, 383]
-constexpr int kAtRel = kHeads * kAtRelStride * 4;  // every head's window, staged once per CTA
+constexpr int kAtRelStride = 2 * kAttnTcMaxLen;    // floats per buffer: bias(d) * log2e for d in [-383, 383] of ONE head
+constexpr int kAtRel = 2 * kAtRelStride * 4;       // double-buffered by unit parity, refilled by the softmax threads
+constexpr int kAtO = 128 * 128;                    // output tile staging (128 rows x 64 bf16, 128-byte swizzle) for the TMA store
 constexpr int kAtCuMax = 768;                      // cu_seqlens entries cached in shared memory
 constexpr int kAtXmax = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial maxima
 constexpr int kAtStat = 2 * 4 * 128 * 4;           // [item parity][group * 2 + column half][row] partial sums
-constexpr int kAtSmem = kAtQ + 2 * kAtKV + 4 * kAtP + kAtRel + 64 + kAtXmax + kAtStat + (kAtCuMax + 1) * 4 + 4 + 256 + 1024;
+constexpr int kAtSmem = kAtQ + 2 * kAtKV + 4 * kAtP + kAtO + kAtRel + 64 + kAtXmax + kAtStat + (kAtCuMax + 1) * 4 + 4 + 256 + 1024;
 static_assert(kAtSmem <= 232448, "attention shared memory exceeds the 227 KB opt-in limit");
 constexpr uint32_t kOCol = 2 * kAtHalfCols;        // O[0] at 384, O[1] at 448
 
@@ -207,7 +209,7 @@ struct AttnMma {
 
 static __global__ void __launch_bounds__(kAttnTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                    AttnTcParams p) {
+                    const __grid_constant__ CUtensorMap tmap_o, AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by pointer arithmetic, so the compiler keeps the shared address space (LDS / STS)
   uint8_t* smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -215,8 +217,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sK = sQ + kAtQ;
   uint8_t* sV = sK + kAtKV;
   uint8_t* sP = sV + kAtKV;                       // [group][buffer] blocks
-  float* sRel = reinterpret_cast<float*>(sP + 4 * kAtP);
-  float* sRelMax = sRel + kHeads * kAtRelStride;  // [16] per-head table maximum * log2e
+  uint8_t* sO = sP + 4 * kAtP;                    // 1024-byte aligned (176 KB into the aligned window)
+  float* sRel = reinterpret_cast<float*>(sO + kAtO);
+  float* sRelMax = sRel + 2 * kAtRelStride;       // [16] per-head table maximum * log2e
   float* sXmax = sRelMax + 16;
   float* sStat = sXmax + kAtXmax / 4;
   int32_t* sCu = reinterpret_cast<int32_t*>(sStat + kAtStat / 4);
@@ -240,6 +243,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_q);
     tc::prefetch_tmap(&tmap_kv);
+    tc::prefetch_tmap(&tmap_o);
     tc::mbar_init(q_full, 1);
     tc::mbar_init(q_empty, 1);
     tc::mbar_init(k_full, 1);
@@ -263,11 +267,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 1) tc::tmem_alloc(tmem_slot, 512);
   // per-CTA constants: every head's bias window (x log2e) and the sequence offsets, so that no
   // item starts with a chain of dependent global loads
-  for (int x = threadIdx.x; x < kHeads * kAtRelStride; x += kAttnTcThreads) {
-    const int hh = x / kAtRelStride, d = x % kAtRelStride - (kAttnTcMaxLen - 1);
-    const int dc = max(-p.rel_half, min(p.rel_half, d));
-    sRel[x] = p.rel_table[(size_t)hh * (2 * p.rel_half + 1) + p.rel_half + dc] * 1.4426950408889634f;
-  }
   if (threadIdx.x < kHeads) sRelMax[threadIdx.x] = p.rel_max[threadIdx.x] * 1.4426950408889634f;
   const bool cu_in_smem = p.n_seq <= kAtCuMax;
   if (cu_in_smem)
@@ -336,8 +335,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc::mbar_wait_sleep(o_full + par, ph, 100);
       tc::tc_fence_after();
       if (tr) attn_trace(p.trace, 4, e, 2);
-      const int row = w.qb * 128 + r;
-      __nv_bfloat16* dst = p.ctx + (size_t)(w.t0 + row) * kHidden + w.h * kHeadDim;
       uint32_t a[32], b[32];
       tc::tmem_ld_32x32(lane_addr + par * kHeadDim, a);
       tc::tmem_ld_32x32(lane_addr + par * kHeadDim + 32, b);
@@ -346,29 +343,53 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(o_free + par);
-      if (row < w.L) {
+      // The tile leaves through shared memory and ONE bulk tensor store.  128 threads each writing
+      // their own 128-byte row straight to global memory (32 scattered 16-byte requests per store
+      // instruction) kept the LSU busy exactly while the softmax warps ran the first key block of the
+      // next item: that block took 4200 cycles instead of 2600 (timeline with the stores removed).
+      if (threadIdx.x == 64) tc::tma_store_wait_read();       // the previous item's store has read sO
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      uint8_t* orow = sO + r * 128;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]) * inv, __uint_as_float(a[q4 * 8 + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]) * inv, __uint_as_float(a[q4 * 8 + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]) * inv, __uint_as_float(a[q4 * 8 + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]) * inv, __uint_as_float(a[q4 * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + q4 * 8) = o;
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(a[q4 * 8 + 0]) * inv, __uint_as_float(a[q4 * 8 + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(a[q4 * 8 + 2]) * inv, __uint_as_float(a[q4 * 8 + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(a[q4 * 8 + 4]) * inv, __uint_as_float(a[q4 * 8 + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(a[q4 * 8 + 6]) * inv, __uint_as_float(a[q4 * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + ((q4 ^ (r & 7)) << 4)) = o;
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(b[q4 * 8 + 0]) * inv, __uint_as_float(b[q4 * 8 + 1]) * inv);
+        o.y = pack_bf16(__uint_as_float(b[q4 * 8 + 2]) * inv, __uint_as_float(b[q4 * 8 + 3]) * inv);
+        o.z = pack_bf16(__uint_as_float(b[q4 * 8 + 4]) * inv, __uint_as_float(b[q4 * 8 + 5]) * inv);
+        o.w = pack_bf16(__uint_as_float(b[q4 * 8 + 6]) * inv, __uint_as_float(b[q4 * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + (((4 + q4) ^ (r & 7)) << 4)) = o;
+      }
+      fence_proxy_async_smem();                                 // generic-proxy writes -> visible to the TMA engine
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      const int q0 = w.qb * 128;
+      if (q0 + 128 <= w.L) {
+        if (threadIdx.x == 64) {
+          tc::tma_store_2d(&tmap_o, sO, w.h * kHeadDim, w.t0 + q0);
+          tc::tma_store_commit();
         }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(b[q4 * 8 + 0]) * inv, __uint_as_float(b[q4 * 8 + 1]) * inv);
-          o.y = pack_bf16(__uint_as_float(b[q4 * 8 + 2]) * inv, __uint_as_float(b[q4 * 8 + 3]) * inv);
-          o.z = pack_bf16(__uint_as_float(b[q4 * 8 + 4]) * inv, __uint_as_float(b[q4 * 8 + 5]) * inv);
-          o.w = pack_bf16(__uint_as_float(b[q4 * 8 + 6]) * inv, __uint_as_float(b[q4 * 8 + 7]) * inv);
-          *reinterpret_cast<uint4*>(dst + 32 + q4 * 8) = o;
+      } else {
+        // last, partial query block of a sequence: the rows past its end belong to the next sequence,
+        // so only the real rows are written (8 lanes x 16 B = one row, 4 rows per instruction)
+        const int et = threadIdx.x - 64;   // 0..127
+        for (int rr = et >> 3; rr < w.L - q0; rr += 16) {
+          const int c = et & 7;
+          const uint4 o = *reinterpret_cast<const uint4*>(sO + rr * 128 + ((c ^ (rr & 7)) << 4));
+          *reinterpret_cast<uint4*>(p.ctx + (size_t)(w.t0 + q0 + rr) * kHidden + w.h * kHeadDim + c * 8) = o;
         }
       }
       if (tr) attn_trace(p.trace, 4, e, 3);
       ++e;
     }
+    if (threadIdx.x == 64) tc::tma_store_wait_all();   // the last tile has left shared memory
   } else {
     // ============================ softmax groups ============================
     const int g = (warp - 6) / kAtGW;                          // key half
@@ -381,12 +402,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kScale = 0.125f * kLog2e;  // 1/sqrt(64) * log2(e)
     uint32_t n = 0, ng = 0, np = 0;            // items / items with keys in this half / P blocks of this group
+    uint32_t nu = 0, nu_next = 0;              // units started
     while (w.advance()) {
       const int nb = g ? w.nb1 : w.nb0;
       const int L = w.L;
       const int key0 = (g ? w.nb0 : 0) * 64 + ch * 32;   // first key of this thread's columns in block 0
       const int i = min(w.qb * 128 + r, L - 1);          // rows past the end mirror the last row, never stored
-      const float* rel_i = sRel + w.h * kAtRelStride + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
+      // bias window of this unit's head (x log2e): refilled by the softmax threads at the unit's first item;
+      // the barrier between pass 1 and pass 2 publishes it, and the buffer was last read two units ago
+      float* relbuf = sRel + (nu & 1) * kAtRelStride;
+      if (w.first_of_unit()) {
+        const float* src = p.rel_table + (size_t)w.h * (2 * p.rel_half + 1) + p.rel_half;
+        for (int x = threadIdx.x - 6 * 32; x < 2 * kAttnTcMaxLen - 1; x += 2 * kAtGW * 32) {
+          const int d = max(-p.rel_half, min(p.rel_half, x - (kAttnTcMaxLen - 1)));   // key - query
+          relbuf[x] = __ldg(src + d) * 1.4426950408889634f;
+        }
+      }
+      if (w.last_of_unit()) ++nu_next;
+      const float* rel_i = relbuf + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
       const uint32_t par = n & 1;
       const bool tr = lane == 0 && ch == 0 && quarter == 0 && g == 0;
       if (tr) attn_trace(p.trace, 2 + g, n, 0);
@@ -516,6 +549,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       if (lane == 0) tc::mbar_arrive(st_full + par);
       if (nb > 0) ++ng;
       ++n;
+      nu = nu_next;
     }
   }
   __syncwarp();
@@ -529,9 +563,10 @@ static int attention_tc_launch(const __nv_bfloat16* qkv, int T, const int32_t* c
                                const float* rel_table, const float* rel_max, int rel_half, __nv_bfloat16* ctx,
                                int n_sm, cudaStream_t st, long long* trace = nullptr) {
   CSS_REQUIRE(max_len <= kAttnTcMaxLen, "attention_tc: sequence of %d tokens exceeds %d", max_len, kAttnTcMaxLen);
-  CUtensorMap tq, tkv;
+  CUtensorMap tq, tkv, to;
   CSS_CHECK(encode_tmap_bf16_2d(&tq, qkv, (uint64_t)T, 3 * kHidden, 3 * kHidden, 128, 64));
   CSS_CHECK(encode_tmap_bf16_2d(&tkv, qkv, (uint64_t)T, 3 * kHidden, 3 * kHidden, 64, 64));
+  CSS_CHECK(encode_tmap_bf16_2d(&to, ctx, (uint64_t)T, kHidden, kHidden, 128, 64));
   static std::atomic<uint64_t> attr_set{0};
   int dev = 0;
   CSS_CUDA(cudaGetDevice(&dev));
@@ -549,7 +584,7 @@ static int attention_tc_launch(const __nv_bfloat16* qkv, int T, const int32_t* c
   p.trace = trace;
   const int units = n_seq * kHeads;
   const int grid = units < n_sm ? units : n_sm;
-  attention_tc_kernel<<<grid, kAttnTcThreads, kAtSmem, st>>>(tq, tkv, p);
+  attention_tc_kernel<<<grid, kAttnTcThreads, kAtSmem, st>>>(tq, tkv, to, p);
   CSS_LAUNCHED();
   return CSS_OK;
 }
