@@ -192,6 +192,25 @@ def test_single_query_graph_path_matches_batch_path(native):
     enc.close()
 
 
+def test_many_short_sequences_one_pass(native):
+    """Thousands of 1..30-token sequences in one pass: cu_seqlens beyond the attention kernel's shared-memory
+    cache, one (sequence, head) unit per few CTA iterations, token rows far below a GEMM tile.  The result
+    must not depend on how the sequences are grouped into passes, and must match the oracle."""
+    from claude_semantic_search_b200.encoder import MPNetEncoder
+    from oracle import encoder_oracle as eo
+    rng = np.random.default_rng(11)
+    lengths = rng.integers(1, 31, size=3000).tolist()
+    seqs = eo.synthetic_ids(len(lengths), lengths, seed=13)
+    model = eo.build_model(seed=0, perturb=True, num_layers=2)
+    enc = MPNetEncoder.from_hf_model(model)
+    one = enc.encode_ids(seqs)
+    parts = np.concatenate([enc.encode_ids(seqs[i:i + 400]) for i in range(0, len(seqs), 400)])
+    np.testing.assert_array_equal(one, parts)
+    want = eo.st_encode_ids(model, seqs[:64], batch_size=16)
+    assert eo.cosine_rows(want, one[:64]).min() >= COS_MIN
+    enc.close()
+
+
 def test_encoder_errors(native):
     from claude_semantic_search_b200.encoder import MPNetEncoder
     from oracle import encoder_oracle as eo
