@@ -655,10 +655,8 @@ struct EpiResidLN {
         uint64_t res2 = f32x2_pack(bf16_lo(rw[k]), bf16_hi(rw[k]));
         if (rebuild) res2 = f32x2_fma(f32x2_fma(res2, rs2, nb2), g2[k], be2[k]);   // LN(resid) = ((v - mu) rstd) gamma + beta
         const uint64_t f2 = f32x2_add(f32x2_add(acc2, bias2[k]), res2);
-#if !(defined(CSS_EPI_EXP) && (CSS_EPI_EXP & 2))
         sum2 = f32x2_add(sum2, f2);
         sq2 = f32x2_fma(f2, f2, sq2);
-#endif
         float f0, f1;
         f32x2_unpack(f2, f0, f1);
         o[k] = pack_bf16(f0, f1);
