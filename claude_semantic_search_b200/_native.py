@@ -120,6 +120,11 @@ SIGNATURES = {
     "css_encoder_max_tokens": (c_int64, [c_void_p]),
     "css_encoder_max_seq_len": (c_int, [c_void_p]),
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
+    "css_tokenizer_create": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
+    "css_tokenizer_destroy": (c_int, [c_void_p]),
+    "css_tokenizer_vocab_size": (c_int, [c_void_p]),
+    "css_tokenizer_encode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                           c_void_p, c_int32]),
     "css_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "css_debug_gemm_resid_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                         ctypes.c_float, c_int, c_int, c_void_p]),

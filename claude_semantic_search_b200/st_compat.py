@@ -116,6 +116,71 @@ class WordPieceTokenizer:
         return out
 
 
+class NativeWordPieceTokenizer:
+    """The same tokenisation through libcss_b200's multi-threaded C++ implementation
+    (css_tokenizer_encode_batch), producing the packed ids / cu_seqlens the encoder consumes.
+    Texts outside its scope (anything but printable ASCII and " \\t\\n\\r") are flagged by the
+    library and tokenised by WordPieceTokenizer above, so the result is always the reference's."""
+
+    def __init__(self, vocab_file: Union[str, Path], do_lower_case: bool = True, n_threads: int = 0):
+        import ctypes
+
+        from . import _native
+        self._native = _native
+        self._py = WordPieceTokenizer(vocab_file, do_lower_case)
+        self._lib = _native.load()
+        self._h = ctypes.c_void_p()
+        _native.check(self._lib.css_tokenizer_create(str(vocab_file).encode(), 1 if do_lower_case else 0,
+                                                     ctypes.byref(self._h)))
+        self.n_threads = n_threads
+
+    def encode_packed(self, texts: Sequence[str], max_length: int):
+        import ctypes
+        n = len(texts)
+        cu = np.zeros(n + 1, np.int32)
+        if n == 0:
+            return np.zeros(0, np.int32), cu
+        raw = [t.encode("utf-8") for t in texts]
+        ptrs = (ctypes.c_char_p * n)(*raw)
+        lens = np.fromiter((len(b) for b in raw), dtype=np.int64, count=n)
+        ids = np.empty(n * max_length, np.int32)
+        fb = np.zeros(n, np.uint8)
+        self._native.check(self._lib.css_tokenizer_encode_batch(
+            self._h, ctypes.cast(ptrs, ctypes.c_void_p), lens.ctypes.data, n, max_length, ids.ctypes.data,
+            cu.ctypes.data, fb.ctypes.data, self.n_threads))
+        if not fb.any():
+            return ids[:cu[-1]], cu
+        # splice the reference-exact Python tokenisation of the flagged texts in
+        rows = np.flatnonzero(fb)
+        extra = self._py.encode_batch([texts[i] for i in rows], max_length)
+        pieces, new_cu, pos, prev = [], np.zeros(n + 1, np.int64), 0, 0
+        lengths = np.diff(cu).astype(np.int64)
+        for i, e in zip(rows, extra):
+            lengths[i] = len(e)
+        new_cu[1:] = np.cumsum(lengths)
+        out = np.empty(int(new_cu[-1]), np.int32)
+        fallback = dict(zip(rows.tolist(), extra))
+        for i in range(n):
+            a, b = int(new_cu[i]), int(new_cu[i + 1])
+            out[a:b] = fallback[i] if i in fallback else ids[cu[i]:cu[i + 1]]
+        return out, new_cu.astype(np.int32)
+
+    def encode_batch(self, texts: Sequence[str], max_length: int) -> List[List[int]]:
+        ids, cu = self.encode_packed(texts, max_length)
+        return [ids[cu[i]:cu[i + 1]].tolist() for i in range(len(texts))]
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.css_tokenizer_destroy(self._h)
+            self._h.value = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FastTokenizer:
     """tokenizer.json through the `tokenizers` package (multi-threaded)."""
 
@@ -165,7 +230,7 @@ class SentenceTransformer:
             if (model_dir / "tokenizer.json").exists():
                 self.tokenizer = FastTokenizer(model_dir / "tokenizer.json")
             elif (model_dir / "vocab.txt").exists():
-                self.tokenizer = WordPieceTokenizer(model_dir / "vocab.txt")
+                self.tokenizer = NativeWordPieceTokenizer(model_dir / "vocab.txt")
             else:
                 raise FileNotFoundError(f"{model_dir}: neither tokenizer.json nor vocab.txt")
             self.synthetic = False
@@ -206,7 +271,12 @@ class SentenceTransformer:
             return np.zeros((0, self._encoder.dim), np.float32)
         # batch_size is a host-memory knob of the reference; the device path packs whole
         # passes of up to max_tokens tokens, results do not depend on it
-        emb = self._encoder.encode_ids(self.tokenize_ids(texts), normalize=normalize_embeddings)
+        if hasattr(self.tokenizer, "encode_packed"):   # native tokenizer: straight to packed ids, no Python lists
+            max_len = min(int(self.max_seq_length), self._encoder.max_seq_len)
+            ids, cu = self.tokenizer.encode_packed(texts, max_len)
+            emb = self._encoder.encode_packed(ids, cu, normalize=normalize_embeddings)
+        else:
+            emb = self._encoder.encode_ids(self.tokenize_ids(texts), normalize=normalize_embeddings)
         return emb[0] if single else emb
 
     def close(self) -> None:

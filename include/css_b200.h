@@ -27,6 +27,7 @@
  *   faiss.write_index / read_index             src/storage.py:306,879-884 -> css_index_save / css_index_load
  *   SentenceTransformer(...).encode(...)       src/embeddings.py:184-188,216-222 -> css_encoder_encode
  *   SentenceTransformer(name).to(device)       src/embeddings.py:86-97 -> css_encoder_create
+ *   tokenisation inside .encode(...)           src/embeddings.py:216-222 -> css_tokenizer_encode_batch
  */
 #ifndef CSS_B200_H
 #define CSS_B200_H
@@ -240,6 +241,23 @@ int css_encoder_encode(css_encoder* h, const int32_t* ids_host, const int32_t* c
 int css_encoder_encode_device(css_encoder* h, const int32_t* ids_dev, const int32_t* cu_seqlens_dev,
                               const int32_t* cu_seqlens_host, int32_t n_seq, int normalize,
                               float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------ */
+/* Batch WordPiece tokenizer (host side of half A)                     */
+/* ------------------------------------------------------------------ */
+/* Replaces the tokenisation inside SentenceTransformer.encode (src/embeddings.py:216-222):
+ * BertTokenizer-style basic + WordPiece tokenisation of MPNetTokenizer over vocab.txt, <s> ... </s>
+ * framing, truncation to max_len tokens, multi-threaded, producing directly the packed ids /
+ * cu_seqlens that css_encoder_encode consumes.  Texts containing anything but printable ASCII and
+ * " \t\n\r" are NOT tokenised here: needs_fallback[i] = 1 and sequence i is empty (the host
+ * tokenises it with the reference-exact Python implementation).  ids_out holds n * max_len entries. */
+typedef struct css_tokenizer css_tokenizer;
+int css_tokenizer_create(const char* vocab_path, int do_lower_case, css_tokenizer** out);
+int css_tokenizer_destroy(css_tokenizer* h);
+int css_tokenizer_vocab_size(const css_tokenizer* h);
+int css_tokenizer_encode_batch(css_tokenizer* h, const char* const* texts, const int64_t* lens, int32_t n,
+                               int32_t max_len, int32_t* ids_out, int32_t* cu_seqlens_out,
+                               uint8_t* needs_fallback, int32_t n_threads);
 
 /* Diagnostic entry points used by the kernel-level parity tests (HOST float32 buffers,
  * rounded to bf16 on the device exactly as the encoder does):

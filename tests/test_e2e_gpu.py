@@ -87,3 +87,45 @@ def test_config1_pipeline_vs_oracle(tmp_path):
     assert st2.faiss_index.ntotal == n
     st2.close()
     gen.model.close()
+
+
+def test_local_checkpoint_text_to_embedding_vs_hf(tmp_path):
+    """Text in, embedding out through the inner seam with a LOCAL checkpoint directory (config.json +
+    pytorch_model.bin + vocab.txt): native WordPiece tokenizer -> packed ids -> B200 encoder, against
+    transformers' BertTokenizer-style tokenisation + fp32 MPNetModel + sentence-transformers pooling."""
+    import json
+    import random
+
+    import torch
+    from transformers import BertTokenizer
+
+    from claude_semantic_search_b200.st_compat import NativeWordPieceTokenizer, SentenceTransformer
+    from oracle import encoder_oracle as eo
+    rnd = random.Random(3)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+    words = sorted({"".join(rnd.choice(letters) for _ in range(rnd.randint(2, 8))) for _ in range(1500)})
+    vocab = ["<s>", "<pad>", "</s>", "[UNK]"] + words + ["##" + w[:3] for w in words[:400]] + list(letters) + \
+        ["##" + c for c in letters] + list(".,!?()-")
+    vocab = list(dict.fromkeys(vocab))
+    model = eo.build_model(seed=0, perturb=True, num_layers=2)   # vocabulary ids stay below the model's 30527 rows
+    d = tmp_path / "all-mpnet-base-v2"
+    d.mkdir()
+    (d / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    cfg = model.config.to_dict()
+    (d / "config.json").write_text(json.dumps({k: v for k, v in cfg.items() if isinstance(v, (int, float, str, bool))}))
+    torch.save(model.state_dict(), d / "pytorch_model.bin")
+    st = SentenceTransformer(str(d))
+    assert isinstance(st.tokenizer, NativeWordPieceTokenizer)
+    texts = [" ".join(rnd.choice(words) + rnd.choice(["", "", ",", ".", "!"]) for _ in range(rnd.randint(1, 120)))
+             for _ in range(40)] + ["Hello (world)!", "", "naïve café " + words[0]]
+    got = st.encode(texts, normalize_embeddings=True)
+    hf = BertTokenizer(str(d / "vocab.txt"), do_lower_case=True, unk_token="[UNK]", cls_token="<s>", sep_token="</s>",
+                       pad_token="<pad>")
+    ids = [hf.encode(t, add_special_tokens=True, truncation=True, max_length=384) for t in texts]
+    assert st.tokenize_ids(texts) == ids
+    want = eo.st_encode_ids(model, ids, batch_size=16)
+    cos = eo.cosine_rows(want, got)
+    assert cos.min() >= 0.9999, cos.min()
+    one = st.encode(texts[0], normalize_embeddings=True)
+    assert one.shape == (768,) and eo.cosine_rows(want[:1], one[None])[0] >= 0.9999
+    st.close()

@@ -33,6 +33,65 @@ def test_wordpiece_matches_transformers_bert(tmp_path):
     assert len(mine.encode_batch(["hello " * 100], max_length=16)[0]) == 16
 
 
+def test_native_wordpiece_matches_python_and_transformers(tmp_path):
+    """css_tokenizer_encode_batch (C++, multi-threaded) == WordPieceTokenizer == transformers BertTokenizer
+    on ASCII text; anything else is flagged and tokenised by the Python path (still == transformers)."""
+    import random
+    import time
+
+    from transformers import BertTokenizer
+
+    from claude_semantic_search_b200.st_compat import NativeWordPieceTokenizer, WordPieceTokenizer
+    rnd = random.Random(5)
+    letters = "abcdefghijklmnopqrstuvwxyz0123456789"
+    words = {"".join(rnd.choice(letters) for _ in range(rnd.randint(1, 7))) for _ in range(3000)}
+    pieces = {"##" + "".join(rnd.choice(letters) for _ in range(rnd.randint(1, 4))) for _ in range(2000)}
+    vocab = ["<s>", "<pad>", "</s>", "[UNK]"] + sorted(words) + sorted(pieces) + list("abcdefghijklmnopqrstuvwxyz") + \
+        ["##" + c for c in letters] + list("!\"#$%&'()*+,-./:;<=>?@[]^_`{|}~") + ["cafe"]
+    vocab = list(dict.fromkeys(vocab))
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    native = NativeWordPieceTokenizer(vf, n_threads=4)
+    py = WordPieceTokenizer(vf)
+    hf = BertTokenizer(str(vf), do_lower_case=True, unk_token="[UNK]", cls_token="<s>", sep_token="</s>",
+                       pad_token="<pad>")
+    wl = sorted(words)
+
+    def text():
+        out = []
+        for _ in range(rnd.randint(0, 60)):
+            r = rnd.random()
+            if r < 0.6:
+                w = rnd.choice(wl)
+            elif r < 0.8:
+                w = rnd.choice(wl) + rnd.choice(wl)[:3]
+            elif r < 0.9:
+                w = "".join(rnd.choice(letters + "ABCXYZ") for _ in range(rnd.randint(1, 12)))
+            else:
+                w = rnd.choice("!,.;:()[]{}-_/\\'\"@#")
+            out.append(w)
+            out.append(rnd.choice([" ", " ", " ", "", "\n", "\t", "  "]))
+        return "".join(out)
+
+    texts = [text() for _ in range(400)] + ["", " ", "x" * 150, "Hello, World!", "a" * 101 + " b", "tab\tsep\r\nline"]
+    texts += ["Unbelievable café", "naïve résumé", "日本語 text", "ctrl\x0bchar", "zero\x00byte"]   # out of the native scope
+    for max_len in (16, 64, 384):
+        got = native.encode_batch(texts, max_len)
+        assert got == py.encode_batch(texts, max_len)
+        for t, g in zip(texts[:120] + texts[-11:], got[:120] + got[-11:]):
+            if "\x0b" in t or "\x00" in t:
+                continue   # transformers drops these control characters; the Python path keeps its documented behaviour
+            assert g == hf.encode(t, add_special_tokens=True, truncation=True, max_length=max_len), t
+    ids, cu = native.encode_packed(texts, 384)
+    assert cu[0] == 0 and cu[-1] == ids.shape[0] and (np.diff(cu) >= 2).all()
+    big = [text() * 8 for _ in range(4000)]
+    t0 = time.perf_counter()
+    ids, cu = native.encode_packed(big, 384)
+    dt = time.perf_counter() - t0
+    print(f"native tokenizer: {len(big) / dt:.0f} texts/s, {ids.shape[0] / dt / 1e6:.1f} M tokens/s")
+    native.close()
+
+
 def test_standin_tokenizer_is_deterministic_and_bounded():
     from claude_semantic_search_b200.st_compat import StandInTokenizer
     t = StandInTokenizer()
