@@ -36,6 +36,42 @@ def cpu_encoder_baseline(n_seq: int = 16):
             "sample": f"{n_seq} chunks x {SEQ_LEN} tokens, batch 16, fp32 transformers MPNetModel + ST pooling on the host"}
 
 
+def bench_text_to_embedding(enc, n_seq: int, reps: int = 3):
+    """Text in, embedding out: native WordPiece tokenizer (css_tokenizer_encode_batch, synthetic 30527-entry
+    vocabulary written to a temporary vocab.txt) -> packed ids -> css_encoder_encode, all on host buffers."""
+    import random
+    import tempfile
+    from pathlib import Path
+
+    from claude_semantic_search_b200.st_compat import NativeWordPieceTokenizer
+    rnd = random.Random(17)
+    letters = "abcdefghijklmnopqrstuvwxyz"
+    words = sorted({"".join(rnd.choice(letters) for _ in range(rnd.randint(2, 9))) for _ in range(24000)})
+    vocab = ["<s>", "<pad>", "</s>", "[UNK]"] + words + ["##" + w[:4] for w in words[:6000]] + list(letters) + \
+        ["##" + c for c in letters] + list(".,!?()-:;")
+    vocab = list(dict.fromkeys(vocab))[:30527]
+    with tempfile.TemporaryDirectory() as d:
+        vf = Path(d) / "vocab.txt"
+        vf.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+        tok = NativeWordPieceTokenizer(vf)
+        texts = [" ".join(rnd.choice(words) + rnd.choice(["", "", "", ",", "."]) for _ in range(400)) for _ in range(n_seq)]
+        tok.encode_packed(texts[:8], SEQ_LEN)
+        t_tok = t_all = 0.0
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ids, cu = tok.encode_packed(texts, SEQ_LEN)
+            t1 = time.perf_counter()
+            emb = enc.encode_packed(ids, cu)
+            t2 = time.perf_counter()
+            t_tok += t1 - t0
+            t_all += t2 - t0
+        tok.close()
+    assert emb.shape == (n_seq, 768) and int(cu[-1]) == n_seq * SEQ_LEN
+    return {"chunks_per_s": n_seq * reps / t_all, "tokenizer_chunks_per_s": n_seq * reps / t_tok,
+            "tokenizer_threads": "hardware_concurrency, at most 16", "chars_per_chunk": int(np.mean([len(t) for t in texts])),
+            "api": "css_tokenizer_encode_batch + css_encoder_encode (host text -> host embeddings, tokenise and encode not overlapped)"}
+
+
 def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warmup: int = 3):
     from claude_semantic_search_b200 import _native as native
     from claude_semantic_search_b200.encoder import MPNetEncoder, random_state_dict
@@ -82,6 +118,12 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warm
     emb = enc.encode_packed(ids, cu)
     t_e2e = time.perf_counter() - t0
     assert np.isfinite(emb).all() and abs(float(np.linalg.norm(emb[0])) - 1) < 1e-3
+    text_leg = None
+    if rank == 0:
+        try:
+            text_leg = bench_text_to_embedding(enc, n_seq)
+        except Exception as e:  # report, never hide
+            text_leg = {"error": repr(e)}
     enc.close()
     res = {"encode": {"chunks_per_s": chunks_s, "ms_per_step": ms / steps, "chunks_per_step_per_gpu": n_seq,
                       "seq_len": SEQ_LEN, "achieved_tflops_per_gpu": tf,
@@ -90,6 +132,8 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warm
                       "gpu_launches": int(launches), "clocks": clocks,
                       "e2e_chunks_per_s": n_seq / t_e2e * world, "h2d_bytes_per_step": int(ids.nbytes + cu.nbytes),
                       "d2h_bytes_per_step": int(emb.nbytes)}}
+    if text_leg is not None:
+        res["encode"]["e2e_from_text"] = text_leg
     if rank == 0 and not getattr(args, "no_cpu", False):
         res["encode"]["cpu_baseline"] = cpu_encoder_baseline()
     return res
