@@ -101,6 +101,7 @@ SIGNATURES = {
     "css_index_reset": (c_int, [c_void_p]),
     "css_index_add": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int64)]),
     "css_index_add_device": (c_int, [c_void_p, c_void_p, c_int64, c_int, POINTER(c_int64), c_void_p]),
+    "css_index_compact": (c_int, [c_void_p, c_void_p, c_int64]),
     "css_index_get_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p]),
     "css_index_set_column": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_int64]),
     "css_index_set_alive": (c_int, [c_void_p, c_void_p, c_int64, c_int64]),
@@ -305,6 +306,11 @@ class Index:
         check(self._lib.css_index_add_device(self._h, c_void_p(x_dev_ptr), n, 1 if normalize else 0,
                                              ctypes.byref(first), c_void_p(stream)))
         return first.value
+
+    def compact(self, keep_ids) -> None:
+        """Keep exactly the rows `keep_ids` (strictly ascending), renumbered 0..len-1, on the device."""
+        k = np.ascontiguousarray(keep_ids, dtype=np.int64)
+        check(self._lib.css_index_compact(self._h, k.ctypes.data, k.shape[0]))
 
     def get_rows(self, start: int, n: int) -> np.ndarray:
         out = np.empty((n, self.dim), np.float32)

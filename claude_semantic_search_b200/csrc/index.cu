@@ -411,6 +411,84 @@ int css_index_reset(css_index* h) {
   return CSS_OK;
 }
 
+int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep) {
+  CSS_REQUIRE(h != nullptr, "index is NULL");
+  CSS_REQUIRE(n_keep >= 0 && (n_keep == 0 || keep_ids_host != nullptr), "bad keep list");
+  std::lock_guard<std::mutex> lk(h->mu);
+  CSS_REQUIRE(n_keep <= h->ntotal, "keep list longer than the index (%lld > %lld)", (long long)n_keep,
+              (long long)h->ntotal);
+  for (int64_t i = 0; i < n_keep; ++i) {
+    const int64_t id = keep_ids_host[i];
+    CSS_REQUIRE(id >= 0 && id < h->ntotal && (i == 0 || id > keep_ids_host[i - 1]),
+                "keep ids must be strictly ascending row ids (entry %lld = %lld)", (long long)i, (long long)id);
+  }
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const int d = h->dim;
+  const int64_t win = 65536;   // rows per window: 200 MB of fp32 staging at d = 768
+  int64_t* ids_dev = nullptr;
+  float* sx = nullptr;
+  __nv_bfloat16* sb = nullptr;
+  int32_t* sc = nullptr;
+  uint32_t* sw = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(ids_dev); cudaFree(sx); cudaFree(sb); cudaFree(sc); cudaFree(sw);
+  };
+  if (n_keep > 0) {
+    const int64_t w = std::min(win, n_keep);
+    if (cudaMalloc(&ids_dev, (size_t)n_keep * 8) != cudaSuccess || cudaMalloc(&sx, (size_t)w * d * 4) != cudaSuccess ||
+        cudaMalloc(&sb, (size_t)w * d * 2) != cudaSuccess || cudaMalloc(&sc, (size_t)w * 4) != cudaSuccess ||
+        cudaMalloc(&sw, (size_t)words_for(n_keep) * 4) != cudaSuccess) {
+      (void)cudaGetLastError();
+      cleanup();
+      set_error("compaction staging allocation failed");
+      return CSS_ERR_OOM;
+    }
+    cudaError_t ce = cudaMemcpyAsync(ids_dev, keep_ids_host, (size_t)n_keep * 8, cudaMemcpyHostToDevice, st);
+    // alive bits first (they are read by row id from the old layout)
+    if (ce == cudaSuccess) {
+      gather_bits_kernel<<<(unsigned)((n_keep + 255) / 256), 256, 0, st>>>(h->alive, ids_dev, n_keep, sw);
+      css::g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    for (int64_t i0 = 0; i0 < n_keep && ce == cudaSuccess; i0 += win) {
+      const int64_t n = std::min(win, n_keep - i0);
+      gather_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h->x, h->xb, ids_dev + i0, n, d, sx, sb);
+      css::g_launches.fetch_add(1, std::memory_order_relaxed);
+      ce = cudaMemcpyAsync(h->x + i0 * d, sx, (size_t)n * d * 4, cudaMemcpyDeviceToDevice, st);
+      if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->xb + i0 * d, sb, (size_t)n * d * 2, cudaMemcpyDeviceToDevice, st);
+      for (int c = 0; c < CSS_MAX_COLUMNS && ce == cudaSuccess; ++c) {
+        if (!h->cols[c]) continue;
+        gather_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cols[c], ids_dev + i0, n, sc);
+        css::g_launches.fetch_add(1, std::memory_order_relaxed);
+        ce = cudaMemcpyAsync(h->cols[c] + i0, sc, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+      }
+    }
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, st);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->alive, sw, (size_t)words_for(n_keep) * 4, cudaMemcpyDeviceToDevice, st);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+    if (ce == cudaSuccess) ce = cudaGetLastError();
+    cleanup();
+    if (ce != cudaSuccess) {
+      set_error("compaction failed: %s", cudaGetErrorString(ce));
+      return CSS_ERR_CUDA;
+    }
+  } else if (h->capacity > 0) {
+    CSS_CUDA(cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, st));
+    CSS_CUDA(cudaStreamSynchronize(st));
+  }
+  // rows past the new end: NULL columns again (what a fresh row looks like)
+  for (int c = 0; c < CSS_MAX_COLUMNS; ++c) {
+    if (!h->cols[c] || h->ntotal <= n_keep) continue;
+    const int64_t n = h->ntotal - n_keep;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cols[c] + n_keep, n, CSS_NULL_VALUE);
+    CSS_LAUNCHED();
+  }
+  CSS_CUDA(cudaStreamSynchronize(st));
+  h->ntotal = n_keep;
+  h->any_dead = true;   // conservative: the scan keeps honouring the alive bits
+  return CSS_OK;
+}
+
 int css_index_add(css_index* h, const float* x_host, int64_t n, int normalize, int64_t* first_id_out) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
   CSS_REQUIRE(n >= 0, "n < 0");

@@ -426,6 +426,42 @@ static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t
   }
 }
 
+// ------------------------------------------------------------------------
+// Compaction (HybridStorage.optimize): row i of the window takes row ids[i] of the index.
+// One warp per row, float4 copies of the fp32 row and its bf16 shadow into a staging
+// buffer; the caller then copies the staging window to rows [i0, i0 + n) (ids ascending,
+// so no source row of a later window has been overwritten).
+// ------------------------------------------------------------------------
+static __global__ void gather_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xb,
+                                          const int64_t* __restrict__ ids, int64_t n, int d,
+                                          float* __restrict__ out, __nv_bfloat16* __restrict__ outb) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const int64_t src = ids[i];
+  for (int j = lane; j < d; j += 32) {
+    out[i * d + j] = x[src * d + j];
+    outb[i * d + j] = xb[src * d + j];
+  }
+}
+static __global__ void gather_i32_kernel(const int32_t* __restrict__ col, const int64_t* __restrict__ ids, int64_t n,
+                                         int32_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = col[ids[i]];
+}
+// alive bits of the gathered rows, one output word per 32 rows (ballot)
+static __global__ void gather_bits_kernel(const uint32_t* __restrict__ bits, const int64_t* __restrict__ ids, int64_t n,
+                                          uint32_t* __restrict__ out_words) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool b = false;
+  if (i < n) {
+    const int64_t s = ids[i];
+    b = (bits[s >> 5] >> (s & 31)) & 1u;
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0 && i < n) out_words[i >> 5] = w;
+}
+
 static __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;

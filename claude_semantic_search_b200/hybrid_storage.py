@@ -616,20 +616,20 @@ class HybridStorage:
         """VACUUM, then compact orphaned vectors out of the device index (the
         reference's rebuild is a stub that drops every vector, src/storage.py:944-969)."""
         self.db.execute("VACUUM")
-        if self.faiss_index is not None and self.total_chunks != self.faiss_index.ntotal:
+        if self.faiss_index is None:
+            return
+        nt = self.faiss_index.ntotal
+        # the reference's trigger (:936) plus rows orphaned by remove_chunks_for_file, which leaves
+        # total_chunks untouched there (:817-846) and here
+        if self.total_chunks != nt or len(self.faiss_id_to_chunk_id) != nt:
             self._rebuild_faiss_index()
 
     def _rebuild_faiss_index(self) -> None:
         rows = self.db.execute("SELECT id, faiss_id FROM chunks WHERE faiss_id IS NOT NULL ORDER BY faiss_id").fetchall()
         old = self.faiss_index
-        new = self._create_index()
         kept = [(r["id"], r["faiss_id"]) for r in rows if 0 <= r["faiss_id"] < old.ntotal]
-        for s in range(0, len(kept), 65536):
-            part = kept[s:s + 65536]
-            vecs = np.concatenate([old._native.get_rows(fid, 1) for _, fid in part]) if part else None
-            if vecs is not None:
-                new._native.add(vecs, normalize=False)
-        self.faiss_index = new
+        # device-side gather of the surviving rows (css_index_compact): no vector leaves HBM
+        old._native.compact([fid for _, fid in kept])
         self.db.executemany("UPDATE chunks SET faiss_id = ? WHERE id = ?",
                             [(i, cid) for i, (cid, _) in enumerate(kept)])
         self.db.commit()

@@ -96,6 +96,11 @@ int css_index_add(css_index* h, const float* x_host, int64_t n, int normalize,
 /* Same with x in DEVICE memory of the index's device (e.g. encoder output). */
 int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normalize,
                          int64_t* first_id_out, void* stream);
+/* Compaction on the device (HybridStorage.optimize / _rebuild_faiss_index, src/storage.py:930-969,
+ * which the reference leaves as a stub): the index keeps exactly the rows keep_ids[0..n_keep)
+ * (strictly ascending row ids), renumbered 0..n_keep-1 in that order, together with their
+ * metadata columns and alive bits.  HBM-bound gather, no host round trip of the vectors. */
+int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep);
 /* faiss reconstruct_n: copy rows [start, start+n) back to host. */
 int css_index_get_rows(css_index* h, int64_t start, int64_t n, float* out_host);
 

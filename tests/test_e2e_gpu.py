@@ -89,6 +89,55 @@ def test_config1_pipeline_vs_oracle(tmp_path):
     gen.model.close()
 
 
+def test_optimize_compacts_orphans_on_device(tmp_path):
+    """remove_chunks_for_file / delete_chunk orphan rows (src/storage.py:836-846); optimize() gathers
+    the survivors on the device (css_index_compact) -- searches before and after return the same
+    chunks and scores, ntotal shrinks to the live count, and the compacted index persists."""
+    from claude_semantic_search_b200 import HybridStorage, SearchConfig, StorageConfig
+
+    n = 600
+    chunks = _make_chunks(n, seed=77)
+    rng = np.random.default_rng(3)
+    emb = rng.standard_normal((n, 768)).astype(np.float32)
+    for c, e in zip(chunks, emb):
+        c.embedding = e
+    st = HybridStorage(StorageConfig(data_dir=str(tmp_path), use_gpu=True))
+    st.initialize()
+    st.add_chunks(chunks)
+    removed = st.remove_chunks_for_file("/f/3.jsonl") + st.remove_chunks_for_file("/f/17.jsonl")
+    assert removed == 30
+    assert st.delete_chunk("chunk_00000")
+    live = n - removed - 1
+    assert st.faiss_index.ntotal == n
+    qs = rng.standard_normal((12, 768)).astype(np.float32)
+    flt = {"project_name": "alpha"}
+    before = [[(r.chunk_id, r.similarity) for r in st.search(q, SearchConfig(top_k=10))] for q in qs]
+    before_f = [[(r.chunk_id, r.similarity) for r in st.search(q, SearchConfig(top_k=10), filters=flt)] for q in qs]
+    assert all(len(b) == 10 for b in before)
+    st.optimize()
+    assert st.faiss_index.ntotal == live and len(st.faiss_id_to_chunk_id) == live
+    assert sorted(st.faiss_id_to_chunk_id) == list(range(live))
+    after = [[(r.chunk_id, r.similarity) for r in st.search(q, SearchConfig(top_k=10))] for q in qs]
+    after_f = [[(r.chunk_id, r.similarity) for r in st.search(q, SearchConfig(top_k=10), filters=flt)] for q in qs]
+    assert after == before and after_f == before_f        # same rows, same fp32 arithmetic: bit-identical
+    # appending after compaction continues from the compacted row count
+    extra = _make_chunks(5, seed=5)
+    for i, c in enumerate(extra):
+        c.id = f"extra_{i}"
+        c.embedding = qs[i]
+    st.add_chunks(extra)
+    assert st.faiss_index.ntotal == live + 5
+    top = st.search(qs[2], SearchConfig(top_k=1))
+    assert top[0].chunk_id == "extra_2" and abs(top[0].similarity - 1.0) < 1e-4
+    st.close()
+    st2 = HybridStorage(StorageConfig(data_dir=str(tmp_path), use_gpu=True))
+    st2.initialize()
+    assert st2.faiss_index.ntotal == live + 5
+    again = [[(r.chunk_id, r.similarity) for r in st2.search(q, SearchConfig(top_k=10))] for q in qs[5:]]
+    assert again == before[5:]
+    st2.close()
+
+
 def test_local_checkpoint_text_to_embedding_vs_hf(tmp_path):
     """Text in, embedding out through the inner seam with a LOCAL checkpoint directory (config.json +
     pytorch_model.bin + vocab.txt): native WordPiece tokenizer -> packed ids -> B200 encoder, against

@@ -295,6 +295,47 @@ def test_faiss_file_roundtrip(native, tmp_path):
     idx2.close()
 
 
+# ------------------------------------------------------------ compaction
+@pytest.mark.parametrize("n,keep_frac", [(1, 1.0), (1000, 0.5), (70_000, 0.3), (70_000, 1.0), (5000, 0.0)])
+def test_compact_on_device(native, n, keep_frac):
+    """css_index_compact (HybridStorage.optimize): the kept rows, their columns and alive bits move
+    to ids 0..n_keep-1 in order; searches and filters afterwards equal the oracle on the kept rows."""
+    rng = np.random.default_rng(n + int(keep_frac * 10))
+    d = 768
+    x = so.normalize_rows(rng.standard_normal((n, d), dtype=np.float32))
+    col = rng.integers(0, 50, size=n).astype(np.int32)
+    alive = (rng.random(n) < 0.9).astype(np.uint8)
+    idx = native.Index(d)
+    idx.add(x)
+    idx.set_column(2, col)
+    idx.set_alive(alive)
+    keep = np.flatnonzero(rng.random(n) < keep_frac).astype(np.int64)
+    idx.compact(keep)
+    assert idx.ntotal == keep.shape[0]
+    if keep.shape[0]:
+        np.testing.assert_array_equal(idx.get_rows(0, keep.shape[0]), x[keep])
+        xk, ak = x[keep], alive[keep].astype(bool)
+        q = so.normalize_rows(rng.standard_normal((20, d), dtype=np.float32))
+        for qq in (q[:2], q):                      # streaming scan and batched path
+            D, I = idx.search(qq, 10)              # dead rows never come back
+            Dr, Ir = so.flat_search(xk, qq, 10, mask=ak)
+            _check(Dr, Ir, D, I)
+        flt = native.Filter().add_range(2, 10, 30)
+        words, n_pass = idx.filter_mask(flt)
+        want = ak & (col[keep] >= 10) & (col[keep] <= 30)
+        np.testing.assert_array_equal(words, so.pack_mask(want))
+        assert n_pass == int(want.sum())
+        # appending after a compaction continues the dense id sequence
+        first = idx.add(x[:3])
+        assert first == keep.shape[0] and idx.ntotal == keep.shape[0] + min(3, n)
+    else:
+        D, I = idx.search(x[:1], 5)
+        assert (I == -1).all()
+    with pytest.raises(native.NativeError):
+        idx.compact([0, 0])                        # not strictly ascending
+    idx.close()
+
+
 # -------------------------------------------- full-size property (config 2)
 def test_one_million_rows_planted_needles(native):
     """BASELINE config 2 size.  The CPU oracle checks 4 queries in full; the rest
