@@ -124,6 +124,7 @@ SIGNATURES = {
     "css_tokenizer_create": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
     "css_tokenizer_destroy": (c_int, [c_void_p]),
     "css_tokenizer_vocab_size": (c_int, [c_void_p]),
+    "css_tokenizer_add_special": (c_int, [c_void_p, ctypes.c_char_p, c_int32]),
     "css_tokenizer_encode_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
                                            c_void_p, c_int32]),
     "css_debug_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

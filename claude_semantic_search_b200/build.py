@@ -34,7 +34,7 @@ def _sources():
 
 
 def _deps():
-    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+    return sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list(CSRC.glob("*.inc"))
                   + [ROOT / "include" / "css_b200.h", Path(__file__)])
 
 

@@ -116,13 +116,61 @@ class WordPieceTokenizer:
         return out
 
 
-class NativeWordPieceTokenizer:
-    """The same tokenisation through libcss_b200's multi-threaded C++ implementation
-    (css_tokenizer_encode_batch), producing the packed ids / cu_seqlens the encoder consumes.
-    Texts outside its scope (anything but printable ASCII and " \\t\\n\\r") are flagged by the
-    library and tokenised by WordPieceTokenizer above, so the result is always the reference's."""
+MPNET_SPECIALS = ("<s>", "<pad>", "</s>", "<unk>", "[UNK]", "<mask>")
 
-    def __init__(self, vocab_file: Union[str, Path], do_lower_case: bool = True, n_threads: int = 0):
+
+def native_tokenizer_settings(tokenizer_json: Union[str, Path]) -> Optional[Dict]:
+    """Read a `tokenizers` tokenizer.json and return {"lower": bool, "specials": {literal: id}} when it
+    is the pipeline css_tokenizer_encode_batch implements (BertNormalizer with clean_text +
+    handle_chinese_chars and strip_accents following lowercase, BertPreTokenizer, WordPiece with "##"
+    and 100 characters per word, <s> ... </s> framing, added tokens matched on the raw text); None
+    otherwise (the caller then keeps the `tokenizers` package)."""
+    import json
+    try:
+        cfg = json.loads(Path(tokenizer_json).read_text(encoding="utf-8"))
+    except (OSError, ValueError):
+        return None
+    nz, pt, model = cfg.get("normalizer") or {}, cfg.get("pre_tokenizer") or {}, cfg.get("model") or {}
+    if nz.get("type") != "BertNormalizer" or not nz.get("clean_text", True) or not nz.get("handle_chinese_chars", True):
+        return None
+    lower = bool(nz.get("lowercase", True))
+    if nz.get("strip_accents") not in (None, lower):
+        return None
+    if pt.get("type") != "BertPreTokenizer" or model.get("type", "WordPiece") != "WordPiece":
+        return None
+    if model.get("continuing_subword_prefix", "##") != "##" or model.get("max_input_chars_per_word", 100) != 100:
+        return None
+    vocab = model.get("vocab") or {}
+    if model.get("unk_token", "[UNK]") not in ("[UNK]", "<unk>") or vocab.get("<s>") is None or vocab.get("</s>") is None:
+        return None
+    post = cfg.get("post_processor") or {}
+    if post.get("type") == "RobertaProcessing":
+        if post.get("cls", ["<s>"])[0] != "<s>" or post.get("sep", ["</s>"])[0] != "</s>":
+            return None
+    elif post.get("type") == "TemplateProcessing":
+        single = [next(iter(x.values())).get("id") for x in post.get("single", [])]
+        if single != ["<s>", "A", "</s>"]:
+            return None
+    else:
+        return None
+    specials = {}
+    for at in cfg.get("added_tokens") or []:
+        if at.get("single_word") or (at.get("normalized") and not at.get("special")):
+            return None
+        specials[at["content"]] = int(at["id"])
+    return {"lower": lower, "specials": specials, "vocab": vocab}
+
+
+class NativeWordPieceTokenizer:
+    """The reference's fast tokenizer pipeline (BertNormalizer -> BertPreTokenizer -> WordPiece, <s> ... </s>,
+    truncation) through libcss_b200's multi-threaded C++ implementation (css_tokenizer_encode_batch),
+    producing the packed ids / cu_seqlens the encoder consumes.  Covers all of Unicode (tables generated
+    from the `tokenizers` package, scripts/gen_unicode_tables.py) and the added special tokens, which are
+    cut out of the raw text like the reference does (`specials`: literal -> id; default: the MPNet
+    specials present in the vocabulary)."""
+
+    def __init__(self, vocab_file: Union[str, Path], do_lower_case: bool = True, n_threads: int = 0,
+                 specials: Optional[Dict[str, int]] = None):
         import ctypes
 
         from . import _native
@@ -132,6 +180,11 @@ class NativeWordPieceTokenizer:
         self._h = ctypes.c_void_p()
         _native.check(self._lib.css_tokenizer_create(str(vocab_file).encode(), 1 if do_lower_case else 0,
                                                      ctypes.byref(self._h)))
+        if specials is None:
+            specials = {s: self._py.vocab[s] for s in MPNET_SPECIALS if s in self._py.vocab}
+        self.specials = dict(specials)
+        for lit, tid in self.specials.items():
+            _native.check(self._lib.css_tokenizer_add_special(self._h, lit.encode("utf-8"), int(tid)))
         self.n_threads = n_threads
 
     def encode_packed(self, texts: Sequence[str], max_length: int):
@@ -150,7 +203,7 @@ class NativeWordPieceTokenizer:
             cu.ctypes.data, fb.ctypes.data, self.n_threads))
         if not fb.any():
             return ids[:cu[-1]], cu
-        # splice the reference-exact Python tokenisation of the flagged texts in
+        # malformed UTF-8 (cannot come from a Python str): splice the Python tokenisation in
         rows = np.flatnonzero(fb)
         extra = self._py.encode_batch([texts[i] for i in rows], max_length)
         pieces, new_cu, pos, prev = [], np.zeros(n + 1, np.int64), 0, 0
@@ -227,11 +280,10 @@ class SentenceTransformer:
         model_dir = None if model_name_or_path == "synthetic-mpnet" else _find_model_dir(model_name_or_path, cache_folder)
         if model_dir is not None:
             self._encoder = MPNetEncoder.from_pretrained(model_dir, device=self._device_index)
-            if (model_dir / "tokenizer.json").exists():
-                self.tokenizer = FastTokenizer(model_dir / "tokenizer.json")
-            elif (model_dir / "vocab.txt").exists():
-                self.tokenizer = NativeWordPieceTokenizer(model_dir / "vocab.txt")
-            else:
+            self.tokenizer = self._load_tokenizer(model_dir)
+            if self.tokenizer is None and (model_dir / "tokenizer.json").exists():
+                self.tokenizer = FastTokenizer(model_dir / "tokenizer.json")   # a pipeline the native one does not implement
+            if self.tokenizer is None:
                 raise FileNotFoundError(f"{model_dir}: neither tokenizer.json nor vocab.txt")
             self.synthetic = False
         elif synthetic:
@@ -243,6 +295,29 @@ class SentenceTransformer:
                 f"model '{model_name_or_path}' not found locally (cache_folder={cache_folder!r}); this build does "
                 "not download.  Point cache_folder at a directory holding the checkpoint, or set "
                 "CSS_B200_SYNTHETIC_MODEL=1 for random-init weights + stand-in tokenizer (benchmarks only).")
+
+    @staticmethod
+    def _load_tokenizer(model_dir: Path):
+        """The native tokenizer whenever the checkpoint's tokenizer is the pipeline it implements
+        (tokenizer.json inspected when present; vocab.txt alone means MPNetTokenizer defaults)."""
+        vocab_txt, tj = model_dir / "vocab.txt", model_dir / "tokenizer.json"
+        if os.environ.get("CSS_B200_NATIVE_TOKENIZER", "1") == "0" and tj.exists():
+            return None
+        if tj.exists():
+            st = native_tokenizer_settings(tj)
+            if st is None or not vocab_txt.exists():
+                return None
+            with open(vocab_txt, encoding="utf-8") as fh:
+                same = all(st["vocab"].get(line.rstrip("\n")) == i for i, line in enumerate(fh))
+            return NativeWordPieceTokenizer(vocab_txt, st["lower"], specials=st["specials"]) if same else None
+        if vocab_txt.exists():
+            lower = True
+            tc = model_dir / "tokenizer_config.json"
+            if tc.exists():
+                import json
+                lower = bool(json.loads(tc.read_text(encoding="utf-8")).get("do_lower_case", True))
+            return NativeWordPieceTokenizer(vocab_txt, lower)
+        return None
 
     # -- API surface the reference uses -----------------------------------------------
     def to(self, device) -> "SentenceTransformer":

@@ -250,16 +250,19 @@ int css_encoder_encode_device(css_encoder* h, const int32_t* ids_dev, const int3
 /* ------------------------------------------------------------------ */
 /* Batch WordPiece tokenizer (host side of half A)                     */
 /* ------------------------------------------------------------------ */
-/* Replaces the tokenisation inside SentenceTransformer.encode (src/embeddings.py:216-222):
- * BertTokenizer-style basic + WordPiece tokenisation of MPNetTokenizer over vocab.txt, <s> ... </s>
- * framing, truncation to max_len tokens, multi-threaded, producing directly the packed ids /
- * cu_seqlens that css_encoder_encode consumes.  Texts containing anything but printable ASCII and
- * " \t\n\r" are NOT tokenised here: needs_fallback[i] = 1 and sequence i is empty (the host
- * tokenises it with the reference-exact Python implementation).  ids_out holds n * max_len entries. */
+/* Replaces the tokenisation inside SentenceTransformer.encode (src/embeddings.py:216-222), i.e. the
+ * fast MPNetTokenizer pipeline BertNormalizer -> BertPreTokenizer -> WordPiece over vocab.txt with
+ * <s> ... </s> framing and truncation to max_len tokens; multi-threaded, producing directly the packed
+ * ids / cu_seqlens that css_encoder_encode consumes.  Any valid UTF-8 is tokenised natively (Unicode
+ * tables generated from that pipeline, scripts/gen_unicode_tables.py).  css_tokenizer_add_special
+ * registers a literal (e.g. "<s>", "<mask>") that is cut out of the RAW text and mapped straight to
+ * `id`, leftmost-longest, like the reference's added special tokens.  Malformed UTF-8 is NOT
+ * tokenised: needs_fallback[i] = 1 and sequence i is empty.  ids_out holds n * max_len entries. */
 typedef struct css_tokenizer css_tokenizer;
 int css_tokenizer_create(const char* vocab_path, int do_lower_case, css_tokenizer** out);
 int css_tokenizer_destroy(css_tokenizer* h);
 int css_tokenizer_vocab_size(const css_tokenizer* h);
+int css_tokenizer_add_special(css_tokenizer* h, const char* literal, int32_t id);
 int css_tokenizer_encode_batch(css_tokenizer* h, const char* const* texts, const int64_t* lens, int32_t n,
                                int32_t max_len, int32_t* ids_out, int32_t* cu_seqlens_out,
                                uint8_t* needs_fallback, int32_t n_threads);

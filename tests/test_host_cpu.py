@@ -35,7 +35,7 @@ def test_wordpiece_matches_transformers_bert(tmp_path):
 
 def test_native_wordpiece_matches_python_and_transformers(tmp_path):
     """css_tokenizer_encode_batch (C++, multi-threaded) == WordPieceTokenizer == transformers BertTokenizer
-    on ASCII text; anything else is flagged and tokenised by the Python path (still == transformers)."""
+    on ASCII and simple accented / CJK text (the full Unicode sweep is the next test)."""
     import random
     import time
 
@@ -74,13 +74,13 @@ def test_native_wordpiece_matches_python_and_transformers(tmp_path):
         return "".join(out)
 
     texts = [text() for _ in range(400)] + ["", " ", "x" * 150, "Hello, World!", "a" * 101 + " b", "tab\tsep\r\nline"]
-    texts += ["Unbelievable café", "naïve résumé", "日本語 text", "ctrl\x0bchar", "zero\x00byte"]   # out of the native scope
+    texts += ["Unbelievable café", "naïve résumé", "日本語 text"]
+    ctrl = ["ctrl\x0bchar", "zero\x00byte"]   # control characters are dropped (the Python stand-in keeps them)
     for max_len in (16, 64, 384):
         got = native.encode_batch(texts, max_len)
         assert got == py.encode_batch(texts, max_len)
-        for t, g in zip(texts[:120] + texts[-11:], got[:120] + got[-11:]):
-            if "\x0b" in t or "\x00" in t:
-                continue   # transformers drops these control characters; the Python path keeps its documented behaviour
+        got_c = native.encode_batch(ctrl, max_len)
+        for t, g in zip(texts[:120] + texts[-9:] + ctrl, got[:120] + got[-9:] + got_c):
             assert g == hf.encode(t, add_special_tokens=True, truncation=True, max_length=max_len), t
     ids, cu = native.encode_packed(texts, 384)
     assert cu[0] == 0 and cu[-1] == ids.shape[0] and (np.diff(cu) >= 2).all()
@@ -90,6 +90,104 @@ def test_native_wordpiece_matches_python_and_transformers(tmp_path):
     dt = time.perf_counter() - t0
     print(f"native tokenizer: {len(big) / dt:.0f} texts/s, {ids.shape[0] / dt / 1e6:.1f} M tokens/s")
     native.close()
+
+
+def _reference_fast_tokenizer(vocab, lower, specials):
+    """The pipeline behind MPNetTokenizerFast (what sentence-transformers' AutoTokenizer gives the
+    reference, src/embeddings.py:136-151), assembled from the `tokenizers` package."""
+    from tokenizers import AddedToken, Tokenizer
+    from tokenizers.models import WordPiece
+    from tokenizers.normalizers import BertNormalizer
+    from tokenizers.pre_tokenizers import BertPreTokenizer
+    from tokenizers.processors import TemplateProcessing
+    ids = {w: i for i, w in enumerate(vocab)}
+    tok = Tokenizer(WordPiece(ids, unk_token="[UNK]", max_input_chars_per_word=100))
+    tok.normalizer = BertNormalizer(clean_text=True, handle_chinese_chars=True, strip_accents=None, lowercase=lower)
+    tok.pre_tokenizer = BertPreTokenizer()
+    tok.post_processor = TemplateProcessing(single="<s> $A </s>", special_tokens=[("<s>", ids["<s>"]), ("</s>", ids["</s>"])])
+    tok.add_special_tokens([AddedToken(s, lstrip=(s == "<mask>")) for s in specials])
+    return tok
+
+
+def test_native_tokenizer_equals_fast_pipeline_on_all_of_unicode(tmp_path):
+    """Every code point (inside a word, doubled, and after a space), random mixed-script strings, the
+    NFD reordering corner, added special tokens in the raw text, truncation -- identical ids to the
+    `tokenizers` BertNormalizer / BertPreTokenizer / WordPiece pipeline, in both case modes; then the
+    tokenizer.json inspection that decides whether a checkpoint may use the native path."""
+    import random
+
+    from tokenizers.normalizers import BertNormalizer
+
+    from claude_semantic_search_b200.st_compat import (MPNET_SPECIALS, NativeWordPieceTokenizer, SentenceTransformer,
+                                                       native_tokenizer_settings)
+    rnd = random.Random(1)
+    allcps = [cp for cp in range(0x110000) if not 0xD800 <= cp <= 0xDFFF]
+    norm = BertNormalizer(lowercase=True)
+    chars = set()
+    for cp in allcps[::7] + list(range(0x20, 0x3000)):
+        chars.update(norm.normalize_str(chr(cp)))
+    chars.discard(" ")
+    keep = [c for c in sorted(chars) if rnd.random() < 0.5]
+    vocab = ["<s>", "<pad>", "</s>", "<unk>"] + [f"[unused{i}]" for i in range(10)] + ["[UNK]"] + keep + \
+        ["##" + c for c in keep if rnd.random() < 0.7] + ["cafe", "##fe", "naive", "resume", "hello", "world", "##llo", "<mask>"]
+    vocab = list(dict.fromkeys(vocab))
+    vf = tmp_path / "vocab.txt"
+    vf.write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    pools = [range(0x20, 0x7F), range(0xA0, 0x250), range(0x300, 0x370), range(0x370, 0x530), range(0x590, 0x700),
+             range(0x900, 0xA00), range(0xE00, 0xE80), range(0x1100, 0x1200), range(0x2000, 0x2070),
+             range(0x3000, 0x3100), range(0x4E00, 0x4F00), range(0xAC00, 0xAD00), range(0xF900, 0xFA00),
+             range(0xFF00, 0xFFF0), range(0x1F600, 0x1F650), range(0x1D160, 0x1D175), range(0x302A, 0x3030),
+             range(0, 0x20), range(0x1B00, 0x1C00), range(0x20000, 0x20100)]
+    mixed = []
+    for _ in range(6000):
+        s = []
+        for _ in range(rnd.randint(0, 40)):
+            pool = pools[0] if rnd.random() < 0.4 else rnd.choice(pools)
+            s.append(chr(rnd.choice(pool)))
+            if rnd.random() < 0.15:
+                s.append(" ")
+            if rnd.random() < 0.03:
+                s.append(rnd.choice(MPNET_SPECIALS + ("<S>", "<mas", "[unk]")))
+        mixed.append("".join(s))
+    mixed += ["", " ", "Unbelievable café", "naïve résumé", "日本語 text", "ctrl\x0bchar", "zero\x00byte", "x" * 150,
+              "é" * 101, "é" * 100 + " ok", "İstanbul ΣΊΣΥΦΟΣ ß ǅ", "a〮ୖ\U0001d165b", "á〮\U0001d165b",
+              "한국어 텍스트", "😀 emoji 👍🏽 zwj 👨‍👩‍👧", "a<s>b</s>c", "x <mask> y<mask>z", "<<s>>", "[UNK][UNK] <pad>", "<unk>hello",
+              "hello<mask", "\ufeffbom\u200bzero\u00adwidth", "\u2028line\u2029para\u00a0nbsp\u3000wide"]
+    sweep = [" ".join("a" + chr(c) + "b " + chr(c) + chr(c) for c in allcps[i:i + 16]) for i in range(0, len(allcps), 16)]
+    for lower in (True, False):
+        ref = _reference_fast_tokenizer(vocab, lower, MPNET_SPECIALS)
+        nat = NativeWordPieceTokenizer(vf, do_lower_case=lower, n_threads=4)
+        assert nat.specials == {s: vocab.index(s) for s in MPNET_SPECIALS}
+        for texts, lens in ((sweep, (384,)), (mixed, (8, 64, 384))):
+            for ml in lens:
+                ref.enable_truncation(max_length=ml)
+                want = [e.ids for e in ref.encode_batch(texts)]
+                ids, cu = nat.encode_packed(texts, ml)
+                bad = [i for i, w in enumerate(want) if ids[cu[i]:cu[i + 1]].tolist() != w]
+                assert not bad, (lower, ml, len(bad), repr(texts[bad[0]]), ids[cu[bad[0]]:cu[bad[0] + 1]].tolist(), want[bad[0]])
+        nat.close()
+        # tokenizer.json inspection: the same pipeline is accepted, with its case mode and added tokens
+        mdir = tmp_path / f"ckpt_{int(lower)}"
+        mdir.mkdir()
+        ref.no_truncation()
+        ref.save(str(mdir / "tokenizer.json"))
+        st = native_tokenizer_settings(mdir / "tokenizer.json")
+        assert st is not None and st["lower"] is lower and st["specials"] == {s: vocab.index(s) for s in MPNET_SPECIALS}
+        (mdir / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+        tk = SentenceTransformer._load_tokenizer(mdir)
+        assert isinstance(tk, NativeWordPieceTokenizer)
+        assert tk.encode_batch(["Héllo <mask> wörld"], 16) == [ref.encode("Héllo <mask> wörld").ids]
+        tk.close()
+    # a different pipeline (no CJK padding) must NOT be taken over by the native tokenizer
+    import json
+    cfg = json.loads((tmp_path / "ckpt_1" / "tokenizer.json").read_text(encoding="utf-8"))
+    cfg["normalizer"]["handle_chinese_chars"] = False
+    other = tmp_path / "other"
+    other.mkdir()
+    (other / "tokenizer.json").write_text(json.dumps(cfg), encoding="utf-8")
+    (other / "vocab.txt").write_text("\n".join(vocab) + "\n", encoding="utf-8")
+    assert native_tokenizer_settings(other / "tokenizer.json") is None
+    assert SentenceTransformer._load_tokenizer(other) is None
 
 
 def test_standin_tokenizer_is_deterministic_and_bounded():
