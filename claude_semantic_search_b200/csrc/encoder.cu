@@ -12,6 +12,7 @@
 #include "encoder_kernels.cuh"
 #include "attention_tc.cuh"
 #include "gemm_tc.cuh"
+#include "query_kernels.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -48,7 +49,7 @@ struct css_encoder {
   std::vector<void*> owned;  // every device allocation, freed on destroy
   // workspace
   __nv_bfloat16 *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *h = nullptr;
-  float2* ln_stats = nullptr;   // [max_tokens][3][4] partial row statistics written by the EpiResidLN epilogues
+  float2* ln_stats = nullptr;   // [max_tokens][3][4] partial row statistics written by the EpiResidLN epilogues (query path: [64][96])
   float2 *mr1 = nullptr, *mr2 = nullptr;   // [max_tokens] (mean, rstd) of the attention / output LayerNorm inputs
   int32_t *ids_dev = nullptr, *cu_dev = nullptr;
   float* out_dev = nullptr;
@@ -147,8 +148,105 @@ int ensure_pinned(css_encoder* e, size_t bytes) {
 }
 
 // One forward pass over T packed tokens; everything on `st`.
+template <int MODE>
+int skinny_gemm(int T, int N, int K, const SkinnyParams& p, cudaStream_t st) {
+  cudaError_t ce;
+  if (K == kHidden) ce = T == 32 ? skinny_launch<2, 4, 6, MODE>(p, N, st) : skinny_launch<4, 4, 6, MODE>(p, N, st);
+  else ce = T == 32 ? skinny_launch<2, 8, 12, MODE>(p, N, st) : skinny_launch<4, 8, 12, MODE>(p, N, st);
+  CSS_CUDA(ce);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+// The interactive query path: T = 32 or 64 token rows, sequences of at most 64 tokens (query_kernels.cuh).
+// Same LayerNorm-folded pipeline as forward(), weight-streaming kernels instead of 128-row tiles; the row
+// statistics stay as per-CTA partials (two buffers: attention-output / layer-output LayerNorm) that the
+// consuming kernels reduce themselves, and every kernel is a programmatic dependent launch whose
+// weight loads overlap its predecessor's tail.
+int forward_query(css_encoder* e, const int32_t* cu_dev, int n_seq, int T, int normalize, float* out_dev,
+                  cudaStream_t st) {
+  const css_mpnet_config& c = e->cfg;
+  float2* parts1 = e->ln_stats;                                       // statistics of x1 (attention-output LayerNorm input)
+  float2* parts2 = e->ln_stats + (size_t)kQueryMaxRows * kQueryParts;  // statistics of x (layer-output LayerNorm input)
+  for (int l = 0; l < c.num_layers; ++l) {
+    const EncLayer& w = e->layers[l];
+    const EncLayer* prev = l > 0 ? &e->layers[l - 1] : nullptr;
+    {
+      SkinnyParams p{};
+      p.A = e->x;
+      p.out = e->qkv;
+      p.ldo = 3 * kHidden;
+      p.eps = c.layer_norm_eps;
+      if (l == 0) {
+        p.W = w.wqkv;
+        p.bias = w.bqkv;
+        CSS_CHECK(skinny_gemm<kSkBias>(T, 3 * kHidden, kHidden, p, st));
+      } else {
+        p.W = w.wqkv_f;
+        p.bias = w.dqkv;
+        p.colsum = w.cqkv;
+        p.stat_parts = parts2;
+        CSS_CHECK(skinny_gemm<kSkFold>(T, 3 * kHidden, kHidden, p, st));
+      }
+    }
+    CSS_CUDA(pdl_launch(query_attention_kernel, dim3(kHeads, (unsigned)n_seq, kQueryAttnRowGroups), dim3(kQueryAttnThreads), st,
+                        (const __nv_bfloat16*)e->qkv, cu_dev, (const float*)e->rel_table, e->rel_half, e->ctx));
+    CSS_LAUNCHED();
+    {
+      SkinnyParams p{};
+      p.A = e->ctx;
+      p.W = w.wo;
+      p.out = e->x1;
+      p.ldo = kHidden;
+      p.bias = w.bo;
+      p.eps = c.layer_norm_eps;
+      p.resid = e->x;
+      p.stat_parts = prev ? parts2 : nullptr;
+      p.rgamma = prev ? prev->ln2_w : nullptr;
+      p.rbeta = prev ? prev->ln2_b : nullptr;
+      p.parts = parts1;
+      CSS_CHECK(skinny_gemm<kSkResidLN>(T, kHidden, kHidden, p, st));
+    }
+    {
+      SkinnyParams p{};
+      p.A = e->x1;
+      p.W = w.w1_f;
+      p.out = e->h;
+      p.ldo = kFfn;
+      p.bias = w.d1;
+      p.colsum = w.c1;
+      p.eps = c.layer_norm_eps;
+      p.stat_parts = parts1;
+      CSS_CHECK(skinny_gemm<kSkFoldGelu>(T, kFfn, kHidden, p, st));
+    }
+    {
+      SkinnyParams p{};
+      p.A = e->h;
+      p.W = w.w2;
+      p.out = e->x;
+      p.ldo = kHidden;
+      p.bias = w.b2;
+      p.eps = c.layer_norm_eps;
+      p.resid = e->x1;
+      p.stat_parts = parts1;
+      p.rgamma = w.ln1_w;
+      p.rbeta = w.ln1_b;
+      p.parts = parts2;
+      CSS_CHECK(skinny_gemm<kSkResidLN>(T, kHidden, kFfn, p, st));
+    }
+  }
+  CSS_CUDA(pdl_launch(ln_stats_finalize_parts_kernel, dim3((unsigned)((T + 3) / 4)), dim3(128), st,
+                      (const float2*)parts2, T, c.layer_norm_eps, e->mr2));
+  CSS_LAUNCHED();
+  const EncLayer& last = e->layers[c.num_layers - 1];
+  pool_normalize_ln_kernel<<<(unsigned)n_seq, 256, 0, st>>>(e->x, e->mr2, last.ln2_w, last.ln2_b, cu_dev, normalize,
+                                                            out_dev);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
 int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n_seq, int T, int max_len,
-            int normalize, float* out_dev, cudaStream_t st) {
+            int normalize, float* out_dev, cudaStream_t st, bool query_path = false) {
   const css_mpnet_config& c = e->cfg;
   const int warps_per_block = 8;
   const unsigned row_blocks = (unsigned)((T + warps_per_block - 1) / warps_per_block);
@@ -171,6 +269,12 @@ int forward(css_encoder* e, const int32_t* ids_dev, const int32_t* cu_dev, int n
   // pre-LayerNorm value + row statistics, the consuming GEMMs fold the LayerNorm into their weights /
   // epilogue, the residual adds rebuild LN(.) in fp32.  0: ln_apply_kernel after each projection.
   static const bool ln_fold = [] { const char* v = getenv("CSS_LN_FOLD"); return v ? atoi(v) != 0 : true; }();
+  // CSS_QUERY_SKINNY=1 (default): the single-query graph path over a bucket of 32 or 64 token rows runs the
+  // weight-streaming kernels of query_kernels.cuh (batch passes never do: their result must not depend on
+  // how sequences happen to be grouped)
+  static const bool query_skinny = [] { const char* v = getenv("CSS_QUERY_SKINNY"); return v ? atoi(v) != 0 : true; }();
+  if (query_path && ln_fold && query_skinny && (T == 32 || T == 64) && max_len <= kQueryMaxRows)
+    return forward_query(e, cu_dev, n_seq, T, normalize, out_dev, st);
   if (ln_fold) {
     const unsigned fin_blocks = (unsigned)((T + 255) / 256);
     for (int l = 0; l < c.num_layers; ++l) {
@@ -284,7 +388,7 @@ int forward_query_graph(css_encoder* e, int bucket, int normalize, cudaStream_t 
   if (it == e->query_graphs.end()) {
     const int64_t l0 = g_launches.load(std::memory_order_relaxed);
     CSS_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
-    const int rc = forward(e, e->ids_dev, e->cu_dev, 1, bucket, bucket, normalize, e->out_dev, st);
+    const int rc = forward(e, e->ids_dev, e->cu_dev, 1, bucket, bucket, normalize, e->out_dev, st, true);
     cudaGraph_t graph = nullptr;
     const cudaError_t ce = cudaStreamEndCapture(st, &graph);
     if (rc != CSS_OK) {
@@ -501,7 +605,7 @@ int css_encoder_create(const css_mpnet_config* cfg, const css_mpnet_weights* w, 
   if ((rc = enc_alloc(e, &e->qkv, T * 3 * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->ctx, T * H)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->h, T * kFfn)) != CSS_OK) return fail(rc);
-  if ((rc = enc_alloc(e, &e->ln_stats, T * 3 * kGemmEpiColSplit)) != CSS_OK) return fail(rc);
+  if ((rc = enc_alloc(e, &e->ln_stats, std::max(T * 3 * kGemmEpiColSplit, (size_t)2 * kQueryMaxRows * kQueryParts))) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->mr1, T)) != CSS_OK) return fail(rc);
   if ((rc = enc_alloc(e, &e->mr2, T)) != CSS_OK) return fail(rc);
   cudaMemsetAsync(e->mr1, 0, T * sizeof(float2), e->stream);

@@ -1,0 +1,297 @@
+// query_kernels.cuh -- kernels of the interactive query path (one short query is
+// encoded per search, src/embeddings.py:216-222 called from the MCP server / CLI with a single text).
+//
+// A query is a bucket of 32 or 64 token rows.  The tcgen05 GEMMs of the indexing path put a
+// 128-row tile on 6 (N = 768) to 24 (N = 3072) CTAs, each walking K serially: 9-30 us per
+// projection, 0.89 ms per query, all of it latency.  At this size the forward pass is a weight
+// stream (170 MB of bf16 per query) and the right shape is the opposite one: every SM pulls a
+// slice of the weight matrix with all of its loads in flight at once.
+//
+//   skinny_gemm_kernel   out[M, N] = A[M, K] W[N, K]^T, M = 32 / 64.  CTA = 8 output columns,
+//       KSPLIT warps each own K / KSPLIT of the reduction: a warp issues ALL of its weight loads
+//       (16 B per lane, 8 rows x 64 B per instruction) before the first mma.sync, so the whole matrix
+//       is in flight across the grid; activations come from L2 / L1.  The k index inside a 32-wide
+//       block is permuted identically for both operands (lane q holds k = 8q .. 8q+7), which lets
+//       both fragments be plain 16-byte loads.  Partial sums meet in shared memory (fixed order);
+//       the epilogues are the ones of the tcgen05 path (bias / folded LayerNorm / GELU / residual +
+//       row statistics), one thread per row.
+//   query_attention_kernel   one CTA per (head, sequence), L <= 64: scores, softmax and P V in fp32
+//       from shared memory, a warp per query row.
+//   ln_stats_finalize_parts_kernel   (mean, rstd) per row from the N / 8 per-CTA partials.
+#pragma once
+#include "encoder_kernels.cuh"
+
+namespace css {
+namespace enc {
+
+enum : int { kSkBias = 0, kSkFold = 1, kSkFoldGelu = 2, kSkResidLN = 3 };
+
+struct SkinnyParams {
+  const __nv_bfloat16* A;   // [M, K], row stride K
+  const __nv_bfloat16* W;   // [N, K]
+  __nv_bfloat16* out;       // [M, ldo]
+  int ldo;
+  const float* bias;        // b, or d when folded
+  const float* colsum;      // folded: c [N]
+  const float2* stat_parts; // folded: partial statistics of the rows of A; kSkResidLN: of the rows of `resid`
+                            // when it is a pre-LayerNorm value (else nullptr).  [M][kQueryParts] (sum, sum of squares)
+  float eps;
+  const __nv_bfloat16* resid;   // kSkResidLN: [M, 768]
+  const float* rgamma;
+  const float* rbeta;
+  float2* parts;                // kSkResidLN: [M][N / 8] (sum, sum of squares) of the output row slice
+};
+
+// Programmatic dependent launch: the next kernel of the stream may start (and issue its weight loads)
+// while this one is still running; it must not touch anything a predecessor writes or reads before
+// pdl_wait() returns (all predecessors complete, their memory visible).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+constexpr int kQueryMaxRows = 64;
+constexpr int kQueryParts = kHidden / 8;   // partial statistics per row
+
+template <int MT, int KSPLIT, int KITERS, int MODE>
+static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const SkinnyParams p) {
+  constexpr int K = KSPLIT * KITERS * 32;
+  constexpr int M = MT * 16;
+  static_assert(M <= KSPLIT * 32, "one epilogue thread per row");
+  __shared__ __align__(16) float red[KSPLIT][M][8];
+  __shared__ float2 smr[M];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const int n0 = blockIdx.x * 8;
+  const int kbase = warp * (KITERS * 32) + q * 8;
+
+  // the warp's whole weight slice: KITERS independent 16-byte loads per lane, issued back to back
+  uint4 b[KITERS];
+  {
+    const uint4* wp = reinterpret_cast<const uint4*>(p.W + (size_t)(n0 + g) * K + kbase);
+#pragma unroll
+    for (int it = 0; it < KITERS; ++it)
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(b[it].x), "=r"(b[it].y), "=r"(b[it].z), "=r"(b[it].w)
+                   : "l"(wp + it * 4));
+  }
+  pdl_wait();   // the weights above are constants; everything below reads what the previous kernels wrote
+  if (MODE != kSkBias && p.stat_parts != nullptr) {
+    // (mean, rstd) of every row from its kQueryParts partials: TPR adjacent lanes per row, fixed order
+    constexpr int TPR = KSPLIT * 32 / M;
+    static_assert(TPR >= 1 && TPR <= 32 && (TPR & (TPR - 1)) == 0 && kQueryParts % TPR == 0, "row groups");
+    const int row = threadIdx.x / TPR, sub = threadIdx.x % TPR;
+    // all loads of a thread are independent and issued together (L2 latency once, not once per load)
+    float2 a[kQueryParts / TPR];
+#pragma unroll
+    for (int j = 0; j < kQueryParts / TPR; ++j) a[j] = p.stat_parts[(size_t)row * kQueryParts + j * TPR + sub];
+    float s = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kQueryParts / TPR; ++j) {
+      s += a[j].x;
+      sq += a[j].y;
+    }
+#pragma unroll
+    for (int o = TPR / 2; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float mean = s * (1.f / kHidden);
+    if (sub == 0) smr[row] = make_float2(mean, rsqrtf(fmaxf(sq * (1.f / kHidden) - mean * mean, 0.f) + p.eps));
+  }
+  float acc[MT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+#pragma unroll
+  for (int it = 0; it < KITERS; ++it) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const __nv_bfloat16* ap = p.A + (size_t)(mt * 16 + g) * K + kbase + it * 32;
+      const uint4 lo = *reinterpret_cast<const uint4*>(ap);
+      const uint4 hi = *reinterpret_cast<const uint4*>(ap + (size_t)8 * K);
+      const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
+      const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
+      mma_bf16_16816(acc[mt], a0, b[it].x, b[it].y);
+      mma_bf16_16816(acc[mt], a1, b[it].z, b[it].w);
+    }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    *reinterpret_cast<float2*>(&red[warp][mt * 16 + g][2 * q]) = make_float2(acc[mt][0], acc[mt][1]);
+    *reinterpret_cast<float2*>(&red[warp][mt * 16 + g + 8][2 * q]) = make_float2(acc[mt][2], acc[mt][3]);
+  }
+  __syncthreads();
+  // only now may the next kernel start prefetching its weights: one kernel ahead, never a cascade of
+  // waiting grids (measured: triggering at kernel entry made the whole path 1.3-2x slower)
+  pdl_launch_dependents();
+  const int m = threadIdx.x;
+  if (m >= M) return;
+  float v[8];
+  {
+    const float4 x = *reinterpret_cast<const float4*>(&red[0][m][0]), y = *reinterpret_cast<const float4*>(&red[0][m][4]);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+  }
+#pragma unroll
+  for (int w = 1; w < KSPLIT; ++w) {
+    const float4 x = *reinterpret_cast<const float4*>(&red[w][m][0]), y = *reinterpret_cast<const float4*>(&red[w][m][4]);
+    v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
+  }
+  float bias[8];
+  {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p.bias + n0)), y = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 1);
+    bias[0] = x.x; bias[1] = x.y; bias[2] = x.z; bias[3] = x.w; bias[4] = y.x; bias[5] = y.y; bias[6] = y.z; bias[7] = y.w;
+  }
+  float f[8];
+  if constexpr (MODE == kSkBias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = v[i] + bias[i];
+  } else if constexpr (MODE == kSkFold || MODE == kSkFoldGelu) {
+    // LN(a) W^T + b = rstd (a (W gamma)^T - mu c) + d   (EpiBiasBf16<., true>)
+    const float2 mr = smr[m];
+    const float rs = mr.y, nb = -mr.x * mr.y;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(p.colsum + n0)), y = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + 1);
+    const float c[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[i] = fmaf(rs, v[i], fmaf(nb, c[i], bias[i]));
+      if constexpr (MODE == kSkFoldGelu) f[i] = gelu_erf(f[i]);
+    }
+  } else {
+    // v + bias + residual, the residual rebuilt as LN(resid) when `resid` is a pre-LayerNorm value (EpiResidLN<false>)
+    const uint4 r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
+    float r[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y), bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
+    if (p.stat_parts != nullptr) {
+      const float2 mr = smr[m];
+      const float rs = mr.y, nb = -mr.x * mr.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] = fmaf(fmaf(r[i], rs, nb), __ldg(p.rgamma + n0 + i), __ldg(p.rbeta + n0 + i));
+    }
+    float s = 0.f, sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      f[i] = (v[i] + bias[i]) + r[i];
+      s += f[i];
+      sq = fmaf(f[i], f[i], sq);
+    }
+    p.parts[(size_t)m * gridDim.x + blockIdx.x] = make_float2(s, sq);
+  }
+  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + n0) =
+      make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// (mean, rstd) per row from the kQueryParts per-CTA partials of skinny_gemm_kernel<kSkResidLN>: a warp per row
+static __global__ void ln_stats_finalize_parts_kernel(const float2* __restrict__ parts, int T, float eps,
+                                                      float2* __restrict__ mr) {
+  pdl_wait();
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (t >= T) return;
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kQueryParts / 32; ++i) {
+    const float2 a = parts[(size_t)t * kQueryParts + i * 32 + lane];
+    s += a.x;
+    q += a.y;
+  }
+  s = warp_sum(s);
+  q = warp_sum(q);
+  const float mean = s * (1.f / kHidden);
+  if (lane == 0) mr[t] = make_float2(mean, rsqrtf(fmaxf(q * (1.f / kHidden) - mean * mean, 0.f) + eps));
+}
+
+// Attention of one (head, sequence) with L <= 64 keys: scores = q.k / 8 + rel_table[h][clamp(j - i)],
+// softmax and P V in fp32.  8 warps, a warp per query row; lane = key for the scores, lane = two
+// output dimensions for P V.
+constexpr int kQueryAttnThreads = 256;
+constexpr int kQueryAttnRowGroups = 4;   // grid.z: CTAs sharing one (head, sequence), 8 query rows per pass each
+static __global__ void __launch_bounds__(kQueryAttnThreads)
+query_attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ cu,
+                       const float* __restrict__ rel_table, int rel_half, __nv_bfloat16* __restrict__ ctx) {
+  constexpr int kLd = 3 * kHidden;
+  constexpr int kKs = 33;   // words per K row: 32 + 1 pad, conflict-free with lane = key
+  __shared__ uint32_t sQ[kQueryMaxRows][32], sK[kQueryMaxRows][kKs], sV[kQueryMaxRows][32];
+  __shared__ __align__(16) float sP[kQueryAttnThreads / 32][kQueryMaxRows];
+  const int h = blockIdx.x, s = blockIdx.y;
+  pdl_wait();
+  const int t0 = cu[s];
+  const int L = min(cu[s + 1] - t0, kQueryMaxRows);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kQueryMaxRows * 8; i += kQueryAttnThreads) {
+    const int r = i >> 3, c = i & 7;
+    uint4 qv = make_uint4(0, 0, 0, 0), kv = qv, vv = qv;
+    if (r < L) {
+      const __nv_bfloat16* gp = qkv + (size_t)(t0 + r) * kLd + h * kHeadDim + c * 8;
+      qv = *reinterpret_cast<const uint4*>(gp);
+      kv = *reinterpret_cast<const uint4*>(gp + kHidden);
+      vv = *reinterpret_cast<const uint4*>(gp + 2 * kHidden);
+    }
+    *reinterpret_cast<uint4*>(&sQ[r][c * 4]) = qv;
+    *reinterpret_cast<uint4*>(&sV[r][c * 4]) = vv;
+    sK[r][c * 4 + 0] = kv.x; sK[r][c * 4 + 1] = kv.y; sK[r][c * 4 + 2] = kv.z; sK[r][c * 4 + 3] = kv.w;
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+  const float* rt = rel_table + (size_t)h * (2 * rel_half + 1) + rel_half;
+  constexpr int kWarps = kQueryAttnThreads / 32;
+  for (int i = blockIdx.z * kWarps + warp; i < L; i += kWarps * gridDim.z) {
+    float sa0 = 0.f, sa1 = 0.f, sb0 = 0.f, sb1 = 0.f;   // split accumulators: the chains are latency-bound
+#pragma unroll
+    for (int d = 0; d < 32; ++d) {
+      const uint32_t qw = sQ[i][d], ka = sK[lane][d], kb = sK[lane + 32][d];
+      const float q0 = bf16_lo(qw), q1 = bf16_hi(qw);
+      sa0 = fmaf(q0, bf16_lo(ka), sa0);
+      sa1 = fmaf(q1, bf16_hi(ka), sa1);
+      sb0 = fmaf(q0, bf16_lo(kb), sb0);
+      sb1 = fmaf(q1, bf16_hi(kb), sb1);
+    }
+    float sa = sa0 + sa1, sb = sb0 + sb1;
+    const int ja = lane, jb = lane + 32;
+    sa = ja < L ? fmaf(sa, 0.125f, __ldg(rt + max(-rel_half, min(rel_half, ja - i)))) : -INFINITY;
+    sb = jb < L ? fmaf(sb, 0.125f, __ldg(rt + max(-rel_half, min(rel_half, jb - i)))) : -INFINITY;
+    float mx = fmaxf(sa, sb);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float pa = __expf(sa - mx), pb = __expf(sb - mx);   // exp(-inf) = 0 for the keys that do not exist
+    const float inv = 1.f / warp_sum(pa + pb);
+    sP[warp][ja] = pa * inv;
+    sP[warp][jb] = pb * inv;
+    __syncwarp();
+    float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+    const int L4 = (L + 3) & ~3;   // rows L .. L4-1 of V are zero and their weights are 0
+    for (int j = 0; j < L4; j += 4) {
+      const float4 pj = *reinterpret_cast<const float4*>(&sP[warp][j]);
+      const float pv[4] = {pj.x, pj.y, pj.z, pj.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t vw = sV[j + u][lane];
+        o0[u] = fmaf(pv[u], bf16_lo(vw), o0[u]);
+        o1[u] = fmaf(pv[u], bf16_hi(vw), o1[u]);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(ctx + (size_t)(t0 + i) * kHidden + h * kHeadDim + 2 * lane) =
+        pack_bf16((o0[0] + o0[1]) + (o0[2] + o0[3]), (o1[0] + o1[1]) + (o1[2] + o1[3]));
+    __syncwarp();
+  }
+}
+
+// launch with the programmatic-stream-serialization attribute (the kernel calls pdl_wait() itself)
+template <typename... KArgs, typename... Args>
+inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  // CSS_QUERY_PDL=0: plain stream order (griddepcontrol.* are no-ops then)
+  static const bool pdl = [] { const char* v = getenv("CSS_QUERY_PDL"); return v ? atoi(v) != 0 : true; }();
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+template <int MT, int KSPLIT, int KITERS, int MODE>
+inline cudaError_t skinny_launch(const SkinnyParams& p, int N, cudaStream_t st) {
+  return pdl_launch(skinny_gemm_kernel<MT, KSPLIT, KITERS, MODE>, dim3((unsigned)(N / 8)), dim3(KSPLIT * 32), st, p);
+}
+
+}  // namespace enc
+}  // namespace css

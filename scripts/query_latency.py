@@ -22,7 +22,7 @@ def main():
     enc = MPNetEncoder(random_state_dict(0), device=0, max_tokens=4096)
     rng = np.random.default_rng(3)
     out = {}
-    for L in (8, 16, 32, 128, 384):
+    for L in (8, 16, 32, 48, 64, 128, 384):
         qs = [[0] + rng.integers(4, 30000, size=L - 2).tolist() + [2] for _ in range(200)]
         for q in qs[:20]:
             enc.encode_ids([q])
@@ -32,6 +32,9 @@ def main():
             enc.encode_ids([q])
             lat.append(time.perf_counter() - t0)
         out[f"encode_L{L}"] = {"p50_ms": pct(lat, 50), "p99_ms": pct(lat, 99)}
+    if "--encode-only" in sys.argv:
+        print(json.dumps(out))
+        return
     dev = torch.device("cuda", 0)
     idx = _native.Index(768, device=0)
     idx.reserve(1_000_000)

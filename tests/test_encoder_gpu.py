@@ -173,7 +173,10 @@ def test_encoder_ragged_batch_vs_oracle(native):
 
 def test_single_query_graph_path_matches_batch_path(native):
     """a single short sequence is served by a captured CUDA graph over a token
-    bucket (32 / 64 / 128 / 256 / 384 rows); it must return exactly what the batch path returns."""
+    bucket (32 / 64 / 128 / 256 / 384 rows).  Buckets of 128+ rows run the batch kernels and must return
+    exactly what the batch path returns; the 32 / 64-row buckets run the weight-streaming query kernels
+    (query_kernels.cuh: different summation order) and are held to the oracle bar instead, and to
+    CSS_QUERY_SKINNY=0-style agreement with the batch path within bf16 noise."""
     from claude_semantic_search_b200.encoder import MPNetEncoder
     from oracle import encoder_oracle as eo
     lengths = [1, 5, 31, 32, 33, 64, 100, 128, 129, 256, 300, 384]
@@ -183,12 +186,23 @@ def test_single_query_graph_path_matches_batch_path(native):
     batch = enc.encode_ids(seqs)                      # n_seq > 1: plain launches
     want = eo.st_encode_ids(model, seqs, batch_size=16)
     assert eo.cosine_rows(want, batch).min() >= COS_MIN
+    first = {}
     for rep in range(2):                              # first call captures, second replays
         for i, q in enumerate(seqs):
             one = enc.encode_ids([q])
-            np.testing.assert_array_equal(one[0], batch[i], err_msg=f"L={lengths[i]} rep={rep}")
+            if lengths[i] > 64:
+                np.testing.assert_array_equal(one[0], batch[i], err_msg=f"L={lengths[i]} rep={rep}")
+            else:
+                assert eo.cosine_rows(want[i:i + 1], one).min() >= COS_MIN, f"L={lengths[i]} rep={rep}"
+                np.testing.assert_allclose(one[0], batch[i], atol=2e-3, err_msg=f"L={lengths[i]} rep={rep}")
+                if rep == 1:
+                    np.testing.assert_array_equal(one[0], first[i])   # replay == capture run
+            if rep == 0:
+                first[i] = one[0].copy()
     raw = enc.encode_ids([seqs[4]], normalize=False)  # separate graph per normalize flag
-    np.testing.assert_allclose(raw[0] / np.linalg.norm(raw[0]), batch[4], atol=2e-6)
+    np.testing.assert_allclose(raw[0] / np.linalg.norm(raw[0]), first[4], atol=2e-6)
+    raw = enc.encode_ids([seqs[7]], normalize=False)
+    np.testing.assert_allclose(raw[0] / np.linalg.norm(raw[0]), batch[7], atol=2e-6)
     enc.close()
 
 
