@@ -72,7 +72,30 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
                    : "=r"(b[it].x), "=r"(b[it].y), "=r"(b[it].z), "=r"(b[it].w)
                    : "l"(wp + it * 4));
   }
+  // the epilogue thread of row m: its per-column constants are requested now, with the weights
+  const int m = threadIdx.x;
+  float bias[8], cs[8], be[8];   // cs: column sums c (folded) or the residual LayerNorm's gamma; be: its beta
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bias[i] = cs[i] = be[i] = 0.f;
+  if (m < M) {
+    auto ld8 = [&](const float* src, float (&dst)[8]) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(src + n0)), y = __ldg(reinterpret_cast<const float4*>(src + n0) + 1);
+      dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; dst[4] = y.x; dst[5] = y.y; dst[6] = y.z; dst[7] = y.w;
+    };
+    ld8(p.bias, bias);
+    if constexpr (MODE == kSkFold || MODE == kSkFoldGelu) ld8(p.colsum, cs);
+    if constexpr (MODE == kSkResidLN) {
+      if (p.stat_parts != nullptr) {
+        ld8(p.rgamma, cs);
+        ld8(p.rbeta, be);
+      }
+    }
+  }
   pdl_wait();   // the weights above are constants; everything below reads what the previous kernels wrote
+  uint4 r4 = make_uint4(0, 0, 0, 0);
+  if constexpr (MODE == kSkResidLN) {
+    if (m < M) r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
+  }
   if (MODE != kSkBias && p.stat_parts != nullptr) {
     // (mean, rstd) of every row from its kQueryParts partials: TPR adjacent lanes per row, fixed order
     constexpr int TPR = KSPLIT * 32 / M;
@@ -121,7 +144,6 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
   // only now may the next kernel start prefetching its weights: one kernel ahead, never a cascade of
   // waiting grids (measured: triggering at kernel entry made the whole path 1.3-2x slower)
   pdl_launch_dependents();
-  const int m = threadIdx.x;
   if (m >= M) return;
   float v[8];
   {
@@ -133,11 +155,6 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
     const float4 x = *reinterpret_cast<const float4*>(&red[w][m][0]), y = *reinterpret_cast<const float4*>(&red[w][m][4]);
     v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
   }
-  float bias[8];
-  {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p.bias + n0)), y = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 1);
-    bias[0] = x.x; bias[1] = x.y; bias[2] = x.z; bias[3] = x.w; bias[4] = y.x; bias[5] = y.y; bias[6] = y.z; bias[7] = y.w;
-  }
   float f[8];
   if constexpr (MODE == kSkBias) {
 #pragma unroll
@@ -146,22 +163,19 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
     // LN(a) W^T + b = rstd (a (W gamma)^T - mu c) + d   (EpiBiasBf16<., true>)
     const float2 mr = smr[m];
     const float rs = mr.y, nb = -mr.x * mr.y;
-    const float4 x = __ldg(reinterpret_cast<const float4*>(p.colsum + n0)), y = __ldg(reinterpret_cast<const float4*>(p.colsum + n0) + 1);
-    const float c[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      f[i] = fmaf(rs, v[i], fmaf(nb, c[i], bias[i]));
+      f[i] = fmaf(rs, v[i], fmaf(nb, cs[i], bias[i]));
       if constexpr (MODE == kSkFoldGelu) f[i] = gelu_erf(f[i]);
     }
   } else {
     // v + bias + residual, the residual rebuilt as LN(resid) when `resid` is a pre-LayerNorm value (EpiResidLN<false>)
-    const uint4 r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
     float r[8] = {bf16_lo(r4.x), bf16_hi(r4.x), bf16_lo(r4.y), bf16_hi(r4.y), bf16_lo(r4.z), bf16_hi(r4.z), bf16_lo(r4.w), bf16_hi(r4.w)};
     if (p.stat_parts != nullptr) {
       const float2 mr = smr[m];
       const float rs = mr.y, nb = -mr.x * mr.y;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r[i] = fmaf(fmaf(r[i], rs, nb), __ldg(p.rgamma + n0 + i), __ldg(p.rbeta + n0 + i));
+      for (int i = 0; i < 8; ++i) r[i] = fmaf(fmaf(r[i], rs, nb), cs[i], be[i]);
     }
     float s = 0.f, sq = 0.f;
 #pragma unroll
