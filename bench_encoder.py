@@ -65,9 +65,18 @@ def bench_text_to_embedding(enc, n_seq: int, reps: int = 3):
             t2 = time.perf_counter()
             t_tok += t1 - t0
             t_all += t2 - t0
+        # what SentenceTransformer.encode does for a whole indexing batch: tokeniser one slab ahead of the GPU
+        from claude_semantic_search_b200.st_compat import encode_texts_pipelined
+        many = texts * max(1, 4096 // n_seq)
+        encode_texts_pipelined(tok, enc, many[:2048], SEQ_LEN, True)
+        t0 = time.perf_counter()
+        emb_p = encode_texts_pipelined(tok, enc, many, SEQ_LEN, True)
+        t_pipe = time.perf_counter() - t0
         tok.close()
     assert emb.shape == (n_seq, 768) and int(cu[-1]) == n_seq * SEQ_LEN
+    assert np.array_equal(emb_p[:n_seq], emb)
     return {"chunks_per_s": n_seq * reps / t_all, "tokenizer_chunks_per_s": n_seq * reps / t_tok,
+            "pipelined_chunks_per_s": len(many) / t_pipe, "pipelined_chunks": len(many),
             "tokenizer_threads": "hardware_concurrency, at most 16", "chars_per_chunk": int(np.mean([len(t) for t in texts])),
             "api": "css_tokenizer_encode_batch + css_encoder_encode (host text -> host embeddings, tokenise and encode not overlapped)"}
 

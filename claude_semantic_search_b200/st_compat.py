@@ -270,11 +270,39 @@ def _find_model_dir(name: str, cache_folder: Optional[str]) -> Optional[Path]:
 
 
 # ---------------------------------------------------------------------- SentenceTransformer
+def encode_texts_pipelined(tokenizer, encoder, texts: Sequence[str], max_len: int, normalize: bool,
+                           slab: int = 1024) -> np.ndarray:
+    """Text in, embeddings out with the host tokenizer one slab ahead of the GPU: a worker thread
+    tokenises texts[i+1] (css_tokenizer_encode_batch, GIL released) while the caller's thread runs
+    css_encoder_encode on texts[i].  The batch kernels' results do not depend on how sequences are
+    grouped into passes, so the output is bit-identical to the one-shot call; a trailing slab of a
+    single text is merged into its predecessor (one sequence alone would take the query-graph path)."""
+    n = len(texts)
+    if n <= slab + slab // 2:
+        ids, cu = tokenizer.encode_packed(texts, max_len)
+        return encoder.encode_packed(ids, cu, normalize=normalize)
+    from concurrent.futures import ThreadPoolExecutor
+    starts = list(range(0, n, slab))
+    if n - starts[-1] < max(2, slab // 2):
+        starts.pop()
+    bounds = list(zip(starts, starts[1:] + [n]))
+    out = np.empty((n, encoder.dim), np.float32)
+    with ThreadPoolExecutor(max_workers=1) as pool:
+        fut = pool.submit(tokenizer.encode_packed, texts[bounds[0][0]:bounds[0][1]], max_len)
+        for i, (b0, b1) in enumerate(bounds):
+            ids, cu = fut.result()
+            if i + 1 < len(bounds):
+                fut = pool.submit(tokenizer.encode_packed, texts[bounds[i + 1][0]:bounds[i + 1][1]], max_len)
+            out[b0:b1] = encoder.encode_packed(ids, cu, normalize=normalize)
+    return out
+
+
 class SentenceTransformer:
     def __init__(self, model_name_or_path: str = "all-mpnet-base-v2", cache_folder: Optional[str] = None,
                  device: Optional[str] = None, **_unused):
         self.model_name = model_name_or_path
         self.max_seq_length = 384
+        self.tokenize_slab = 1024   # texts per tokeniser slab when tokenising overlaps encoding
         self._device_index = 0
         synthetic = model_name_or_path == "synthetic-mpnet" or os.environ.get("CSS_B200_SYNTHETIC_MODEL") == "1"
         model_dir = None if model_name_or_path == "synthetic-mpnet" else _find_model_dir(model_name_or_path, cache_folder)
@@ -348,8 +376,8 @@ class SentenceTransformer:
         # passes of up to max_tokens tokens, results do not depend on it
         if hasattr(self.tokenizer, "encode_packed"):   # native tokenizer: straight to packed ids, no Python lists
             max_len = min(int(self.max_seq_length), self._encoder.max_seq_len)
-            ids, cu = self.tokenizer.encode_packed(texts, max_len)
-            emb = self._encoder.encode_packed(ids, cu, normalize=normalize_embeddings)
+            emb = encode_texts_pipelined(self.tokenizer, self._encoder, texts, max_len, normalize_embeddings,
+                                         self.tokenize_slab)
         else:
             emb = self._encoder.encode_ids(self.tokenize_ids(texts), normalize=normalize_embeddings)
         return emb[0] if single else emb

@@ -177,4 +177,9 @@ def test_local_checkpoint_text_to_embedding_vs_hf(tmp_path):
     assert cos.min() >= 0.9999, cos.min()
     one = st.encode(texts[0], normalize_embeddings=True)
     assert one.shape == (768,) and eo.cosine_rows(want[:1], one[None])[0] >= 0.9999
+    # tokeniser one slab ahead of the GPU (worker thread): bit-identical to the one-shot call, whatever the
+    # slab size, including a single-text tail (merged into the previous slab)
+    for slab in (4, 6, 14):
+        st.tokenize_slab = slab
+        np.testing.assert_array_equal(st.encode(texts, normalize_embeddings=True), got, err_msg=f"slab={slab}")
     st.close()
