@@ -233,7 +233,11 @@ class HybridStorage:
             raise RuntimeError("FAISS index not initialized")
         if not self.db:
             raise RuntimeError("Database not initialized")
-        x = np.asarray([c.embedding for c in todo], dtype=np.float32)
+        embs = [c.embedding for c in todo]
+        if all(isinstance(e, np.ndarray) and e.dtype == np.float32 and e.ndim == 1 for e in embs):
+            x = np.stack(embs)   # ndarray rows (EmbeddingConfig.embedding_as_ndarray): one 3 KB memcpy per chunk
+        else:
+            x = np.asarray(embs, dtype=np.float32)
         # normalisation x / (||x|| + 1e-8) happens on the device (S1)
         first = self.faiss_index._native.add(x, normalize=self.config.normalize_embeddings)
 

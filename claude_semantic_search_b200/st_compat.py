@@ -316,7 +316,9 @@ class SentenceTransformer:
             self.synthetic = False
         elif synthetic:
             self._encoder = MPNetEncoder(random_state_dict(0), device=self._device_index)
-            self.tokenizer = StandInTokenizer(DEFAULT_CONFIG["vocab_size"])
+            # benchmarks of the text path: random-init weights with a real WordPiece vocabulary file
+            vocab = os.environ.get("CSS_B200_SYNTHETIC_VOCAB")
+            self.tokenizer = NativeWordPieceTokenizer(vocab) if vocab else StandInTokenizer(DEFAULT_CONFIG["vocab_size"])
             self.synthetic = True
         else:
             raise FileNotFoundError(

@@ -80,6 +80,20 @@ def test_config1_pipeline_vs_oracle(tmp_path):
         wantf = so.prefilter_search(x, rows, q, top_k=10, filters=flt)
         np.testing.assert_allclose([g.similarity for g in gotf], [s for _, s in wantf], atol=1e-4)
         assert all("beta" in g.metadata["project_name"].lower() and g.metadata["has_code"] for g in gotf)
+    # ndarray-view embeddings (EmbeddingConfig.embedding_as_ndarray): same vectors, same search
+    gen.config.embedding_as_ndarray = True
+    chunks_b = _make_chunks(n)
+    emb_b = gen.generate_embeddings(chunks_b)
+    np.testing.assert_array_equal(emb_b, emb)
+    assert all(isinstance(c.embedding, np.ndarray) and c.embedding.dtype == np.float32 and c.embedding.base is not None
+               for c in chunks_b)
+    st_b = HybridStorage(StorageConfig(data_dir=str(tmp_path / "views"), use_gpu=True))
+    st_b.initialize()
+    st_b.add_chunks(chunks_b)
+    q = gen.generate_single_embedding(chunks[7].text[:80])
+    assert [(g.chunk_id, g.similarity) for g in st_b.search(q, SearchConfig(top_k=10))] == \
+        [(g.chunk_id, g.similarity) for g in st.search(q, SearchConfig(top_k=10))]
+    st_b.close()
     st.close()
     # persistence: a new instance sees the same index (reference tests/test_storage.py:541-558)
     st2 = HybridStorage(StorageConfig(data_dir=str(tmp_path), use_gpu=True))
