@@ -96,20 +96,20 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
   if constexpr (MODE == kSkResidLN) {
     if (m < M) r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
   }
-  if (MODE != kSkBias && p.stat_parts != nullptr) {
-    // (mean, rstd) of every row from its kQueryParts partials: TPR adjacent lanes per row, fixed order
-    constexpr int TPR = KSPLIT * 32 / M;
-    static_assert(TPR >= 1 && TPR <= 32 && (TPR & (TPR - 1)) == 0 && kQueryParts % TPR == 0, "row groups");
-    const int row = threadIdx.x / TPR, sub = threadIdx.x % TPR;
-    // all loads of a thread are independent and issued together (L2 latency once, not once per load)
-    float2 a[kQueryParts / TPR];
-#pragma unroll
-    for (int j = 0; j < kQueryParts / TPR; ++j) a[j] = p.stat_parts[(size_t)row * kQueryParts + j * TPR + sub];
+  // partial row statistics: TPR adjacent lanes per row, all loads of a thread independent.  Where they are
+  // reduced was measured on one box (p50 per query): 64-row bucket, after the main loop (loads overlap
+  // the activation loads) 0.526 against 0.570 ms; 32-row bucket, before it 0.311 against 0.324-0.353 ms
+  constexpr int TPR = KSPLIT * 32 / M;
+  constexpr bool kLateStats = MT >= 4;
+  static_assert(TPR >= 1 && TPR <= 32 && (TPR & (TPR - 1)) == 0 && kQueryParts % TPR == 0, "row groups");
+  const bool has_stats = MODE != kSkBias && p.stat_parts != nullptr;
+  float2 sp[kQueryParts / TPR];
+  auto reduce_stats = [&]() {
     float s = 0.f, sq = 0.f;
 #pragma unroll
     for (int j = 0; j < kQueryParts / TPR; ++j) {
-      s += a[j].x;
-      sq += a[j].y;
+      s += sp[j].x;
+      sq += sp[j].y;
     }
 #pragma unroll
     for (int o = TPR / 2; o > 0; o >>= 1) {
@@ -117,11 +117,20 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
       sq += __shfl_xor_sync(0xffffffffu, sq, o);
     }
     const float mean = s * (1.f / kHidden);
-    if (sub == 0) smr[row] = make_float2(mean, rsqrtf(fmaxf(sq * (1.f / kHidden) - mean * mean, 0.f) + p.eps));
-  }
-  float acc[MT][4];
+    if (threadIdx.x % TPR == 0)
+      smr[threadIdx.x / TPR] = make_float2(mean, rsqrtf(fmaxf(sq * (1.f / kHidden) - mean * mean, 0.f) + p.eps));
+  };
+  if (has_stats) {
+    const float2* src = p.stat_parts + (size_t)(threadIdx.x / TPR) * kQueryParts + threadIdx.x % TPR;
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+    for (int j = 0; j < kQueryParts / TPR; ++j) sp[j] = src[j * TPR];
+    if constexpr (!kLateStats) reduce_stats();
+  }
+  float acc[MT][4], acc2[MT][4];   // 64-row bucket: two accumulator sets, half the dependent mma chain (0.526 against 0.537 ms)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[mt][i] = acc2[mt][i] = 0.f;
 #pragma unroll
   for (int it = 0; it < KITERS; ++it) {
 #pragma unroll
@@ -132,8 +141,15 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
       const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
       const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
       mma_bf16_16816(acc[mt], a0, b[it].x, b[it].y);
-      mma_bf16_16816(acc[mt], a1, b[it].z, b[it].w);
+      mma_bf16_16816(kLateStats ? acc2[mt] : acc[mt], a1, b[it].z, b[it].w);
     }
+  }
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[mt][i] += acc2[mt][i];
+  if constexpr (kLateStats) {
+    if (has_stats) reduce_stats();
   }
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
