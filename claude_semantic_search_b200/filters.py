@@ -203,11 +203,51 @@ class ColumnCodec:
         if self.kind == "ordered" and len(values) >= 2048:
             self._bulk_ordered(list(values), start)
             return
+        if len(values) >= 64 and self._bulk_plain(values, start):
+            return
         for j, v in enumerate(values):
             # encode may rebalance (rewrites self.codes[:self.n]); keep n current
             c = self.encode(v, start + j)
             self.codes[start + j] = c
             self.n = start + j + 1
+
+    def _bulk_plain(self, values: Sequence[Any], start: int) -> bool:
+        """Batch append for the common shapes of an indexing batch (add_chunks hands over thousands of rows):
+        `int` columns whose values are all Python / numpy bools or in-range integers, `dict` columns whose
+        values are all hashable.  Same codes as the per-value path; False = not applicable, nothing changed."""
+        n = len(values)
+        if self.kind == "int":
+            try:
+                arr = np.asarray(values)
+            except (ValueError, TypeError):
+                return False
+            if arr.ndim != 1 or arr.dtype.kind not in "biu":
+                return False
+            if arr.dtype.kind != "b" and arr.size and (arr.min() < _INT_MIN or arr.max() > _INT_MAX):
+                return False
+            self.codes[start:start + n] = arr.astype(np.int32)
+            self.n = start + n
+            return True
+        if self.kind == "dict":
+            v2i, vals = self.value_to_id, self.values
+            out = np.empty(n, dtype=np.int32)
+            try:
+                for j, v in enumerate(values):
+                    if v is None:
+                        out[j] = NULL
+                        continue
+                    i = v2i.get(v)
+                    if i is None:
+                        i = len(vals)
+                        v2i[v] = i
+                        vals.append(v)
+                    out[j] = i
+            except TypeError:   # an unhashable value: the per-value path records it as exotic (ids assigned so far stand)
+                return False
+            self.codes[start:start + n] = out
+            self.n = start + n
+            return True
+        return False
 
     def set_row(self, row: int, value) -> None:
         self.exotic.pop(row, None)

@@ -119,6 +119,33 @@ def test_bulk_and_incremental_ordered_agree():
     np.testing.assert_array_equal(eval_clauses_host(a, a.compile(f)), so.filter_mask(rows, f))
 
 
+def test_batch_append_of_plain_columns_equals_per_value_path():
+    """ColumnCodec._bulk_plain (int / dict columns, batches of >= 64 rows) assigns exactly the codes of the
+    per-value path, falls back when a value does not fit (None in an int column, unhashable, out of range)."""
+    rows = make_rows(3000, seed=4)
+    rows[17]["message_count"] = None          # int column with a null: per-value path for that batch
+    rows[400]["project_name"] = ["a", "list"]  # unhashable in a dict column: exotic row
+    rows[900]["char_count"] = 2 ** 40          # out of int32 range: exotic row
+    rows[1200]["has_code"] = np.bool_(True)
+    a, b = ColumnStore(), ColumnStore()
+    for s in range(0, 3000, 300):
+        a.append_rows(rows[s:s + 300])                    # batch path where applicable
+    for s in range(0, 3000, 50):
+        b.append_rows(rows[s:s + 50])                     # below the batch threshold: per value
+    for ca, cb in zip(a.codecs, b.codecs):
+        if ca.kind == "ordered":
+            continue                                      # order-preserving codes depend on insertion history
+        np.testing.assert_array_equal(ca.codes[:ca.n], cb.codes[:cb.n], err_msg=ca.name)
+        assert ca.values == cb.values and ca.exotic == cb.exotic, ca.name
+    for f in ({"has_code": True}, {"project_name": "alpha"}, {"message_count": rows[0]["message_count"]}, {"char_count": {"lt": 500}},
+              {"has_code": True, "timestamp": {"gte": "2023-06-01"}}):
+        want = so.filter_mask(rows, f)
+        for st in (a, b):
+            c = st.compile(f)
+            got = eval_clauses_host(st, c)
+            np.testing.assert_array_equal(got, want, err_msg=str(f))
+
+
 def test_range_on_string_column_with_wrong_bound_type_raises_like_reference():
     store = ColumnStore()
     store.append_rows([{"timestamp": "2024-01-01"}])
