@@ -151,6 +151,18 @@ int ensure_pinned(css_encoder* e, size_t bytes) {
 template <int MODE>
 int skinny_gemm(int T, int N, int K, const SkinnyParams& p, cudaStream_t st) {
   cudaError_t ce;
+  // 64-row bucket: the wide (N >= 2304) projections run two 8-column groups per CTA on the same activation
+  // fragments (same box, p50: 0.534 -> 0.471 ms; the 32-row bucket loses 4 % with it and keeps one group).
+  // CSS_QUERY_NT=1 / 2 forces one / two groups for both buckets.
+  static const int nt_env = [] { const char* v = getenv("CSS_QUERY_NT"); return v ? atoi(v) : 0; }();
+  if constexpr (MODE != kSkResidLN) {
+    const bool two = nt_env ? nt_env == 2 : T == 64;
+    if (K == kHidden && N >= 3 * kHidden && two) {
+      CSS_CUDA(T == 32 ? (skinny_launch<2, 4, 6, MODE, 2>(p, N, st)) : (skinny_launch<4, 4, 6, MODE, 2>(p, N, st)));
+      CSS_LAUNCHED();
+      return CSS_OK;
+    }
+  }
   if (K == kHidden) ce = T == 32 ? skinny_launch<2, 4, 6, MODE>(p, N, st) : skinny_launch<4, 4, 6, MODE>(p, N, st);
   else ce = T == 32 ? skinny_launch<2, 8, 12, MODE>(p, N, st) : skinny_launch<4, 8, 12, MODE>(p, N, st);
   CSS_CUDA(ce);

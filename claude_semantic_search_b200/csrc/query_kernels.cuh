@@ -51,33 +51,38 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 constexpr int kQueryMaxRows = 64;
 constexpr int kQueryParts = kHidden / 8;   // partial statistics per row
 
-template <int MT, int KSPLIT, int KITERS, int MODE>
+// NT: 8-column groups per CTA (each warp runs NT n8 tiles on the same activation fragments: the activation
+// re-read, which is what the SMs mostly ingest here, drops by NT; the wide projections use 2).
+template <int MT, int KSPLIT, int KITERS, int MODE, int NT = 1>
 static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const SkinnyParams p) {
   constexpr int K = KSPLIT * KITERS * 32;
   constexpr int M = MT * 16;
-  static_assert(M <= KSPLIT * 32, "one epilogue thread per row");
-  __shared__ __align__(16) float red[KSPLIT][M][8];
+  static_assert(M * NT <= KSPLIT * 32, "one epilogue thread per row and column group");
+  static_assert(MODE != kSkResidLN || NT == 1, "the statistics partials are per 8-column CTA");
+  __shared__ __align__(16) float red[KSPLIT][M][8 * NT];
   __shared__ float2 smr[M];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-  const int n0 = blockIdx.x * 8;
   const int kbase = warp * (KITERS * 32) + q * 8;
 
-  // the warp's whole weight slice: KITERS independent 16-byte loads per lane, issued back to back
-  uint4 b[KITERS];
-  {
-    const uint4* wp = reinterpret_cast<const uint4*>(p.W + (size_t)(n0 + g) * K + kbase);
+  // the warp's whole weight slice: NT * KITERS independent 16-byte loads per lane, issued back to back
+  uint4 b[NT][KITERS];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const uint4* wp = reinterpret_cast<const uint4*>(p.W + (size_t)(blockIdx.x * (8 * NT) + nt * 8 + g) * K + kbase);
 #pragma unroll
     for (int it = 0; it < KITERS; ++it)
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
-                   : "=r"(b[it].x), "=r"(b[it].y), "=r"(b[it].z), "=r"(b[it].w)
+                   : "=r"(b[nt][it].x), "=r"(b[nt][it].y), "=r"(b[nt][it].z), "=r"(b[nt][it].w)
                    : "l"(wp + it * 4));
   }
-  // the epilogue thread of row m: its per-column constants are requested now, with the weights
-  const int m = threadIdx.x;
+  // the epilogue thread of (row m, column group): its per-column constants are requested now, with the weights
+  const int m = threadIdx.x % M, cg = threadIdx.x / M;
+  const bool epi = threadIdx.x < M * NT;
+  const int n0 = blockIdx.x * (8 * NT) + (epi ? cg : 0) * 8;
   float bias[8], cs[8], be[8];   // cs: column sums c (folded) or the residual LayerNorm's gamma; be: its beta
 #pragma unroll
   for (int i = 0; i < 8; ++i) bias[i] = cs[i] = be[i] = 0.f;
-  if (m < M) {
+  if (epi) {
     auto ld8 = [&](const float* src, float (&dst)[8]) {
       const float4 x = __ldg(reinterpret_cast<const float4*>(src + n0)), y = __ldg(reinterpret_cast<const float4*>(src + n0) + 1);
       dst[0] = x.x; dst[1] = x.y; dst[2] = x.z; dst[3] = x.w; dst[4] = y.x; dst[5] = y.y; dst[6] = y.z; dst[7] = y.w;
@@ -94,7 +99,7 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
   pdl_wait();   // the weights above are constants; everything below reads what the previous kernels wrote
   uint4 r4 = make_uint4(0, 0, 0, 0);
   if constexpr (MODE == kSkResidLN) {
-    if (m < M) r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
+    if (epi) r4 = *reinterpret_cast<const uint4*>(p.resid + (size_t)m * kHidden + n0);
   }
   // partial row statistics: TPR adjacent lanes per row, all loads of a thread independent.  Where they are
   // reduced was measured on one box (p50 per query): 64-row bucket, after the main loop (loads overlap
@@ -126,11 +131,13 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
     for (int j = 0; j < kQueryParts / TPR; ++j) sp[j] = src[j * TPR];
     if constexpr (!kLateStats) reduce_stats();
   }
-  float acc[MT][4], acc2[MT][4];   // 64-row bucket: two accumulator sets, half the dependent mma chain (0.526 against 0.537 ms)
+  float acc[NT][MT][4], acc2[NT][MT][4];   // 64-row bucket: two accumulator sets, half the dependent mma chain (0.526 against 0.537 ms)
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[mt][i] = acc2[mt][i] = 0.f;
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][mt][i] = acc2[nt][mt][i] = 0.f;
 #pragma unroll
   for (int it = 0; it < KITERS; ++it) {
 #pragma unroll
@@ -140,35 +147,42 @@ static __global__ void __launch_bounds__(KSPLIT * 32) skinny_gemm_kernel(const S
       const uint4 hi = *reinterpret_cast<const uint4*>(ap + (size_t)8 * K);
       const uint32_t a0[4] = {lo.x, hi.x, lo.y, hi.y};
       const uint32_t a1[4] = {lo.z, hi.z, lo.w, hi.w};
-      mma_bf16_16816(acc[mt], a0, b[it].x, b[it].y);
-      mma_bf16_16816(kLateStats ? acc2[mt] : acc[mt], a1, b[it].z, b[it].w);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        mma_bf16_16816(acc[nt][mt], a0, b[nt][it].x, b[nt][it].y);
+        mma_bf16_16816(kLateStats ? acc2[nt][mt] : acc[nt][mt], a1, b[nt][it].z, b[nt][it].w);
+      }
     }
   }
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt)
+  for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[mt][i] += acc2[mt][i];
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[nt][mt][i] += acc2[nt][mt][i];
   if constexpr (kLateStats) {
     if (has_stats) reduce_stats();
   }
 #pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-    *reinterpret_cast<float2*>(&red[warp][mt * 16 + g][2 * q]) = make_float2(acc[mt][0], acc[mt][1]);
-    *reinterpret_cast<float2*>(&red[warp][mt * 16 + g + 8][2 * q]) = make_float2(acc[mt][2], acc[mt][3]);
-  }
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      *reinterpret_cast<float2*>(&red[warp][mt * 16 + g][nt * 8 + 2 * q]) = make_float2(acc[nt][mt][0], acc[nt][mt][1]);
+      *reinterpret_cast<float2*>(&red[warp][mt * 16 + g + 8][nt * 8 + 2 * q]) = make_float2(acc[nt][mt][2], acc[nt][mt][3]);
+    }
   __syncthreads();
   // only now may the next kernel start prefetching its weights: one kernel ahead, never a cascade of
   // waiting grids (measured: triggering at kernel entry made the whole path 1.3-2x slower)
   pdl_launch_dependents();
-  if (m >= M) return;
+  if (!epi) return;
   float v[8];
   {
-    const float4 x = *reinterpret_cast<const float4*>(&red[0][m][0]), y = *reinterpret_cast<const float4*>(&red[0][m][4]);
+    const float4 x = *reinterpret_cast<const float4*>(&red[0][m][cg * 8]), y = *reinterpret_cast<const float4*>(&red[0][m][cg * 8 + 4]);
     v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
   }
 #pragma unroll
   for (int w = 1; w < KSPLIT; ++w) {
-    const float4 x = *reinterpret_cast<const float4*>(&red[w][m][0]), y = *reinterpret_cast<const float4*>(&red[w][m][4]);
+    const float4 x = *reinterpret_cast<const float4*>(&red[w][m][cg * 8]), y = *reinterpret_cast<const float4*>(&red[w][m][cg * 8 + 4]);
     v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w; v[4] += y.x; v[5] += y.y; v[6] += y.z; v[7] += y.w;
   }
   float f[8];
@@ -318,9 +332,9 @@ inline cudaError_t pdl_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, c
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-template <int MT, int KSPLIT, int KITERS, int MODE>
+template <int MT, int KSPLIT, int KITERS, int MODE, int NT = 1>
 inline cudaError_t skinny_launch(const SkinnyParams& p, int N, cudaStream_t st) {
-  return pdl_launch(skinny_gemm_kernel<MT, KSPLIT, KITERS, MODE>, dim3((unsigned)(N / 8)), dim3(KSPLIT * 32), st, p);
+  return pdl_launch(skinny_gemm_kernel<MT, KSPLIT, KITERS, MODE, NT>, dim3((unsigned)(N / (8 * NT))), dim3(KSPLIT * 32), st, p);
 }
 
 }  // namespace enc
