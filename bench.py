@@ -37,6 +37,7 @@ BYTES_PER_ROW = D * 4  # 3072 B per corpus row per batch-1 query
 # DRAM traffic of one scan_topk_kernel launch from the committed ncu --set full capture
 # (profiles/r1_ncu_kernels_summary.txt: 3.072071 GB read + 4.0 MB written), keyed by rows per GPU.
 NCU_SCAN_TRAFFIC = {1_000_000: 3_072_071_000 + 4_015_872}
+NCU_SCAN_TRAFFIC_BF16 = {1_000_000: 1_536_116_000 + 7_468_288}   # phase-1 kernel of the two-phase scan
 
 
 def peaks():
@@ -257,7 +258,7 @@ def main():
     sharded = ShardedSearch(idx, id_offset)
     D_loc = torch.empty((1, K), device=dev, dtype=torch.float32)
     I_loc = torch.empty((1, K), device=dev, dtype=torch.int64)
-    launches_per_step = 1 if world == 1 else 2
+    launches_per_step = (3 if os.environ.get("CSS_SCAN_BF16", "1") != "0" else 1) + (0 if world == 1 else 1)
 
     def step(i):
         # local scan (+ for N > 1: all-gather of the k x 12 B lists and merge kernel)
@@ -284,7 +285,20 @@ def main():
         idx.search_device(qs[i % nq_pool].data_ptr(), 1, K, D_loc.data_ptr(), I_loc.data_ptr(), 0, id_offset, sp)
     ms_scan, _ = time_region(torch, dev, scan_only, args.steps, dist)
     ms_scan /= args.steps
-    achieved = rows * BYTES_PER_ROW / (ms_scan * 1e-3) / 1e9
+    # The default path is the two-phase exact scan: the dominant kernel sweeps the bf16 shadow rows (1536 B per row,
+    # half of SURVEY 8(d)'s 3072 B fp32 row), the fp32 rows are touched only for the few re-scored candidates.
+    # Its roofline is quoted on the bytes it has to read, timed alone through css_debug_scan_bf16.
+    two_phase = os.environ.get("CSS_SCAN_BF16", "1") != "0"
+    if two_phase:
+        def phase1_only(i):
+            idx.debug_scan_bf16(qs[i % nq_pool].data_ptr(), 1, sp)
+        ms_kernel, _ = time_region(torch, dev, phase1_only, args.steps, dist)
+        ms_kernel /= args.steps
+        kernel_bytes = rows * D * 2
+        kernel_name = "scan_topk_kernel<bf16 shadow> (phase 1 of the two-phase exact scan; + rescore768_kernel + idle fp32 fallback launch per step)"
+    else:
+        ms_kernel, kernel_bytes, kernel_name = ms_scan, rows * BYTES_PER_ROW, "scan_topk_kernel"
+    achieved = kernel_bytes / (ms_kernel * 1e-3) / 1e9
 
     # ---- e2e: the C-ABI call with HOST buffers (H2D of the query + D2H of D/I inside) ----
     qh = qs_host.numpy()
@@ -331,15 +345,23 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "exact top-10, 1M x 768 fp32 corpus per GPU, batch-1 queries (BASELINE configs[1])",
                        "rows_per_gpu": rows, "corpus_rows": rows * world, "dim": D, "k": K, "qps": qps,
+                       "path": "two-phase exact scan (bf16 shadow sweep + proven fp32 re-score)" if two_phase else "fp32 sweep",
                        "l2": "corpus (3.07 GB) >> 126 MB L2, no flush needed",
                        "exchange": "none" if world == 1 else "2 x ncclAllGather (k x 4 B + k x 8 B per rank) + merge kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / pk["hbm_gbs"], "traffic": NCU_SCAN_TRAFFIC.get(rows),
+                         "frac": achieved / pk["hbm_gbs"],
+                         "traffic": (NCU_SCAN_TRAFFIC_BF16 if two_phase else NCU_SCAN_TRAFFIC).get(rows),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
-                                           "(profiles/r1_ncu_kernels_summary.txt)" if rows in NCU_SCAN_TRAFFIC else None,
+                                           "(profiles/r1_scan_bf16_ncu_summary.txt)" if two_phase and rows in NCU_SCAN_TRAFFIC_BF16
+                                           else ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                                                 "(profiles/r1_ncu_kernels_summary.txt)" if rows in NCU_SCAN_TRAFFIC else None),
                          "peak_source": pk["source"],
-                         "kernel": "scan_topk_kernel", "kernel_ms": ms_scan,
-                         "algorithmic_bytes_per_launch": rows * BYTES_PER_ROW},
+                         "kernel": kernel_name, "kernel_ms": ms_kernel, "step_ms_device": ms_scan,
+                         "algorithmic_bytes_per_launch": kernel_bytes,
+                         "fp32_scan_equivalent_gbs": rows * BYTES_PER_ROW / (ms_scan * 1e-3) / 1e9,
+                         "note": ("two-phase exact scan: bf16 shadow sweep (1536 B/row) + fp32 re-score of the proven candidate "
+                                  "set; CSS_SCAN_BF16=0 selects the single fp32 sweep (3072 B/row)") if two_phase else
+                                 "single fp32 sweep (CSS_SCAN_BF16=0)"},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_qps * world, "unit": "queries/s" if world == 1 else "1M-row shard scans/s",
                     "h2d_bytes_per_step": D * 4, "d2h_bytes_per_step": K * 12,

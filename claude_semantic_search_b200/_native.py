@@ -121,6 +121,7 @@ SIGNATURES = {
     "css_encoder_max_tokens": (c_int64, [c_void_p]),
     "css_encoder_max_seq_len": (c_int, [c_void_p]),
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
+    "css_debug_scan_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "css_tokenizer_create": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
     "css_tokenizer_destroy": (c_int, [c_void_p]),
     "css_tokenizer_vocab_size": (c_int, [c_void_p]),
@@ -365,6 +366,10 @@ class Index:
         check(self._lib.css_index_search_device(self._h, c_void_p(q_ptr), nq, k,
                                                 c_void_p(mask_ptr) if mask_ptr else None, id_offset,
                                                 c_void_p(D_ptr), c_void_p(I_ptr), c_void_p(stream)))
+
+    def debug_scan_bf16(self, q_ptr: int, nq: int, stream: int = 0) -> None:
+        """Phase 1 alone of the two-phase scan (benchmark hook, css_debug_scan_bf16)."""
+        check(self._lib.css_debug_scan_bf16(self._h, c_void_p(q_ptr), nq, c_void_p(stream)))
 
     # -- persistence --------------------------------------------------------
     def save(self, path) -> None:

@@ -266,16 +266,94 @@ int ensure_query_scratch(css_index* h, int nq) {
   cudaFree(h->ticket);
   cudaFree(h->D_dev);
   cudaFree(h->I_dev);
+  cudaFree(h->ovf_list);
+  cudaFree(h->ovf_count);
   h->q_dev = nullptr; h->part = nullptr; h->ticket = nullptr; h->D_dev = nullptr; h->I_dev = nullptr;
+  h->ovf_list = nullptr; h->ovf_count = nullptr;
   h->max_nq = 0;
   CSS_CHECK(dev_alloc(&h->q_dev, (size_t)want * h->dim));
   CSS_CHECK(dev_alloc(&h->part, (size_t)want * h->scan_blocks * CSS_MAX_K));
   CSS_CHECK(dev_alloc(&h->ticket, (size_t)want));
   CSS_CHECK(dev_alloc(&h->D_dev, (size_t)want * CSS_MAX_K));
   CSS_CHECK(dev_alloc(&h->I_dev, (size_t)want * CSS_MAX_K));
+  CSS_CHECK(dev_alloc(&h->ovf_list, (size_t)want));
+  CSS_CHECK(dev_alloc(&h->ovf_count, (size_t)1));
   CSS_CUDA(cudaMemsetAsync(h->ticket, 0, (size_t)want * sizeof(unsigned int), h->stream));
   CSS_CUDA(cudaStreamSynchronize(h->stream));
   h->max_nq = want;
+  return CSS_OK;
+}
+
+// Two-phase exact scan (inner product, d = 768, no filter mask -- the alive bits of orphaned rows are fine --, k <= 32): phase 1 streams the bf16 shadow
+// rows -- half the bytes of the fp32 corpus -- and leaves the 32 best of every scan block's slice by that
+// score; phase 2 (rescore768_kernel) proves that the true top-k lies inside those lists, re-scores the
+// candidates in fp32 with the arithmetic of the fp32 scan and emits the exact result; queries it cannot
+// prove are re-run by the fp32 scan on the device (qlist), so the answer is always the exact one.
+// CSS_SCAN_BF16=0 disables it.
+int launch_phase1(css_index* h, const float* q_dev, int nq, const uint32_t* mask_dev, ScanParams* out, cudaStream_t st) {
+  ScanParams p;
+  p.x = h->x;
+  p.xb = h->xb;
+  p.n = h->ntotal;
+  p.d = h->dim;
+  p.q = q_dev;
+  p.mask = mask_dev;   // nullptr or the alive bits (dense): masked rows are skipped, not compacted
+  p.k = kTwoPhaseMaxK;
+  p.part = h->part;
+  p.ticket = h->ticket;
+  p.id_offset = 0;
+  p.D = nullptr;
+  p.I = nullptr;
+  p.qlist = nullptr;
+  p.qcount = nullptr;
+  p.no_merge = 1;
+  p.zero_on_entry = h->ovf_count;
+  const size_t smem = sizeof(KeyId) * kMergeCap;
+  auto kern = scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>;
+  CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<dim3((unsigned)h->scan_blocks, (unsigned)nq), kScanThreads, smem, st>>>(p);
+  CSS_LAUNCHED();
+  if (out) *out = p;
+  return CSS_OK;
+}
+
+int two_phase_scan(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev, int64_t id_offset,
+                   float* D_dev, int64_t* I_dev, cudaStream_t st) {
+  const int kp = kTwoPhaseMaxK;
+  ScanParams p;
+  CSS_CHECK(launch_phase1(h, q_dev, nq, mask_dev, &p, st));
+  RescoreParams r;
+  r.x = h->x;
+  r.q = q_dev;
+  r.k = k;
+  r.kp = kp;
+  r.blocks = h->scan_blocks;
+  r.eps_scale = 1.10f / 512.f;
+  r.max_norm = h->max_norm_dev;
+  r.part = h->part;
+  r.id_offset = id_offset;
+  r.D = D_dev;
+  r.I = I_dev;
+  r.ovf_list = h->ovf_list;
+  r.ovf_count = h->ovf_count;
+  {
+    const size_t smem = sizeof(KeyId) * kRescoreSort;
+    CSS_CUDA(cudaFuncSetAttribute(rescore768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rescore768_kernel<<<(unsigned)nq, kRescoreThreads, smem, st>>>(r);
+    CSS_LAUNCHED();
+  }
+  // unproven queries: fp32 scan, driven by the device-side list (an empty list costs one idle launch)
+  ScanParams f = p;
+  f.xb = nullptr;
+  f.k = k;
+  f.id_offset = id_offset;
+  f.D = D_dev;
+  f.I = I_dev;
+  f.qlist = h->ovf_list;
+  f.qcount = h->ovf_count;
+  f.no_merge = 0;
+  f.zero_on_entry = nullptr;
+  CSS_CHECK((launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, f, nq, st)));
   return CSS_OK;
 }
 
@@ -283,12 +361,17 @@ int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t*
                 int64_t id_offset, float* D_dev, int64_t* I_dev, cudaStream_t st) {
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
   CSS_CHECK(ensure_query_scratch(h, nq));
+  static const bool bf16_phase = [] { const char* v = getenv("CSS_SCAN_BF16"); return v ? atoi(v) != 0 : true; }();
+  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && (mask_dev == nullptr || mask_dev == h->alive) && k <= kTwoPhaseMaxK &&
+      nq <= 64 && h->xb != nullptr && h->ntotal > 0 && (int64_t)h->scan_blocks * kTwoPhaseMaxK <= kRescoreSort)
+    return two_phase_scan(h, q_dev, nq, k, mask_dev, id_offset, D_dev, I_dev, st);
   // gridDim.y is limited to 65535; chunk the query batch
   const int chunk = 4096;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     int nqc = std::min(chunk, nq - q0);
     ScanParams p;
     p.x = h->x;
+    p.xb = nullptr;
     p.n = h->ntotal;
     p.d = h->dim;
     p.q = q_dev + (size_t)q0 * h->dim;
@@ -301,6 +384,8 @@ int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t*
     p.I = I_dev + (size_t)q0 * k;
     p.qlist = nullptr;
     p.qcount = nullptr;
+    p.no_merge = 0;
+    p.zero_on_entry = nullptr;
     if (h->metric == CSS_METRIC_INNER_PRODUCT)
       CSS_CHECK((launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, p, nqc, st)));
     else
@@ -367,6 +452,8 @@ int css_index_destroy(css_index* h) {
     cudaFree(h->ticket);
     cudaFree(h->D_dev);
     cudaFree(h->I_dev);
+    cudaFree(h->ovf_list);
+    cudaFree(h->ovf_count);
     cudaFree(h->set_scratch);
     cudaFree(h->rowmask_scratch);
     cudaFree(h->n_pass_dev);
@@ -648,6 +735,17 @@ int css_index_filter_mask_device(css_index* h, const css_filter* f, const uint32
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st);
+}
+
+int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream) {
+  CSS_REQUIRE(h != nullptr && q_dev != nullptr, "NULL argument");
+  CSS_REQUIRE(nq >= 1 && nq <= 64, "nq=%d outside [1, 64]", nq);
+  CSS_REQUIRE(h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && h->ntotal > 0 && h->xb != nullptr,
+              "the two-phase scan needs a non-empty 768-d inner-product index");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  CSS_CHECK(ensure_query_scratch(h, nq));
+  return launch_phase1(h, q_dev, nq, h->any_dead ? h->alive : nullptr, nullptr, stream ? (cudaStream_t)stream : h->stream);
 }
 
 int css_index_search_device(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev,

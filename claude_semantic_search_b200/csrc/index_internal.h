@@ -35,6 +35,8 @@ struct css_index {
   unsigned int* ticket = nullptr;    // [max_nq]
   float* D_dev = nullptr;            // [max_nq, CSS_MAX_K]
   int64_t* I_dev = nullptr;          // [max_nq, CSS_MAX_K]
+  int* ovf_list = nullptr;           // two-phase scan: [max_nq] queries handed to the fp32 scan
+  int* ovf_count = nullptr;          // [1]
   uint32_t* set_scratch = nullptr;   // clause bitsets
   size_t set_scratch_words = 0;
   uint32_t* rowmask_scratch = nullptr;  // uploaded explicit row mask

@@ -132,6 +132,7 @@ struct WarpTopK {
 
 struct ScanParams {
   const float* x;        // [n, d]
+  const __nv_bfloat16* xb;  // [n, d] bf16 shadow rows (two-phase scan only)
   int64_t n;
   int d;
   const float* q;        // [nq, d]
@@ -144,6 +145,8 @@ struct ScanParams {
   int64_t* I;            // [nq, k]
   const int* qlist;      // nullable: explicit list of query indices to scan (device)
   const int* qcount;     // number of entries of qlist (device)
+  int no_merge;          // 1: stop after the per-block lists (two-phase scan, phase 1)
+  int* zero_on_entry;    // nullable: one int cleared by the first thread of the grid (phase 2's overflow count)
 };
 
 // Dot products (or negated squared distances) of up to 4 rows against the query.
@@ -203,11 +206,51 @@ __device__ __forceinline__ void score_rows(const ScanParams& p, const float4* qr
   }
 }
 
+// Two-phase scan, phase 1: inner products of the 8 rows of one unit against the fp32 query, the rows read
+// from the bf16 shadow copy (1536 B per 768-d row: 3 x 16 B per lane, lane l holds elements
+// 256 j + 8 l .. + 8 of the row; qreg is loaded in the same layout).
+__device__ __forceinline__ void score_unit_bf16(const ScanParams& p, const float4* qreg, int64_t row0, unsigned m,
+                                                int lane, float (&acc)[kRowsPerUnit]) {
+  uint4 v[kRowsPerUnit][3];
+#pragma unroll
+  for (int i = 0; i < kRowsPerUnit; ++i) {
+    const int64_t r = row0 + (((m >> i) & 1u) ? i : 0);   // rows past the end re-read the unit's first row
+    const uint4* row = reinterpret_cast<const uint4*>(p.xb + r * 768);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                   : "=r"(v[i][j].x), "=r"(v[i][j].y), "=r"(v[i][j].z), "=r"(v[i][j].w)
+                   : "l"(row + j * 32 + lane));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRowsPerUnit; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float4 qa = qreg[2 * j], qb = qreg[2 * j + 1];
+      a = fmaf(__uint_as_float(v[i][j].x << 16), qa.x, a);
+      a = fmaf(__uint_as_float(v[i][j].x & 0xffff0000u), qa.y, a);
+      a = fmaf(__uint_as_float(v[i][j].y << 16), qa.z, a);
+      a = fmaf(__uint_as_float(v[i][j].y & 0xffff0000u), qa.w, a);
+      a = fmaf(__uint_as_float(v[i][j].z << 16), qb.x, a);
+      a = fmaf(__uint_as_float(v[i][j].z & 0xffff0000u), qb.y, a);
+      a = fmaf(__uint_as_float(v[i][j].w << 16), qb.z, a);
+      a = fmaf(__uint_as_float(v[i][j].w & 0xffff0000u), qb.w, a);
+    }
+    acc[i] = a;
+  }
+#pragma unroll
+  for (int i = 0; i < kRowsPerUnit; ++i) acc[i] = warp_sum(acc[i]);
+}
+
 // grid = (blocks, nq).  Each warp owns a contiguous range of 8-row units, keeps
 // a register top-k, the block merges its 16 warps in shared memory, and the last
 // block to finish (atomic ticket) merges the per-block lists into D/I.
-template <int KPL, int METRIC, bool D768>
+// BF16 (inner product, d = 768, no mask): phase 1 of the two-phase scan -- scores from the bf16 shadow rows.
+template <int KPL, int METRIC, bool D768, bool BF16 = false>
 __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi) {
+  static_assert(!BF16 || (D768 && METRIC == CSS_METRIC_INNER_PRODUCT), "bf16 phase: inner product, d = 768");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
   float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
@@ -220,7 +263,13 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   const float* q = p.q + (int64_t)qi * p.d;
 
   float4 qreg[6];
-  if constexpr (D768) {
+  if constexpr (BF16) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      qreg[2 * j] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + lane * 8));
+      qreg[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + lane * 8) + 1);
+    }
+  } else if constexpr (D768) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) qreg[j] = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
   } else {
@@ -250,6 +299,18 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       }
     }
     const int nu = (int)min((int64_t)32, u_end - ub);
+    if constexpr (BF16) {
+      for (int j = 0; j < nu; ++j) {
+        const unsigned m = __shfl_sync(0xffffffffu, mb, j);
+        const int64_t row0 = (ub + j) * kRowsPerUnit;
+        float acc[kRowsPerUnit];
+        score_unit_bf16(p, qreg, row0, m, lane, acc);
+#pragma unroll
+        for (int i = 0; i < kRowsPerUnit; ++i)
+          if ((m >> i) & 1u) top.consider(acc[i], (int)(row0 + i), lane);
+      }
+      continue;
+    }
     if (mask8 != nullptr) {
       // Filtered scan: compact the selected rows of the 256-row window into a per-warp list first,
       // so that every score_rows call carries kRowsPerGroup distinct rows whatever the selectivity
@@ -324,6 +385,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   bitonic_sort_desc(s_list, kBlockEntries, tid, kScanThreads);
   KeyId* my_part = p.part + ((int64_t)qi * gridDim.x + blockIdx.x) * p.k;
   for (int i = tid; i < p.k; i += kScanThreads) my_part[i] = s_list[i];
+  if (p.no_merge) return;
 
   // ---- grid merge by the last block -----------------------------------------
   __threadfence();
@@ -379,16 +441,131 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 
 // grid = (blocks, nq) scans query blockIdx.y; with p.qlist set, grid = (blocks, F) and
 // slice y walks the listed queries y, y+F, ... (device-side fallback of the batched path).
-template <int KPL, int METRIC, bool D768>
+template <int KPL, int METRIC, bool D768, bool BF16 = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
+  if (p.zero_on_entry != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.zero_on_entry = 0;
   if (p.qlist == nullptr) {
-    scan_one_query<KPL, METRIC, D768>(p, blockIdx.y);
+    scan_one_query<KPL, METRIC, D768, BF16>(p, blockIdx.y);
     return;
   }
   const int cnt = *p.qcount;
   for (int slot = blockIdx.y; slot < cnt; slot += gridDim.y) {
-    scan_one_query<KPL, METRIC, D768>(p, p.qlist[slot]);
+    scan_one_query<KPL, METRIC, D768, BF16>(p, p.qlist[slot]);
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------
+// Two-phase scan, phase 2.  Phase 1 (scan_topk_kernel<.., BF16> with no_merge) left, per query and per
+// scan block, the kp = 32 best rows of that block's slice by their score against the bf16 shadow copy
+// (sorted; `part`).  Rounding a row to bf16 (the query stays fp32) moves its score by at most
+//   eps = eps_scale * ||q|| * max_row_norm        (u = 2^-9, |x.q| <= ||x|| ||q||, 10 % slack for the fp32 sums)
+// so with t <= the k-th best bf16 score overall (k rows are known to score at least t) the true k-th best
+// score is >= t - eps and every row of the true top-k has a bf16 score >= t - 2 eps =: thr.
+// A block list whose last entry is still >= thr may have dropped such a row: the query is then queued for
+// the fp32 scan (ovf_list), as it is when more than kRescoreCap rows pass -- never answered approximately.
+// Otherwise every row with bf16 score >= thr is in the lists: they are re-scored in fp32 with the
+// arithmetic of the fp32 scan (bit-identical scores) and the best k are the exact result.
+// One CTA per query; dynamic shared memory: kRescoreSort KeyId entries.
+// ------------------------------------------------------------------------
+constexpr int kRescoreThreads = 512;
+constexpr int kRescoreSort = 8192;   // >= scan blocks * k for k <= 32
+constexpr int kRescoreCap = 4096;    // candidates re-scored per query at most
+constexpr int kTwoPhaseMaxK = 32;    // = the per-block list length of phase 1 (KPL = 1)
+
+struct RescoreParams {
+  const float* x;
+  const float* q;
+  int k, kp, blocks;
+  float eps_scale;
+  const float* max_norm;
+  const KeyId* part;      // [nq][blocks][kp]
+  int64_t id_offset;
+  float* D;
+  int64_t* I;
+  int* ovf_list;
+  int* ovf_count;
+};
+
+static __global__ void __launch_bounds__(kRescoreThreads) rescore768_kernel(RescoreParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  KeyId* s = reinterpret_cast<KeyId*>(smem_raw);
+  __shared__ float s_qn;
+  __shared__ int s_count, s_unproven;
+  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* q = p.q + (size_t)qi * 768;
+  const KeyId* lists = p.part + (size_t)qi * p.blocks * p.kp;
+  if (warp == 0) {
+    float ss = 0.f;
+    for (int j = lane; j < 768; j += 32) ss = fmaf(q[j], q[j], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      s_qn = sqrtf(ss);
+      s_count = 0;
+      s_unproven = 0;
+    }
+  }
+  // t: a lower bound of the k-th best bf16 score overall.  With at least k block lists, the k-th largest of
+  // their heads (k distinct rows score at least that; ~150 values to sort instead of blocks * k -- the
+  // looser bound admits a few more candidates); otherwise the exact k-th best, which lies among the
+  // first k entries of the lists.
+  const int per = p.blocks >= p.k ? 1 : p.k;
+  const int nsel = p.blocks * per;
+  int n_sort = 32;
+  while (n_sort < nsel) n_sort <<= 1;
+  for (int i = tid; i < n_sort; i += kRescoreThreads) {
+    KeyId e;
+    e.key = -INFINITY;
+    e.id = kEmptyId;
+    if (i < nsel) e = lists[(i / per) * p.kp + (i % per)];
+    s[i] = e;
+  }
+  bitonic_sort_desc(s, n_sort, tid, kRescoreThreads);
+  const float eps = p.eps_scale * s_qn * (*p.max_norm);
+  const float thr = (s[p.k - 1].id != kEmptyId) ? s[p.k - 1].key - 2.f * eps : -INFINITY;
+  __syncthreads();
+  // proof + candidates over the full lists (s[] is free again)
+  for (int i = tid; i < p.blocks * p.kp; i += kRescoreThreads) {
+    const KeyId e = lists[i];
+    if (e.id != kEmptyId && e.key >= thr) {
+      if (i % p.kp == p.kp - 1) s_unproven = 1;
+      const int pos = atomicAdd(&s_count, 1);
+      if (pos < kRescoreCap) s[pos] = e;
+    }
+  }
+  __syncthreads();
+  const int keep = s_count;
+  if (s_unproven || keep > kRescoreCap) {
+    if (tid == 0) p.ovf_list[atomicAdd(p.ovf_count, 1)] = qi;
+    return;
+  }
+  for (int i = warp; i < keep; i += kRescoreThreads / 32) {
+    const float4* row = reinterpret_cast<const float4*>(p.x + (size_t)s[i].id * 768);
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 xv = ld_stream_f4(row + j * 32 + lane);
+      const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
+      a = fmaf(xv.x, qv.x, a);
+      a = fmaf(xv.y, qv.y, a);
+      a = fmaf(xv.z, qv.z, a);
+      a = fmaf(xv.w, qv.w, a);
+    }
+    a = warp_sum(a);
+    if (lane == 0) s[i].key = a;
+  }
+  int n2 = 32;
+  while (n2 < keep) n2 <<= 1;
+  __syncthreads();
+  for (int i = keep + tid; i < n2; i += kRescoreThreads) {
+    s[i].key = -INFINITY;
+    s[i].id = kEmptyId;
+  }
+  bitonic_sort_desc(s, n2, tid, kRescoreThreads);
+  for (int i = tid; i < p.k; i += kRescoreThreads) {
+    const bool empty = s[i].id == kEmptyId;
+    p.D[(size_t)qi * p.k + i] = empty ? -FLT_MAX : s[i].key;
+    p.I[(size_t)qi * p.k + i] = empty ? (int64_t)-1 : (int64_t)s[i].id + p.id_offset;
   }
 }
 

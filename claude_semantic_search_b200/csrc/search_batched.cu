@@ -459,6 +459,9 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
     // overflowed queries (if any): exact streaming scan, driven by the device-side list
     ScanParams p;
     p.x = h->x;
+    p.xb = nullptr;
+    p.no_merge = 0;
+    p.zero_on_entry = nullptr;
     p.n = N;
     p.d = d;
     p.q = qc;

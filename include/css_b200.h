@@ -285,6 +285,10 @@ int css_debug_gemm_resid_ln(const float* A, const float* B, const float* bias, c
 int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, const float* rel_table,
                         int rel_half, int device, float* ctx);
 
+/*   scan_bf16: phase 1 alone of the two-phase batch-1 scan (the bf16 shadow sweep that leaves the per-block
+ *              candidate lists), on `stream`, for the roofline measurement of bench.py; no result is produced. */
+int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream);
+
 /* Timing hook for benchmarks: number of kernels this library has launched in
  * this process (all handles). */
 int64_t css_kernel_launch_count(void);

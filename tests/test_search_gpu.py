@@ -159,6 +159,66 @@ def test_scan_200k_vs_oracle(native):
     idx.close()
 
 
+def test_two_phase_scan_proof_and_fallback(native):
+    """Batch-1 / small-nq searches of a 768-d inner-product index stream the bf16 shadow rows first and prove the
+    exact top-k from the 64 / 128 best of that pass (rescore768_kernel); what cannot be proven -- more rows within
+    the rounding bound of the k-th score than the list holds -- is re-run by the fp32 scan on the device.  Either
+    way the answer is the exact one, with the fp32 scan's scores (bit-identical to the batched path)."""
+    rng = np.random.default_rng(123)
+    n, d = 150_000, 768
+    x = so.normalize_rows(rng.standard_normal((n, d), dtype=np.float32))
+    q = so.normalize_rows(rng.standard_normal((15, d), dtype=np.float32))
+    # query 0: 400 near-duplicates of the query, all inside the bf16 rounding bound of each other -> fallback
+    near = rng.choice(n, size=400, replace=False)
+    x[near] = so.normalize_rows(q[0] + 1e-4 * rng.standard_normal((400, d), dtype=np.float32))
+    # query 1: 30 exact duplicates straddle the k-th place -> ids decide, proven from the list (30 < 64)
+    dup = rng.choice(np.setdiff1d(np.arange(n), near), size=30, replace=False)
+    x[dup] = so.normalize_rows(q[1] + 0.5 * so.normalize_rows(rng.standard_normal((1, d), dtype=np.float32)))[0]
+    # query 2: scores 1e-3 apart around the k-th place (inside 2 eps: order must come from the fp32 re-score)
+    lad = rng.choice(np.setdiff1d(np.arange(n), np.concatenate([near, dup])), size=24, replace=False)
+    u = so.normalize_rows(rng.standard_normal((1, d), dtype=np.float32))[0]
+    u -= (u @ q[2]) * q[2]
+    u /= np.linalg.norm(u)
+    for j, r in enumerate(lad):
+        c = 0.9 - 1e-3 * j
+        x[r] = c * q[2] + np.sqrt(1 - c * c) * u
+    idx = native.Index(d)
+    idx.add(x, normalize=False)
+    for k in (1, 10, 32, 33, 64):
+        D, I = idx.search(q, k)
+        Dr, Ir = so.flat_search_c(x, q, k)
+        _check(Dr, Ir, D, I)
+    D, I = idx.search(q[:3], 10)
+    assert set(I[0]) <= set(near.tolist()) and set(I[1]) <= set(dup.tolist())
+    np.testing.assert_array_equal(I[1], np.sort(dup)[:10])          # ties: ascending id
+    np.testing.assert_array_equal(I[2], lad[:10])                    # the ladder, in order
+    # same scores, bit for bit, as the tensor-core batched path (both re-score with the fp32 scan's arithmetic)
+    qb = np.concatenate([q, so.normalize_rows(rng.standard_normal((17, d), dtype=np.float32))])
+    Db, Ib = idx.search(qb, 10)
+    for i in range(15):
+        D1, I1 = idx.search(q[i:i + 1], 10)
+        np.testing.assert_array_equal(I1[0], Ib[i])
+        np.testing.assert_array_equal(D1[0], Db[i])
+    # orphaned rows (alive bits) stay on the two-phase path: kill the current winners and 2000 random rows
+    alive = np.ones(n, np.uint8)
+    alive[I[:3, :5].ravel()] = 0
+    alive[rng.choice(n, size=2000, replace=False)] = 0
+    idx.set_alive(alive)
+    Da, Ia = idx.search(q, 10)
+    Dr, Ir = so.flat_search_c(x, q, 10, mask_words=so.pack_mask(alive.astype(bool)))
+    _check(Dr, Ir, Da, Ia)
+    assert alive[Ia].all()
+    idx.close()
+    # un-normalised rows (norms 0.1 .. 30): the bound scales with the largest row norm
+    y = x[:60_000] * rng.uniform(0.1, 30.0, size=(60_000, 1)).astype(np.float32)
+    idy = native.Index(d)
+    idy.add(y, normalize=False)
+    D, I = idy.search(q[3:9], 10)
+    Dr, Ir = so.flat_search_c(y, q[3:9], 10)
+    _check(Dr, Ir, D, I, tol=TOL * 30)
+    idy.close()
+
+
 def test_batched_queries_vs_oracle(native):
     """nq >= 16 over >= 65536 rows takes the batched (tensor-core) entry."""
     rng = np.random.default_rng(43)
