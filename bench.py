@@ -347,7 +347,7 @@ def main():
                        "rows_per_gpu": rows, "corpus_rows": rows * world, "dim": D, "k": K, "qps": qps,
                        "path": "two-phase exact scan (bf16 shadow sweep + proven fp32 re-score)" if two_phase else "fp32 sweep",
                        "l2": "corpus (3.07 GB) >> 126 MB L2, no flush needed",
-                       "exchange": "none" if world == 1 else "2 x ncclAllGather (k x 4 B + k x 8 B per rank) + merge kernel"},
+                       "exchange": "none" if world == 1 else "1 x ncclAllGather of the packed lists (k x 12 B per rank) + merge kernel"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"],
                          "traffic": (NCU_SCAN_TRAFFIC_BF16 if two_phase else NCU_SCAN_TRAFFIC).get(rows),

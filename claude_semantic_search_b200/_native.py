@@ -110,6 +110,8 @@ SIGNATURES = {
     "css_index_search": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(css_filter), c_void_p, c_void_p]),
     "css_index_search_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "css_topk_merge_device": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "css_topk_merge_strided_device": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int,
+                                              c_void_p, c_void_p, c_void_p]),
     "css_index_save": (c_int, [c_void_p, c_char_p]),
     "css_index_load": (c_int, [c_void_p, c_char_p]),
     "css_kernel_launch_count": (c_int64, []),
@@ -378,6 +380,12 @@ class Index:
     def load(self, path) -> None:
         check(self._lib.css_index_load(self._h, str(path).encode()))
         self.metric = int(self._lib.css_index_metric(self._h))
+
+
+def topk_merge_strided_device(D_in_ptr: int, d_stride: int, I_in_ptr: int, i_stride: int, n_lists: int, nq: int, k: int,
+                              metric: int, D_out_ptr: int, I_out_ptr: int, stream: int = 0) -> None:
+    check(load().css_topk_merge_strided_device(c_void_p(D_in_ptr), d_stride, c_void_p(I_in_ptr), i_stride, n_lists, nq, k,
+                                               metric, c_void_p(D_out_ptr), c_void_p(I_out_ptr), c_void_p(stream)))
 
 
 def topk_merge_device(D_in_ptr: int, I_in_ptr: int, n_lists: int, nq: int, k: int, metric: int,

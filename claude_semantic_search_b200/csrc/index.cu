@@ -807,11 +807,12 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   return CSS_OK;
 }
 
-int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, int nq, int k,
-                          int metric, float* D_out, int64_t* I_out, void* stream) {
+int css_topk_merge_strided_device(const float* D_in, int64_t d_list_stride, const int64_t* I_in, int64_t i_list_stride,
+                                  int n_lists, int nq, int k, int metric, float* D_out, int64_t* I_out, void* stream) {
   CSS_REQUIRE(D_in && I_in && D_out && I_out, "NULL device buffer");
   CSS_REQUIRE(n_lists >= 1 && nq >= 0 && k >= 1 && k <= CSS_MAX_K, "bad merge shape");
   CSS_REQUIRE((int64_t)n_lists * k <= 8192, "n_lists*k too large for the merge kernel");
+  CSS_REQUIRE(d_list_stride >= (int64_t)nq * k && i_list_stride >= (int64_t)nq * k, "list stride below nq*k");
   if (nq == 0) return CSS_OK;
   int n_sort = 32;
   while (n_sort < n_lists * k) n_sort <<= 1;
@@ -821,14 +822,20 @@ int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, i
   if (metric == CSS_METRIC_INNER_PRODUCT) {
     auto kern = merge_lists_kernel<CSS_METRIC_INNER_PRODUCT>;
     CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<nq, threads, smem, st>>>(D_in, I_in, n_lists, nq, k, D_out, I_out);
+    kern<<<nq, threads, smem, st>>>(D_in, I_in, d_list_stride, i_list_stride, n_lists, nq, k, D_out, I_out);
   } else {
     auto kern = merge_lists_kernel<CSS_METRIC_L2>;
     CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<nq, threads, smem, st>>>(D_in, I_in, n_lists, nq, k, D_out, I_out);
+    kern<<<nq, threads, smem, st>>>(D_in, I_in, d_list_stride, i_list_stride, n_lists, nq, k, D_out, I_out);
   }
   CSS_LAUNCHED();
   return CSS_OK;
+}
+
+int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, int nq, int k,
+                          int metric, float* D_out, int64_t* I_out, void* stream) {
+  return css_topk_merge_strided_device(D_in, (int64_t)nq * k, I_in, (int64_t)nq * k, n_lists, nq, k, metric, D_out,
+                                       I_out, stream);
 }
 
 // ---------------------------------------------------------------------------

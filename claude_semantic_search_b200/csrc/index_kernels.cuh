@@ -721,6 +721,7 @@ static __global__ void filter_mask_kernel(FilterParams p) {
 // ------------------------------------------------------------------------
 template <int METRIC>
 __global__ void merge_lists_kernel(const float* __restrict__ D_in, const int64_t* __restrict__ I_in,
+                                   int64_t d_stride, int64_t i_stride,   // elements between consecutive lists
                                    int n_lists, int nq, int k, float* __restrict__ D_out,
                                    int64_t* __restrict__ I_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -737,10 +738,10 @@ __global__ void merge_lists_kernel(const float* __restrict__ D_in, const int64_t
     e.id = LLONG_MAX;
     if (i < total) {
       int l = i / k, j = i % k;
-      int64_t src = ((int64_t)l * nq + qi) * k + j;
-      int64_t id = I_in[src];
+      const int64_t within = (int64_t)qi * k + j;
+      int64_t id = I_in[l * i_stride + within];
       if (id >= 0) {
-        float dv = D_in[src];
+        float dv = D_in[l * d_stride + within];
         e.key = (METRIC == CSS_METRIC_INNER_PRODUCT) ? dv : -dv;
         e.id = id;
       }

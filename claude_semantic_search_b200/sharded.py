@@ -59,11 +59,15 @@ class ShardedSearch:
     def _device_bufs(self, torch, dev, nq, k):
         key = (nq, k)
         if key not in self._bufs:
+            # one packed buffer per rank -- scores, then (8-byte aligned) ids -- so that a search needs ONE all-gather
+            d_bytes = (nq * k * 4 + 7) // 8 * 8
+            stride = d_bytes + nq * k * 8
+            loc = torch.empty(stride, device=dev, dtype=torch.uint8)
+            allb = torch.empty(self.world * stride, device=dev, dtype=torch.uint8)
             self._bufs[key] = dict(
-                D_loc=torch.empty((nq, k), device=dev, dtype=torch.float32),
-                I_loc=torch.empty((nq, k), device=dev, dtype=torch.int64),
-                D_all=torch.empty((self.world, nq, k), device=dev, dtype=torch.float32),
-                I_all=torch.empty((self.world, nq, k), device=dev, dtype=torch.int64),
+                loc=loc, all=allb, stride=stride, d_bytes=d_bytes,
+                D_loc=loc[:nq * k * 4].view(torch.float32).view(nq, k),
+                I_loc=loc[d_bytes:].view(torch.int64).view(nq, k),
                 D_out=torch.empty((nq, k), device=dev, dtype=torch.float32),
                 I_out=torch.empty((nq, k), device=dev, dtype=torch.int64))
         return self._bufs[key]
@@ -80,10 +84,10 @@ class ShardedSearch:
                                  self.id_offset, sp)
         if self.world == 1:
             return b["D_loc"], b["I_loc"]
-        self.dist.all_gather_into_tensor(b["D_all"], b["D_loc"], group=self.group)
-        self.dist.all_gather_into_tensor(b["I_all"], b["I_loc"], group=self.group)
-        _native.topk_merge_device(b["D_all"].data_ptr(), b["I_all"].data_ptr(), self.world, nq, k, self.index.metric,
-                                  b["D_out"].data_ptr(), b["I_out"].data_ptr(), sp)
+        self.dist.all_gather_into_tensor(b["all"], b["loc"], group=self.group)
+        base = b["all"].data_ptr()
+        _native.topk_merge_strided_device(base, b["stride"] // 4, base + b["d_bytes"], b["stride"] // 8, self.world, nq, k,
+                                          self.index.metric, b["D_out"].data_ptr(), b["I_out"].data_ptr(), sp)
         return b["D_out"], b["I_out"]
 
     def search_host(self, q: np.ndarray, k: int):

@@ -171,6 +171,11 @@ int css_index_filter_mask_device(css_index* h, const css_filter* f,
  * all DEVICE; writes the merged best-k per query.  metric as in css_metric. */
 int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, int nq,
                           int k, int metric, float* D_out, int64_t* I_out, void* stream);
+/* The same with list l at D_in + l * d_list_stride / I_in + l * i_list_stride (elements): lets every rank
+ * ship its scores and ids in ONE packed buffer, i.e. one all-gather per search instead of two. */
+int css_topk_merge_strided_device(const float* D_in, int64_t d_list_stride, const int64_t* I_in,
+                                  int64_t i_list_stride, int n_lists, int nq, int k, int metric, float* D_out,
+                                  int64_t* I_out, void* stream);
 
 /* faiss-compatible persistence: IndexFlatIP ("IxFI") / IndexFlatL2 ("IxF2")
  * files as written by faiss.write_index (src/storage.py:879-884). */
