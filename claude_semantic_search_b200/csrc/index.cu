@@ -284,7 +284,7 @@ int ensure_query_scratch(css_index* h, int nq) {
   return CSS_OK;
 }
 
-// Two-phase exact scan (inner product, d = 768, no filter mask -- the alive bits of orphaned rows are fine --, k <= 32): phase 1 streams the bf16 shadow
+// Two-phase exact scan (inner product, d = 768, k <= 32, with or without a row mask): phase 1 streams the bf16 shadow
 // rows -- half the bytes of the fp32 corpus -- and leaves the 32 best of every scan block's slice by that
 // score; phase 2 (rescore768_kernel) proves that the true top-k lies inside those lists, re-scores the
 // candidates in fp32 with the arithmetic of the fp32 scan and emits the exact result; queries it cannot
@@ -297,7 +297,7 @@ int launch_phase1(css_index* h, const float* q_dev, int nq, const uint32_t* mask
   p.n = h->ntotal;
   p.d = h->dim;
   p.q = q_dev;
-  p.mask = mask_dev;   // nullptr or the alive bits (dense): masked rows are skipped, not compacted
+  p.mask = mask_dev;   // nullable: filter / alive bits (the selected rows of a window are compacted first)
   p.k = kTwoPhaseMaxK;
   p.part = h->part;
   p.ticket = h->ticket;
@@ -362,7 +362,7 @@ int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t*
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
   CSS_CHECK(ensure_query_scratch(h, nq));
   static const bool bf16_phase = [] { const char* v = getenv("CSS_SCAN_BF16"); return v ? atoi(v) != 0 : true; }();
-  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && (mask_dev == nullptr || mask_dev == h->alive) && k <= kTwoPhaseMaxK &&
+  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK &&
       nq <= 64 && h->xb != nullptr && h->ntotal > 0 && (int64_t)h->scan_blocks * kTwoPhaseMaxK <= kRescoreSort)
     return two_phase_scan(h, q_dev, nq, k, mask_dev, id_offset, D_dev, I_dev, st);
   // gridDim.y is limited to 65535; chunk the query batch

@@ -206,16 +206,15 @@ __device__ __forceinline__ void score_rows(const ScanParams& p, const float4* qr
   }
 }
 
-// Two-phase scan, phase 1: inner products of the 8 rows of one unit against the fp32 query, the rows read
+// Two-phase scan, phase 1: inner products of 8 rows against the fp32 query, the rows read
 // from the bf16 shadow copy (1536 B per 768-d row: 3 x 16 B per lane, lane l holds elements
 // 256 j + 8 l .. + 8 of the row; qreg is loaded in the same layout).
-__device__ __forceinline__ void score_unit_bf16(const ScanParams& p, const float4* qreg, int64_t row0, unsigned m,
+__device__ __forceinline__ void score_rows_bf16(const ScanParams& p, const float4* qreg, const int64_t (&r)[kRowsPerUnit],
                                                 int lane, float (&acc)[kRowsPerUnit]) {
   uint4 v[kRowsPerUnit][3];
 #pragma unroll
   for (int i = 0; i < kRowsPerUnit; ++i) {
-    const int64_t r = row0 + (((m >> i) & 1u) ? i : 0);   // rows past the end re-read the unit's first row
-    const uint4* row = reinterpret_cast<const uint4*>(p.xb + r * 768);
+    const uint4* row = reinterpret_cast<const uint4*>(p.xb + r[i] * 768);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -300,16 +299,21 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     }
     const int nu = (int)min((int64_t)32, u_end - ub);
     if constexpr (BF16) {
-      for (int j = 0; j < nu; ++j) {
-        const unsigned m = __shfl_sync(0xffffffffu, mb, j);
-        const int64_t row0 = (ub + j) * kRowsPerUnit;
-        float acc[kRowsPerUnit];
-        score_unit_bf16(p, qreg, row0, m, lane, acc);
+      if (mask8 == nullptr) {   // dense: one 8-row unit per step (only the corpus tail has cleared bits)
+        for (int j = 0; j < nu; ++j) {
+          const unsigned m = __shfl_sync(0xffffffffu, mb, j);
+          const int64_t row0 = (ub + j) * kRowsPerUnit;
+          int64_t r[kRowsPerUnit];
 #pragma unroll
-        for (int i = 0; i < kRowsPerUnit; ++i)
-          if ((m >> i) & 1u) top.consider(acc[i], (int)(row0 + i), lane);
+          for (int i = 0; i < kRowsPerUnit; ++i) r[i] = row0 + (((m >> i) & 1u) ? i : 0);   // rows past the end re-read the first
+          float acc[kRowsPerUnit];
+          score_rows_bf16(p, qreg, r, lane, acc);
+#pragma unroll
+          for (int i = 0; i < kRowsPerUnit; ++i)
+            if ((m >> i) & 1u) top.consider(acc[i], (int)(row0 + i), lane);
+        }
+        continue;
       }
-      continue;
     }
     if (mask8 != nullptr) {
       // Filtered scan: compact the selected rows of the 256-row window into a per-warp list first,
@@ -332,6 +336,20 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       }
       __syncwarp();
       const int64_t base = ub * kRowsPerUnit;
+      if constexpr (BF16) {
+        for (int g0 = 0; g0 < total; g0 += kRowsPerUnit) {
+          int64_t r[kRowsPerUnit];
+#pragma unroll
+          for (int i = 0; i < kRowsPerUnit; ++i) r[i] = base + s_rows[warp][min(g0 + i, total - 1)];
+          float acc[kRowsPerUnit];
+          score_rows_bf16(p, qreg, r, lane, acc);
+#pragma unroll
+          for (int i = 0; i < kRowsPerUnit; ++i)
+            if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
+        }
+        __syncwarp();
+        continue;
+      }
       for (int g0 = 0; g0 < total; g0 += kRowsPerGroup) {
         int64_t r[kRowsPerGroup];
 #pragma unroll
