@@ -265,17 +265,15 @@ int ensure_query_scratch(css_index* h, int nq) {
   cudaFree(h->part);
   cudaFree(h->ticket);
   cudaFree(h->D_dev);
-  cudaFree(h->I_dev);
   cudaFree(h->ovf_list);
   cudaFree(h->ovf_count);
-  h->q_dev = nullptr; h->part = nullptr; h->ticket = nullptr; h->D_dev = nullptr; h->I_dev = nullptr;
+  h->q_dev = nullptr; h->part = nullptr; h->ticket = nullptr; h->D_dev = nullptr;
   h->ovf_list = nullptr; h->ovf_count = nullptr;
   h->max_nq = 0;
   CSS_CHECK(dev_alloc(&h->q_dev, (size_t)want * h->dim));
   CSS_CHECK(dev_alloc(&h->part, (size_t)want * h->scan_blocks * CSS_MAX_K));
   CSS_CHECK(dev_alloc(&h->ticket, (size_t)want));
-  CSS_CHECK(dev_alloc(&h->D_dev, (size_t)want * CSS_MAX_K));
-  CSS_CHECK(dev_alloc(&h->I_dev, (size_t)want * CSS_MAX_K));
+  CSS_CHECK(dev_alloc(&h->D_dev, (size_t)want * CSS_MAX_K * 3 + 8));   // scores, then the ids of the same call (one D2H)
   CSS_CHECK(dev_alloc(&h->ovf_list, (size_t)want));
   CSS_CHECK(dev_alloc(&h->ovf_count, (size_t)1));
   CSS_CUDA(cudaMemsetAsync(h->ticket, 0, (size_t)want * sizeof(unsigned int), h->stream));
@@ -451,7 +449,6 @@ int css_index_destroy(css_index* h) {
     cudaFree(h->part);
     cudaFree(h->ticket);
     cudaFree(h->D_dev);
-    cudaFree(h->I_dev);
     cudaFree(h->ovf_list);
     cudaFree(h->ovf_count);
     cudaFree(h->set_scratch);
@@ -792,15 +789,16 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   size_t d_off = (qbytes + 15) / 16 * 16;
   size_t i_off = (d_off + dbytes + 15) / 16 * 16;
   CSS_CUDA(cudaMemcpyAsync(h->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
+  // results of this call: scores at D_dev, ids right behind them (same spacing as in the pinned block)
+  int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(h->D_dev) + (i_off - d_off));
   int rc;
   if (nq >= CSS_BATCH_MIN_NQ && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim % 64 == 0 &&
       h->ntotal >= 65536)
-    rc = batched_search(h, h->q_dev, nq, k, m, 0, h->D_dev, h->I_dev, st);
+    rc = batched_search(h, h->q_dev, nq, k, m, 0, h->D_dev, I_dev, st);
   else
-    rc = scan_search(h, h->q_dev, nq, k, m, 0, h->D_dev, h->I_dev, st);
+    rc = scan_search(h, h->q_dev, nq, k, m, 0, h->D_dev, I_dev, st);
   if (rc != CSS_OK) return rc;
-  CSS_CUDA(cudaMemcpyAsync(pin + d_off, h->D_dev, dbytes, cudaMemcpyDeviceToHost, st));
-  CSS_CUDA(cudaMemcpyAsync(pin + i_off, h->I_dev, ibytes, cudaMemcpyDeviceToHost, st));
+  CSS_CUDA(cudaMemcpyAsync(pin + d_off, h->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
   CSS_CUDA(cudaStreamSynchronize(st));
   memcpy(D_host, pin + d_off, dbytes);
   memcpy(I_host, pin + i_off, ibytes);

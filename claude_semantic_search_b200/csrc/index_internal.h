@@ -33,8 +33,7 @@ struct css_index {
   float* q_dev = nullptr;            // [max_nq, dim]
   css::KeyId* part = nullptr;        // [max_nq][scan_blocks][CSS_MAX_K]
   unsigned int* ticket = nullptr;    // [max_nq]
-  float* D_dev = nullptr;            // [max_nq, CSS_MAX_K]
-  int64_t* I_dev = nullptr;          // [max_nq, CSS_MAX_K]
+  float* D_dev = nullptr;            // [max_nq, CSS_MAX_K] scores + ids of one host call (12 B per slot)
   int* ovf_list = nullptr;           // two-phase scan: [max_nq] queries handed to the fp32 scan
   int* ovf_count = nullptr;          // [1]
   uint32_t* set_scratch = nullptr;   // clause bitsets
