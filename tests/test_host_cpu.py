@@ -190,6 +190,77 @@ def test_native_tokenizer_equals_fast_pipeline_on_all_of_unicode(tmp_path):
     assert SentenceTransformer._load_tokenizer(other) is None
 
 
+def test_tokenizer_json_of_the_mpnet_layout_is_accepted(tmp_path):
+    """The layout all-mpnet-base-v2 ships (RobertaProcessing post-processor, six added special tokens with
+    lstrip on <mask>) is recognised as the native pipeline; near misses are not."""
+    import json
+
+    from claude_semantic_search_b200.st_compat import native_tokenizer_settings
+    vocab = {"<s>": 0, "<pad>": 1, "</s>": 2, "<unk>": 3, "[UNK]": 4, "hello": 5, "<mask>": 6}
+    added = [{"id": i, "content": c, "single_word": False, "lstrip": c == "<mask>", "rstrip": False, "normalized": False,
+              "special": True} for c, i in (("<s>", 0), ("<pad>", 1), ("</s>", 2), ("<unk>", 3), ("[UNK]", 4), ("<mask>", 6))]
+    cfg = {"version": "1.0", "truncation": {"max_length": 384}, "padding": None, "added_tokens": added,
+           "normalizer": {"type": "BertNormalizer", "clean_text": True, "handle_chinese_chars": True, "strip_accents": None,
+                          "lowercase": True},
+           "pre_tokenizer": {"type": "BertPreTokenizer"},
+           "post_processor": {"type": "RobertaProcessing", "sep": ["</s>", 2], "cls": ["<s>", 0], "trim_offsets": True,
+                              "add_prefix_space": False},
+           "decoder": {"type": "WordPiece", "prefix": "##", "cleanup": True},
+           "model": {"type": "WordPiece", "unk_token": "[UNK]", "continuing_subword_prefix": "##",
+                     "max_input_chars_per_word": 100, "vocab": vocab}}
+    f = tmp_path / "tokenizer.json"
+
+    def settings(mut=None):
+        c = json.loads(json.dumps(cfg))
+        if mut:
+            mut(c)
+        f.write_text(json.dumps(c), encoding="utf-8")
+        return native_tokenizer_settings(f)
+    st = settings()
+    assert st is not None and st["lower"] is True and st["specials"] == {a["content"]: a["id"] for a in added}
+    assert settings(lambda c: c["normalizer"].update(lowercase=False))["lower"] is False
+    assert settings(lambda c: c["normalizer"].update(strip_accents=False)) is None       # accents kept while lower-casing
+    assert settings(lambda c: c["normalizer"].update(type="NFKC")) is None
+    assert settings(lambda c: c["pre_tokenizer"].update(type="Whitespace")) is None
+    assert settings(lambda c: c["model"].update(max_input_chars_per_word=200)) is None
+    assert settings(lambda c: c["model"].update(continuing_subword_prefix="@@")) is None
+    assert settings(lambda c: c["post_processor"].update(cls=["[CLS]", 0])) is None
+    assert settings(lambda c: c["added_tokens"][0].update(single_word=True)) is None
+    assert settings(lambda c: c["added_tokens"].append({"id": 5, "content": "hello", "single_word": False, "lstrip": False,
+                                                        "rstrip": False, "normalized": True, "special": False})) is None
+    f.write_text("{not json", encoding="utf-8")
+    assert native_tokenizer_settings(f) is None
+
+
+def test_pipelined_text_encoding_slabs():
+    """encode_texts_pipelined: every text is tokenised and encoded exactly once, in order, whatever the slab size;
+    a short tail is merged into the previous slab (a slab of one text would take the single-query path)."""
+    from claude_semantic_search_b200.st_compat import encode_texts_pipelined
+
+    class Tok:
+        def __init__(self):
+            self.calls = []
+
+        def encode_packed(self, texts, max_len):
+            self.calls.append(len(texts))
+            ids = np.asarray([int(t) for t in texts], np.int32)
+            return ids, np.arange(len(texts) + 1, dtype=np.int32)
+
+    class Enc:
+        dim = 3
+
+        def encode_packed(self, ids, cu, normalize=True):
+            assert cu[-1] == ids.shape[0]
+            return np.stack([ids, ids * 2, ids * 3], axis=1).astype(np.float32)
+    for n, slab in ((0, 4), (1, 4), (5, 4), (6, 4), (7, 4), (9, 4), (100, 7), (1000, 64), (1025, 1024), (4096, 1024)):
+        tok = Tok()
+        texts = [str(i) for i in range(n)]
+        out = encode_texts_pipelined(tok, Enc(), texts, 384, True, slab)
+        assert out.shape == (n, 3)
+        np.testing.assert_array_equal(out[:, 0], np.arange(n, dtype=np.float32))
+        assert sum(tok.calls) == n and (n < 2 or min(tok.calls) >= 2), (n, slab, tok.calls)
+
+
 def test_standin_tokenizer_is_deterministic_and_bounded():
     from claude_semantic_search_b200.st_compat import StandInTokenizer
     t = StandInTokenizer()
