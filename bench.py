@@ -36,6 +36,7 @@ ROWS = 1_000_000
 BYTES_PER_ROW = D * 4  # 3072 B per corpus row per batch-1 query
 # DRAM traffic of one scan_topk_kernel launch from the committed ncu --set full capture
 # (profiles/r1_ncu_kernels_summary.txt: 3.072071 GB read + 4.0 MB written), keyed by rows per GPU.
+WORKLOAD = "exact top-10, 1M x 768 fp32 corpus per GPU, batch-1 queries (BASELINE configs[1])"
 NCU_SCAN_TRAFFIC = {1_000_000: 3_072_071_000 + 4_015_872}
 NCU_SCAN_TRAFFIC_BF16 = {1_000_000: 1_536_116_000 + 7_468_288}   # phase-1 kernel of the two-phase scan
 
@@ -149,7 +150,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "exact top-10 QPS @ 1Mx768 fp32, batch-1", "value": qps,
             "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": "exact top-10, 1M x 768 fp32 corpus, batch-1 queries (BASELINE configs[1])"},
+            "data": "synthetic", "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "dim": D, "k": K, "path": "CPU port of faiss IndexFlatIP.search"},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": int(cores), "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -343,7 +344,7 @@ def main():
             "value": qps * world, "unit": "queries/s" if world == 1 else "1M-row shard scans/s (= QPS x n_gpus)",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "exact top-10, 1M x 768 fp32 corpus per GPU, batch-1 queries (BASELINE configs[1])",
+            "config": {"workload": WORKLOAD,
                        "rows_per_gpu": rows, "corpus_rows": rows * world, "dim": D, "k": K, "qps": qps,
                        "path": "two-phase exact scan (bf16 shadow sweep + proven fp32 re-score)" if two_phase else "fp32 sweep",
                        "l2": "corpus (3.07 GB) >> 126 MB L2, no flush needed",
