@@ -43,8 +43,10 @@ class StandInTokenizer:
 
 
 class WordPieceTokenizer:
-    """BERT-style basic + WordPiece tokenisation over vocab.txt (what MPNetTokenizer does:
-    lower-case, strip accents, split punctuation, greedy longest-match with '##')."""
+    """Plain-Python BERT-style basic + WordPiece tokenisation over vocab.txt (lower-case, strip accents, split
+    punctuation and the main CJK block, greedy longest-match with '##').  Readable cross-check of the native
+    tokenizer on ordinary text (tests) and holder of the vocabulary; the product path is
+    NativeWordPieceTokenizer, which alone reproduces the reference's pipeline on all of Unicode."""
 
     def __init__(self, vocab_file: Union[str, Path], do_lower_case: bool = True):
         self.vocab: Dict[str, int] = {}
@@ -201,22 +203,12 @@ class NativeWordPieceTokenizer:
         self._native.check(self._lib.css_tokenizer_encode_batch(
             self._h, ctypes.cast(ptrs, ctypes.c_void_p), lens.ctypes.data, n, max_length, ids.ctypes.data,
             cu.ctypes.data, fb.ctypes.data, self.n_threads))
-        if not fb.any():
-            return ids[:cu[-1]], cu
-        # malformed UTF-8 (cannot come from a Python str): splice the Python tokenisation in
-        rows = np.flatnonzero(fb)
-        extra = self._py.encode_batch([texts[i] for i in rows], max_length)
-        pieces, new_cu, pos, prev = [], np.zeros(n + 1, np.int64), 0, 0
-        lengths = np.diff(cu).astype(np.int64)
-        for i, e in zip(rows, extra):
-            lengths[i] = len(e)
-        new_cu[1:] = np.cumsum(lengths)
-        out = np.empty(int(new_cu[-1]), np.int32)
-        fallback = dict(zip(rows.tolist(), extra))
-        for i in range(n):
-            a, b = int(new_cu[i]), int(new_cu[i + 1])
-            out[a:b] = fallback[i] if i in fallback else ids[cu[i]:cu[i + 1]]
-        return out, new_cu.astype(np.int32)
+        if fb.any():
+            # the library flags malformed UTF-8 only; str.encode cannot produce it (lone surrogates raise above,
+            # as they do in the reference's tokenizer): never answer with an approximation
+            bad = int(np.flatnonzero(fb)[0])
+            raise UnicodeError(f"text {bad} is not valid UTF-8")
+        return ids[:cu[-1]], cu
 
     def encode_batch(self, texts: Sequence[str], max_length: int) -> List[List[int]]:
         ids, cu = self.encode_packed(texts, max_length)

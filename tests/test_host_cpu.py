@@ -178,6 +178,19 @@ def test_native_tokenizer_equals_fast_pipeline_on_all_of_unicode(tmp_path):
         assert isinstance(tk, NativeWordPieceTokenizer)
         assert tk.encode_batch(["Héllo <mask> wörld"], 16) == [ref.encode("Héllo <mask> wörld").ids]
         tk.close()
+    # malformed UTF-8 (overlong, lone continuation, surrogate, truncated, > U+10FFFF) is flagged by the library, never tokenised
+    import ctypes
+    nat = NativeWordPieceTokenizer(vf, n_threads=1)
+    raws = [b"ok text", b"bad \xc0\xaf", b"\x80lone", b"sur \xed\xa0\x80", b"cut \xe2\x82", b"big \xf4\x90\x80\x80", "fine é 日本".encode()]
+    n = len(raws)
+    ptrs = (ctypes.c_char_p * n)(*raws)
+    lens = np.asarray([len(b) for b in raws], np.int64)
+    ids, cu, fb = np.empty(n * 16, np.int32), np.zeros(n + 1, np.int32), np.zeros(n, np.uint8)
+    assert nat._lib.css_tokenizer_encode_batch(nat._h, ctypes.cast(ptrs, ctypes.c_void_p), lens.ctypes.data, n, 16,
+                                               ids.ctypes.data, cu.ctypes.data, fb.ctypes.data, 1) == 0
+    assert fb.tolist() == [0, 1, 1, 1, 1, 1, 0]
+    assert [int(cu[i + 1] - cu[i]) for i in (1, 2, 3, 4, 5)] == [0] * 5 and cu[1] - cu[0] >= 2
+    nat.close()
     # a different pipeline (no CJK padding) must NOT be taken over by the native tokenizer
     import json
     cfg = json.loads((tmp_path / "ckpt_1" / "tokenizer.json").read_text(encoding="utf-8"))
