@@ -329,27 +329,47 @@ class HybridStorage:
             pairs = [(int(i), float(d)) for d, i in zip(D[0], I[0])
                      if i >= 0 and float(d) >= cfg.similarity_threshold]
 
-        results: List[SearchResult] = []
+        # one SELECT for all hits, only the columns the result needs (the reference issues SELECT * per hit,
+        # src/storage.py:452-470: ten round trips and ten 14-column dicts per query cost as much host time as the
+        # whole device search)
+        hits = []
         for fid, sim in pairs:
             cid = self.faiss_id_to_chunk_id.get(fid)
-            if not cid:
+            if cid:
+                hits.append((cid, sim))
+        rows = self._get_chunk_rows([cid for cid, _ in hits], cfg.include_text, cfg.include_metadata)
+        results: List[SearchResult] = []
+        for cid, sim in hits:
+            data = rows.get(cid)
+            if data is None:
                 continue
-            data = self._get_chunk_data(cid)
-            if not data:
-                continue
+            text, meta = data
             res = SearchResult(chunk_id=cid, similarity=sim)
             md = None
             if cfg.include_metadata:
-                md = json.loads(data["metadata"]) if data["metadata"] else {}
+                md = json.loads(meta) if meta else {}
                 res.metadata = md
             if cfg.include_text:
-                res.text = data["text"]
+                res.text = text
             if cfg.include_metadata and cfg.include_text:
-                res.chunk = Chunk(id=cid, text=data["text"], metadata=md, embedding=None)
+                res.chunk = Chunk(id=cid, text=text, metadata=md, embedding=None)
             results.append(res)
             if len(results) >= cfg.top_k:
                 break
         return results
+
+    def _get_chunk_rows(self, chunk_ids: List[str], want_text: bool, want_metadata: bool) -> Dict[str, tuple]:
+        """{chunk id: (text | None, metadata JSON | None)} of the ids that still exist, in one query."""
+        if not self.db:
+            raise RuntimeError("Database not initialized")
+        out: Dict[str, tuple] = {}
+        cols = "id, " + ("text" if want_text else "NULL") + ", " + ("metadata" if want_metadata else "NULL")
+        for s0 in range(0, len(chunk_ids), 500):   # stay below SQLite's bound-variable limit
+            part = chunk_ids[s0:s0 + 500]
+            q = f"SELECT {cols} FROM chunks WHERE id IN ({','.join('?' * len(part))})"
+            for r in self.db.execute(q, part):
+                out[r[0]] = (r[1], r[2])
+        return out
 
     def _search_reference_mode(self, native, q, k_ref, cfg, filters):
         """R = (global top-k' incl. orphans) walked best-first with threshold, orphan and
