@@ -30,6 +30,9 @@ METRIC_L2 = 1
 MAX_K = 128
 MAX_COLUMNS = 12
 MAX_CLAUSES = 16
+MAX_RANKS = 8
+IPC_HANDLE_BYTES = 64
+EXCHANGE_MAX_NQ = 64
 NULL_VALUE = -(2 ** 31)
 CLAUSE_RANGE = 0
 CLAUSE_SET = 1
@@ -92,6 +95,15 @@ SIGNATURES = {
     "css_device_count": (c_int, [POINTER(c_int)]),
     "css_device_info": (c_int, [c_int, POINTER(c_int64)]),
     "css_index_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p)]),
+    "css_index_create_sharded": (c_int, [c_int, c_int, POINTER(c_int), c_int, POINTER(c_void_p)]),
+    "css_index_n_devices": (c_int, [c_void_p]),
+    "css_index_set_alive_ids": (c_int, [c_void_p, c_void_p, c_int64, c_int]),
+    "css_index_scan_stats": (c_int, [c_void_p, POINTER(c_int64)]),
+    "css_exchange_create": (c_int, [c_int, c_int, c_int, POINTER(c_void_p), c_void_p]),
+    "css_exchange_connect": (c_int, [c_void_p, c_void_p]),
+    "css_exchange_destroy": (c_int, [c_void_p]),
+    "css_index_search_exchange_device": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64,
+                                                 c_void_p, c_void_p, c_void_p]),
     "css_index_destroy": (c_int, [c_void_p]),
     "css_index_dim": (c_int, [c_void_p]),
     "css_index_metric": (c_int, [c_void_p]),
@@ -254,16 +266,57 @@ class Filter:
         return f
 
 
-class Index:
-    """Thin OO wrapper over the css_index_* entry points."""
+class Exchange:
+    """css_exchange: the in-kernel result exchange between the row shards of one search
+    (one per rank / GPU).  `handle` is the 64-byte CUDA IPC handle the ranks all-gather."""
 
-    def __init__(self, dim: int, metric: int = METRIC_INNER_PRODUCT, device: int = 0):
+    def __init__(self, device: int, n_ranks: int, rank: int):
         self._lib = load()
         self._h = c_void_p()
-        check(self._lib.css_index_create(dim, metric, device, ctypes.byref(self._h)))
+        buf = (ctypes.c_ubyte * IPC_HANDLE_BYTES)()
+        check(self._lib.css_exchange_create(device, n_ranks, rank, ctypes.byref(self._h), buf))
+        self.handle = bytes(buf)
+        self.n_ranks = n_ranks
+        self.rank = rank
+        self.device = device
+
+    def connect(self, handles) -> None:
+        """handles: the n_ranks IPC handles in rank order (bytes each)."""
+        blob = b"".join(handles)
+        if len(blob) != self.n_ranks * IPC_HANDLE_BYTES:
+            raise ValueError("expected n_ranks handles of 64 bytes")
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        check(self._lib.css_exchange_connect(self._h, buf))
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.css_exchange_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Index:
+    """Thin OO wrapper over the css_index_* entry points.  `devices` (a list of device ordinals)
+    builds ONE index row-sharded over several GPUs of this process (css_index_create_sharded)."""
+
+    def __init__(self, dim: int, metric: int = METRIC_INNER_PRODUCT, device: int = 0, devices=None):
+        self._lib = load()
+        self._h = c_void_p()
+        if devices is not None and len(devices) > 0:
+            devs = (c_int * len(devices))(*[int(d) for d in devices])
+            check(self._lib.css_index_create_sharded(dim, metric, devs, len(devices), ctypes.byref(self._h)))
+            device = int(devices[0])
+        else:
+            check(self._lib.css_index_create(dim, metric, device, ctypes.byref(self._h)))
         self.dim = dim
         self.metric = metric
         self.device = device
+        self.devices = [int(d) for d in devices] if devices else [device]
 
     # -- lifecycle --------------------------------------------------------
     def close(self) -> None:
@@ -329,6 +382,17 @@ class Index:
         a = np.ascontiguousarray(alive, dtype=np.uint8)
         check(self._lib.css_index_set_alive(self._h, a.ctypes.data, start, a.shape[0]))
 
+    def set_alive_ids(self, ids, alive: bool) -> None:
+        """Mark the listed rows alive / dead in one device call."""
+        a = np.ascontiguousarray(ids, dtype=np.int64)
+        check(self._lib.css_index_set_alive_ids(self._h, a.ctypes.data, a.shape[0], 1 if alive else 0))
+
+    def scan_stats(self) -> dict:
+        out = (c_int64 * 4)()
+        check(self._lib.css_index_scan_stats(self._h, out))
+        return {"two_phase_queries": int(out[0]), "unproven_queries": int(out[1]), "bypassed": bool(out[2]),
+                "max_bf16_error_norm": out[3] * 1e-9}
+
     # -- filter / search ----------------------------------------------------
     def filter_mask(self, flt: Optional[Filter]) -> tuple:
         n = self.ntotal
@@ -346,12 +410,41 @@ class Index:
         if q.shape[1] != self.dim:
             raise ValueError(f"expected [nq, {self.dim}] float32, got {q.shape}")
         nq = q.shape[0]
+        if k > MAX_K:
+            return self._search_large_k(q, k, flt)
         D = np.empty((nq, k), np.float32)
         I = np.empty((nq, k), np.int64)
         cf = flt.build() if flt is not None else None
         check(self._lib.css_index_search(self._h, q.ctypes.data, nq, k,
                                          ctypes.byref(cf) if cf is not None else None,
                                          D.ctypes.data, I.ctypes.data))
+        return D, I
+
+    def _search_large_k(self, q: np.ndarray, k: int, flt: Optional[Filter]) -> tuple:
+        """k > CSS_MAX_K (the reference's max_results is a free field, src/storage.py:69,432): the exact
+        top-k is the top-128, then the top-128 of the remaining rows, ... -- each pass is one exact device
+        search with the rows found so far cleared from the row mask."""
+        nq = q.shape[0]
+        fill = -np.finfo(np.float32).max if self.metric == METRIC_INNER_PRODUCT else np.finfo(np.float32).max
+        D = np.full((nq, k), fill, np.float32)
+        I = np.full((nq, k), -1, np.int64)
+        base, _ = self.filter_mask(flt)          # honours the alive bits unless flt.ignore_alive
+        for qi in range(nq):
+            words = base.copy()
+            got = 0
+            while got < k:
+                kk = min(MAX_K, k - got)
+                f = Filter(ignore_alive=True).set_row_mask(words)
+                d, i = self.search(q[qi:qi + 1], kk, f)
+                ok = i[0] >= 0
+                n = int(ok.sum())
+                D[qi, got:got + n] = d[0][ok]
+                I[qi, got:got + n] = i[0][ok]
+                got += n
+                if n < kk:
+                    break
+                ids = i[0][ok]
+                np.bitwise_and.at(words, ids >> 5, ~(np.uint32(1) << (ids & 31).astype(np.uint32)))
         return D, I
 
     def filter_mask_device(self, flt: Optional[Filter], stream: int = 0, want_count: bool = False):
@@ -368,6 +461,14 @@ class Index:
         check(self._lib.css_index_search_device(self._h, c_void_p(q_ptr), nq, k,
                                                 c_void_p(mask_ptr) if mask_ptr else None, id_offset,
                                                 c_void_p(D_ptr), c_void_p(I_ptr), c_void_p(stream)))
+
+    def search_exchange_device(self, ex: Exchange, q_ptr: int, nq: int, k: int, D_ptr: int, I_ptr: int,
+                               mask_ptr: int = 0, id_offset: int = 0, stream: int = 0) -> None:
+        """Collective over the ranks of `ex`: local scan + in-kernel NVLink exchange + merge; D/I hold
+        the merged global top-k on every rank when the stream reaches this point."""
+        check(self._lib.css_index_search_exchange_device(self._h, ex._h, c_void_p(q_ptr), nq, k,
+                                                         c_void_p(mask_ptr) if mask_ptr else None, id_offset,
+                                                         c_void_p(D_ptr), c_void_p(I_ptr), c_void_p(stream)))
 
     def debug_scan_bf16(self, q_ptr: int, nq: int, stream: int = 0) -> None:
         """Phase 1 alone of the two-phase scan (benchmark hook, css_debug_scan_bf16)."""

@@ -1,7 +1,9 @@
-// index.cu -- host side of the flat index C ABI (see include/css_b200.h).
+// index.cu -- host side of the flat index C ABI (see include/css_b200.h): one single-device shard.
+// The multi-device composite lives in index_sharded.cu, the result exchange in exchange.cu.
 #include "index_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 using namespace css;
@@ -23,58 +25,56 @@ int dev_alloc(T** p, size_t count) {
 
 inline int64_t words_for(int64_t rows) { return (rows + 31) / 32; }
 
-// Grow every per-row array to `new_cap` rows, preserving contents.
+int vmm_status(int rc) { return rc == 0 ? CSS_OK : (rc == -4 ? CSS_ERR_OOM : CSS_ERR_CUDA); }
+
+// Largest row count the virtual ranges are sized for: what fits the device's HBM as fp32 rows.
+int64_t max_rows_for(const css_index* h) {
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) total_b = (size_t)192 << 30;
+  int64_t rows = (int64_t)(total_b / ((size_t)h->dim * 4));
+  rows = std::min<int64_t>(rows, ((int64_t)1 << 31) - 64);
+  return std::max<int64_t>(rows, 1024) / 32 * 32;
+}
+
+int reserve_ranges(css_index* h) {
+  if (h->vx.base) return CSS_OK;
+  const int64_t mr = max_rows_for(h);
+  const size_t d = (size_t)h->dim;
+  CSS_CHECK(vmm_status(vmm_reserve(&h->vx, h->device, (size_t)mr * d * 4)));
+  CSS_CHECK(vmm_status(vmm_reserve(&h->vxb, h->device, (size_t)mr * d * 2)));
+  CSS_CHECK(vmm_status(vmm_reserve(&h->valive, h->device, (size_t)words_for(mr) * 4)));
+  CSS_CHECK(vmm_status(vmm_reserve(&h->vmask, h->device, (size_t)words_for(mr) * 4)));
+  h->x = reinterpret_cast<float*>(h->vx.ptr());
+  h->xb = reinterpret_cast<__nv_bfloat16*>(h->vxb.ptr());
+  h->alive = reinterpret_cast<uint32_t*>(h->valive.ptr());
+  h->mask = reinterpret_cast<uint32_t*>(h->vmask.ptr());
+  return CSS_OK;
+}
+
+// Grow every per-row array to `new_cap` rows: more physical memory is mapped behind the same
+// addresses (vmm.h); existing rows are not touched, nothing is copied.
 int grow(css_index* h, int64_t new_cap) {
   if (new_cap <= h->capacity) return CSS_OK;
-  // keep row-bitmask words whole and rows a multiple of 32
-  new_cap = (new_cap + 31) / 32 * 32;
+  new_cap = (new_cap + 31) / 32 * 32;   // keep row-bitmask words whole
+  CSS_CHECK(reserve_ranges(h));
   const size_t d = (size_t)h->dim;
-  float* nx = nullptr;
-  __nv_bfloat16* nxb = nullptr;
-  uint32_t *nalive = nullptr, *nmask = nullptr;
-  CSS_CHECK(dev_alloc(&nx, (size_t)new_cap * d));
-  if (dev_alloc(&nxb, (size_t)new_cap * d) != CSS_OK) {
-    cudaFree(nx);
-    return CSS_ERR_OOM;
-  }
-  if (dev_alloc(&nalive, (size_t)words_for(new_cap)) != CSS_OK ||
-      dev_alloc(&nmask, (size_t)words_for(new_cap)) != CSS_OK) {
-    cudaFree(nx);
-    cudaFree(nxb);
-    cudaFree(nalive);
-    return CSS_ERR_OOM;
-  }
+  const int64_t old_cap = h->capacity;
+  CSS_CHECK(vmm_status(vmm_grow(&h->vx, (size_t)new_cap * d * 4)));
+  CSS_CHECK(vmm_status(vmm_grow(&h->vxb, (size_t)new_cap * d * 2)));
+  CSS_CHECK(vmm_status(vmm_grow(&h->valive, (size_t)words_for(new_cap) * 4)));
+  CSS_CHECK(vmm_status(vmm_grow(&h->vmask, (size_t)words_for(new_cap) * 4)));
   cudaStream_t st = h->stream;
-  CSS_CUDA(cudaMemsetAsync(nalive, 0, (size_t)words_for(new_cap) * 4, st));
-  CSS_CUDA(cudaMemsetAsync(nmask, 0, (size_t)words_for(new_cap) * 4, st));
-  if (h->ntotal > 0) {
-    CSS_CUDA(cudaMemcpyAsync(nx, h->x, (size_t)h->ntotal * d * 4, cudaMemcpyDeviceToDevice, st));
-    CSS_CUDA(cudaMemcpyAsync(nxb, h->xb, (size_t)h->ntotal * d * 2, cudaMemcpyDeviceToDevice, st));
-    CSS_CUDA(cudaMemcpyAsync(nalive, h->alive, (size_t)words_for(h->ntotal) * 4,
-                             cudaMemcpyDeviceToDevice, st));
-  }
+  const int64_t w0 = words_for(old_cap), w1 = words_for(new_cap);
+  CSS_CUDA(cudaMemsetAsync(h->alive + w0, 0, (size_t)(w1 - w0) * 4, st));
+  CSS_CUDA(cudaMemsetAsync(h->mask + w0, 0, (size_t)(w1 - w0) * 4, st));
   for (int c = 0; c < CSS_MAX_COLUMNS; ++c) {
     if (!h->cols[c]) continue;
-    int32_t* nc = nullptr;
-    CSS_CHECK(dev_alloc(&nc, (size_t)new_cap));
-    int64_t blocks = (new_cap + 255) / 256;
-    fill_i32_kernel<<<(unsigned)blocks, 256, 0, st>>>(nc, new_cap, CSS_NULL_VALUE);
+    CSS_CHECK(vmm_status(vmm_grow(&h->vcols[c], (size_t)new_cap * 4)));
+    const int64_t n = new_cap - old_cap;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cols[c] + old_cap, n, CSS_NULL_VALUE);
     CSS_LAUNCHED();
-    if (h->ntotal > 0)
-      CSS_CUDA(cudaMemcpyAsync(nc, h->cols[c], (size_t)h->ntotal * 4, cudaMemcpyDeviceToDevice, st));
-    CSS_CUDA(cudaStreamSynchronize(st));
-    cudaFree(h->cols[c]);
-    h->cols[c] = nc;
   }
   CSS_CUDA(cudaStreamSynchronize(st));
-  cudaFree(h->x);
-  cudaFree(h->xb);
-  cudaFree(h->alive);
-  cudaFree(h->mask);
-  h->x = nx;
-  h->xb = nxb;
-  h->alive = nalive;
-  h->mask = nmask;
   h->capacity = new_cap;
   return CSS_OK;
 }
@@ -82,25 +82,49 @@ int grow(css_index* h, int64_t new_cap) {
 int ensure_room(css_index* h, int64_t extra) {
   int64_t need = h->ntotal + extra;
   if (need <= h->capacity) return CSS_OK;
-  int64_t cap = std::max<int64_t>(need, std::max<int64_t>(1024, h->capacity + h->capacity / 2));
+  // geometric growth bounds the number of mappings; it costs no copy and no transient memory
+  int64_t cap = std::max<int64_t>(need, std::max<int64_t>(1024, h->capacity + h->capacity / 4));
   return grow(h, cap);
 }
 
-// Rows [ntotal, ntotal+n) were produced in `src_dev`; normalise/copy + bookkeeping.
-int append_from_device(css_index* h, const float* src_dev, int64_t n, int normalize,
-                       cudaStream_t st) {
+int ensure_column(css_index* h, int column) {
+  if (h->cols[column]) return CSS_OK;
+  CSS_CHECK(reserve_ranges(h));
+  CSS_CHECK(vmm_status(vmm_reserve(&h->vcols[column], h->device, (size_t)(h->vmask.reserved / 4 * 32) * 4)));
+  if (h->capacity > 0) {
+    CSS_CHECK(vmm_status(vmm_grow(&h->vcols[column], (size_t)h->capacity * 4)));
+    int32_t* c = reinterpret_cast<int32_t*>(h->vcols[column].ptr());
+    fill_i32_kernel<<<(unsigned)((h->capacity + 255) / 256), 256, 0, h->stream>>>(c, h->capacity, CSS_NULL_VALUE);
+    CSS_LAUNCHED();
+  }
+  h->cols[column] = reinterpret_cast<int32_t*>(h->vcols[column].ptr());
+  return CSS_OK;
+}
+
+// Rows [row0, row0+n) of x hold (or, with src != their place, receive) new data: normalise / copy,
+// bf16 shadow, norm and rounding-error maxima.
+int finish_rows(css_index* h, const float* src_dev, int64_t row0, int64_t n, int normalize, cudaStream_t st) {
   const int warps_per_block = 8;
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
-  const size_t off = (size_t)h->ntotal * h->dim;
+  const size_t off = (size_t)row0 * h->dim;
   append_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(
-      src_dev, n, h->dim, normalize, h->x + off, h->xb + off, h->max_norm_dev);
-  CSS_LAUNCHED();
-  // new rows are alive
-  int64_t w0 = h->ntotal >> 5, w1 = (h->ntotal + n - 1) >> 5;
-  int64_t nw = w1 - w0 + 1;
-  set_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(h->alive, h->ntotal, n, 1);
+      src_dev, n, h->dim, normalize, h->x + off, h->xb + off, h->max_norm_dev, h->max_err_dev);
   CSS_LAUNCHED();
   return CSS_OK;
+}
+
+int mark_alive(css_index* h, int64_t row0, int64_t n, cudaStream_t st) {
+  int64_t w0 = row0 >> 5, w1 = (row0 + n - 1) >> 5;
+  int64_t nw = w1 - w0 + 1;
+  set_bits_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(h->alive, row0, n, 1);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+// Rows [ntotal, ntotal+n) were produced in `src_dev`; normalise/copy + bookkeeping.
+int append_from_device(css_index* h, const float* src_dev, int64_t n, int normalize, cudaStream_t st) {
+  CSS_CHECK(finish_rows(h, src_dev, h->ntotal, n, normalize, st));
+  return mark_alive(h, h->ntotal, n, st);
 }
 
 template <int KPL, int METRIC>
@@ -126,6 +150,11 @@ int launch_scan_m(css_index* h, const ScanParams& p, int nq, cudaStream_t st) {
   if (p.k <= 32) return launch_scan_kd<1, METRIC>(h, p, nq, st);
   if (p.k <= 64) return launch_scan_kd<2, METRIC>(h, p, nq, st);
   return launch_scan_kd<4, METRIC>(h, p, nq, st);
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 // Compile a host css_filter into device FilterParams (uploads bitsets / row mask).
@@ -205,10 +234,18 @@ int build_filter_params(css_index* h, const css_filter* f, FilterParams* fp, cud
   return CSS_OK;
 }
 
-// Evaluate `f` into h->mask.  *mask_out = nullptr when every row passes trivially.
+}  // namespace
+
+namespace css {
+
+// Evaluate `f` into h->mask.  *mask_out = nullptr when every row passes trivially; *ignore_alive_out
+// tells the caller that the alive bits must NOT be substituted for a null mask (css_filter.ignore_alive:
+// HybridStorage's reference mode wants the orphans in its global top-100 window).
 int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, int64_t* n_pass,
-                bool need_count, cudaStream_t st) {
-  const bool trivial = (!f || (f->n_clauses == 0 && !f->row_mask)) && (!h->any_dead || (f && f->ignore_alive));
+                bool need_count, cudaStream_t st, bool* ignore_alive_out) {
+  const bool ignore_alive = f && f->ignore_alive;
+  if (ignore_alive_out) *ignore_alive_out = ignore_alive;
+  const bool trivial = (!f || (f->n_clauses == 0 && !f->row_mask)) && (!h->any_dead || ignore_alive);
   if (trivial && !need_count) {
     *mask_out = nullptr;
     if (n_pass) *n_pass = h->ntotal;
@@ -235,10 +272,6 @@ int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, in
   return CSS_OK;
 }
 
-}  // namespace
-
-namespace css {
-
 int ensure_pinned(css_index* h, size_t bytes) {
   if (bytes <= h->pinned_bytes) return CSS_OK;
   if (h->pinned) {
@@ -258,132 +291,165 @@ int ensure_pinned(css_index* h, size_t bytes) {
   return CSS_OK;
 }
 
-int ensure_query_scratch(css_index* h, int nq) {
-  if (nq <= h->max_nq) return CSS_OK;
-  int want = std::max(nq, std::max(16, h->max_nq * 2));
-  cudaFree(h->q_dev);
-  cudaFree(h->part);
-  cudaFree(h->ticket);
-  cudaFree(h->D_dev);
-  cudaFree(h->ovf_list);
-  cudaFree(h->ovf_count);
-  h->q_dev = nullptr; h->part = nullptr; h->ticket = nullptr; h->D_dev = nullptr;
-  h->ovf_list = nullptr; h->ovf_count = nullptr;
-  h->max_nq = 0;
-  CSS_CHECK(dev_alloc(&h->q_dev, (size_t)want * h->dim));
-  CSS_CHECK(dev_alloc(&h->part, (size_t)want * h->scan_blocks * CSS_MAX_K));
-  CSS_CHECK(dev_alloc(&h->ticket, (size_t)want));
-  CSS_CHECK(dev_alloc(&h->D_dev, (size_t)want * CSS_MAX_K * 3 + 8));   // scores, then the ids of the same call (one D2H)
-  CSS_CHECK(dev_alloc(&h->ovf_list, (size_t)want));
-  CSS_CHECK(dev_alloc(&h->ovf_count, (size_t)1));
-  CSS_CUDA(cudaMemsetAsync(h->ticket, 0, (size_t)want * sizeof(unsigned int), h->stream));
-  CSS_CUDA(cudaStreamSynchronize(h->stream));
-  h->max_nq = want;
+static void free_scratch(css_scan_scratch* sc) {
+  batched_release(sc);
+  cudaFree(sc->q_dev);
+  cudaFree(sc->part);
+  cudaFree(sc->ticket);
+  cudaFree(sc->D_dev);
+  cudaFree(sc->ovf_list);
+  *sc = css_scan_scratch();
+}
+
+// Scratch of the searches issued on stream `st` (created on first use, grown geometrically).
+int get_scratch(css_index* h, cudaStream_t st, int nq, css_scan_scratch** out) {
+  css_scan_scratch& sc = h->scratch[st];
+  *out = &sc;
+  if (nq <= sc.max_nq) return CSS_OK;
+  const int want = std::max(nq, std::max(16, sc.max_nq * 2));
+  if (sc.max_nq > 0) CSS_CUDA(cudaStreamSynchronize(st));   // work in flight may still use the old buffers
+  void* keep_batched = sc.batched;
+  sc.batched = nullptr;
+  free_scratch(&sc);
+  sc.batched = keep_batched;
+  CSS_CHECK(dev_alloc(&sc.q_dev, (size_t)want * h->dim));
+  CSS_CHECK(dev_alloc(&sc.part, (size_t)want * h->scan_blocks * CSS_MAX_K));
+  CSS_CHECK(dev_alloc(&sc.ticket, (size_t)want));
+  // scores, then the ids of the same call, then the overflow count: one D2H returns all three
+  CSS_CHECK(dev_alloc(&sc.D_dev, (size_t)want * CSS_MAX_K * 3 + 16));
+  sc.ovf_count = reinterpret_cast<int*>(sc.D_dev + (size_t)want * CSS_MAX_K * 3 + 8);
+  CSS_CHECK(dev_alloc(&sc.ovf_list, (size_t)want));
+  CSS_CUDA(cudaMemsetAsync(sc.ticket, 0, (size_t)want * sizeof(unsigned int), st));
+  CSS_CUDA(cudaMemsetAsync(sc.ovf_count, 0, sizeof(int), st));
+  sc.max_nq = want;
   return CSS_OK;
+}
+
+IdMap index_idmap(const css_index* h, int64_t id_offset) {
+  IdMap m;
+  m.offset = id_offset;
+  m.shift = h->id_shift;
+  m.ndev = h->id_ndev;
+  m.shard = h->id_shard;
+  return m;
+}
+
+static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const float* q_dev, const uint32_t* mask_dev,
+                        const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev) {
+  memset(p, 0, sizeof(*p));
+  p->x = h->x;
+  p->n = h->ntotal;
+  p->d = h->dim;
+  p->q = q_dev;
+  p->mask = mask_dev;
+  p->part = sc->part;
+  p->ticket = sc->ticket;
+  p->idmap = idmap;
+  p->D = D_dev;
+  p->I = I_dev;
+  p->max_norm = h->max_norm_dev;
+  p->max_err = h->max_err_dev;
+  p->ovf_list = sc->ovf_list;
+  p->ovf_count = sc->ovf_count;
+  p->stats_dev = h->stats_dev;
+  p->stats_host = h->stats_host_devptr;
+  if (ex) p->ex = *ex;
 }
 
 // Two-phase exact scan (inner product, d = 768, k <= 32, with or without a row mask): phase 1 streams the bf16 shadow
-// rows -- half the bytes of the fp32 corpus -- and leaves the 32 best of every scan block's slice by that
-// score; phase 2 (rescore768_kernel) proves that the true top-k lies inside those lists, re-scores the
-// candidates in fp32 with the arithmetic of the fp32 scan and emits the exact result; queries it cannot
-// prove are re-run by the fp32 scan on the device (qlist), so the answer is always the exact one.
-// CSS_SCAN_BF16=0 disables it.
-int launch_phase1(css_index* h, const float* q_dev, int nq, const uint32_t* mask_dev, ScanParams* out, cudaStream_t st) {
+// rows -- half the bytes of the fp32 corpus -- and leaves the best rows of every scan block by that score; the
+// last CTA to finish (two_phase_finish) proves that the true top-k lies inside those lists, re-scores the
+// candidates in fp32 with the arithmetic of the fp32 scan and emits the exact result -- one launch; queries it
+// cannot prove are queued on the device and re-run by the fp32 scan (scan_fallback), so the answer is always
+// the exact one.  CSS_SCAN_BF16=0 disables it; CSS_SCAN_LIST=32|64 fixes the per-block list length (default 32
+// for k <= 16, 64 above); CSS_SCAN_INTERLEAVE=0 walks contiguous row ranges per warp instead of dealing 8-row
+// units block-cyclically.
+static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
+                         const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, int no_merge,
+                         cudaStream_t st) {
+  static const int list_env = env_int("CSS_SCAN_LIST", 0);
+  static const int interleave = env_int("CSS_SCAN_INTERLEAVE", 1);
+  const int kp = list_env == 32 || list_env == 64 ? list_env : (k <= 16 ? 32 : 64);
   ScanParams p;
-  p.x = h->x;
+  fill_common(h, sc, &p, q_dev, mask_dev, idmap, ex, D_dev, I_dev);
   p.xb = h->xb;
-  p.n = h->ntotal;
-  p.d = h->dim;
-  p.q = q_dev;
-  p.mask = mask_dev;   // nullable: filter / alive bits (the selected rows of a window are compacted first)
-  p.k = kTwoPhaseMaxK;
-  p.part = h->part;
-  p.ticket = h->ticket;
-  p.id_offset = 0;
-  p.D = nullptr;
-  p.I = nullptr;
-  p.qlist = nullptr;
-  p.qcount = nullptr;
-  p.no_merge = 1;
-  p.zero_on_entry = h->ovf_count;
+  p.k = kp;
+  p.k_out = k;
+  p.no_merge = no_merge;
+  p.interleave = interleave;
+  p.zero_on_entry = sc->ovf_count;
   const size_t smem = sizeof(KeyId) * kMergeCap;
-  auto kern = scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>;
-  CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<dim3((unsigned)h->scan_blocks, (unsigned)nq), kScanThreads, smem, st>>>(p);
-  CSS_LAUNCHED();
-  if (out) *out = p;
-  return CSS_OK;
-}
-
-int two_phase_scan(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev, int64_t id_offset,
-                   float* D_dev, int64_t* I_dev, cudaStream_t st) {
-  const int kp = kTwoPhaseMaxK;
-  ScanParams p;
-  CSS_CHECK(launch_phase1(h, q_dev, nq, mask_dev, &p, st));
-  RescoreParams r;
-  r.x = h->x;
-  r.q = q_dev;
-  r.k = k;
-  r.kp = kp;
-  r.blocks = h->scan_blocks;
-  r.eps_scale = 1.10f / 512.f;
-  r.max_norm = h->max_norm_dev;
-  r.part = h->part;
-  r.id_offset = id_offset;
-  r.D = D_dev;
-  r.I = I_dev;
-  r.ovf_list = h->ovf_list;
-  r.ovf_count = h->ovf_count;
-  {
-    const size_t smem = sizeof(KeyId) * kRescoreSort;
-    CSS_CUDA(cudaFuncSetAttribute(rescore768_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rescore768_kernel<<<(unsigned)nq, kRescoreThreads, smem, st>>>(r);
-    CSS_LAUNCHED();
+  const dim3 grid((unsigned)h->scan_blocks, (unsigned)nq);
+  if (kp == 32) {
+    auto kern = scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>;
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanThreads, smem, st>>>(p);
+  } else {
+    auto kern = scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, true>;
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kScanThreads, smem, st>>>(p);
   }
-  // unproven queries: fp32 scan, driven by the device-side list (an empty list costs one idle launch)
-  ScanParams f = p;
-  f.xb = nullptr;
-  f.k = k;
-  f.id_offset = id_offset;
-  f.D = D_dev;
-  f.I = I_dev;
-  f.qlist = h->ovf_list;
-  f.qcount = h->ovf_count;
-  f.no_merge = 0;
-  f.zero_on_entry = nullptr;
-  CSS_CHECK((launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, f, nq, st)));
+  CSS_LAUNCHED();
   return CSS_OK;
 }
 
-int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
-                int64_t id_offset, float* D_dev, int64_t* I_dev, cudaStream_t st) {
+int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
+                  const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st) {
+  ScanParams f;
+  fill_common(h, sc, &f, q_dev, mask_dev, idmap, ex, D_dev, I_dev);
+  f.k = k;
+  f.k_out = k;
+  f.qlist = sc->ovf_list;
+  f.qcount = sc->ovf_count;
+  // an empty list costs one idle launch; few slices: unproven queries are rare
+  return launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, f, std::min(nq, 8), st);
+}
+
+// Should this call try the two-phase scan?  The kernels mirror {queries, unproven} into mapped host memory;
+// when more than half of the recent queries could not be proven (a corpus whose rows sit within the bf16
+// rounding error of each other), phase 1 is wasted work and the next calls go straight to the fp32 sweep,
+// with a new probe every 4096 queries.  Exactness never depends on this choice.
+static bool two_phase_wanted(css_index* h, int nq) {
+  static const bool adaptive = env_int("CSS_SCAN_ADAPTIVE", 1) != 0;
+  if (!adaptive || !h->stats_host) return true;
+  if (h->skip_two_phase > 0) {
+    h->skip_two_phase -= nq;
+    return false;
+  }
+  const unsigned q = h->stats_host[0], u = h->stats_host[1];
+  if (q - h->seen_q >= 64u) {
+    const bool bad = (u - h->seen_u) * 2u > (q - h->seen_q);
+    h->seen_q = q;
+    h->seen_u = u;
+    if (bad) {
+      h->skip_two_phase = 4096;
+      return false;
+    }
+  }
+  return true;
+}
+
+int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
+                const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st,
+                bool defer_fallback, bool* two_phase_used) {
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
-  CSS_CHECK(ensure_query_scratch(h, nq));
-  static const bool bf16_phase = [] { const char* v = getenv("CSS_SCAN_BF16"); return v ? atoi(v) != 0 : true; }();
-  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK &&
-      nq <= 64 && h->xb != nullptr && h->ntotal > 0 && (int64_t)h->scan_blocks * kTwoPhaseMaxK <= kRescoreSort)
-    return two_phase_scan(h, q_dev, nq, k, mask_dev, id_offset, D_dev, I_dev, st);
+  if (two_phase_used) *two_phase_used = false;
+  static const bool bf16_phase = env_int("CSS_SCAN_BF16", 1) != 0;
+  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK && nq <= 64 &&
+      h->ntotal > 0 && two_phase_wanted(h, nq)) {
+    CSS_CHECK(launch_phase1(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, 0, st));
+    if (two_phase_used) *two_phase_used = true;
+    if (defer_fallback) return CSS_OK;   // the caller reads the overflow count with the result
+    return scan_fallback(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, st);
+  }
   // gridDim.y is limited to 65535; chunk the query batch
   const int chunk = 4096;
   for (int q0 = 0; q0 < nq; q0 += chunk) {
     int nqc = std::min(chunk, nq - q0);
     ScanParams p;
-    p.x = h->x;
-    p.xb = nullptr;
-    p.n = h->ntotal;
-    p.d = h->dim;
-    p.q = q_dev + (size_t)q0 * h->dim;
-    p.mask = mask_dev;
+    fill_common(h, sc, &p, q_dev + (size_t)q0 * h->dim, mask_dev, idmap, ex, D_dev + (size_t)q0 * k, I_dev + (size_t)q0 * k);
     p.k = k;
-    p.part = h->part;
-    p.ticket = h->ticket;
-    p.id_offset = id_offset;
-    p.D = D_dev + (size_t)q0 * k;
-    p.I = I_dev + (size_t)q0 * k;
-    p.qlist = nullptr;
-    p.qcount = nullptr;
-    p.no_merge = 0;
-    p.zero_on_entry = nullptr;
+    p.k_out = k;
     if (h->metric == CSS_METRIC_INNER_PRODUCT)
       CSS_CHECK((launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, p, nqc, st)));
     else
@@ -392,19 +458,17 @@ int scan_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t*
   return CSS_OK;
 }
 
-}  // namespace css
+// One search on device buffers, any nq: tensor-core path for batches, streaming scan otherwise.
+int search_on_device(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* m,
+                     const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st,
+                     bool defer_fallback, bool* two_phase_used) {
+  if (two_phase_used) *two_phase_used = false;
+  if (!ex && nq >= CSS_BATCH_MIN_NQ && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim % 64 == 0 && h->ntotal >= 65536)
+    return batched_search(h, sc, q_dev, nq, k, m, idmap, D_dev, I_dev, st);
+  return scan_search(h, sc, q_dev, nq, k, m, idmap, ex, D_dev, I_dev, st, defer_fallback, two_phase_used);
+}
 
-// ===========================================================================
-// C ABI
-// ===========================================================================
-extern "C" {
-
-int css_index_create(int dim, int metric, int device, css_index** out) {
-  CSS_REQUIRE(out != nullptr, "out is NULL");
-  *out = nullptr;
-  CSS_REQUIRE(dim >= 1 && dim <= 65536, "dim %d out of range", dim);
-  CSS_REQUIRE(metric == CSS_METRIC_INNER_PRODUCT || metric == CSS_METRIC_L2, "unknown metric %d",
-              metric);
+int index_create_single(int dim, int metric, int device, css_index** out) {
   CSS_CHECK(ensure_device(device));
   DeviceGuard g(device);
   css_index* h = new (std::nothrow) css_index();
@@ -423,65 +487,81 @@ int css_index_create(int dim, int metric, int device, css_index** out) {
     delete h;
     return CSS_ERR_CUDA;
   }
+  void* sh = nullptr;
   if (dev_alloc(&h->n_pass_dev, 1) != CSS_OK || dev_alloc(&h->max_norm_dev, 1) != CSS_OK ||
-      cudaMemset(h->max_norm_dev, 0, sizeof(float)) != cudaSuccess) {
+      dev_alloc(&h->max_err_dev, 1) != CSS_OK || dev_alloc(&h->stats_dev, 2) != CSS_OK ||
+      cudaMemset(h->max_norm_dev, 0, sizeof(float)) != cudaSuccess ||
+      cudaMemset(h->max_err_dev, 0, sizeof(float)) != cudaSuccess ||
+      cudaMemset(h->stats_dev, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
+      cudaHostAlloc(&sh, 2 * sizeof(unsigned), cudaHostAllocMapped) != cudaSuccess) {
+    (void)cudaGetLastError();
+    set_error("index bookkeeping allocation failed");
     cudaFree(h->n_pass_dev);
+    cudaFree(h->max_norm_dev);
+    cudaFree(h->max_err_dev);
+    cudaFree(h->stats_dev);
     cudaStreamDestroy(h->stream);
     delete h;
     return CSS_ERR_OOM;
   }
+  h->stats_host = reinterpret_cast<volatile unsigned*>(sh);
+  h->stats_host[0] = 0;
+  h->stats_host[1] = 0;
+  void* dp = nullptr;
+  if (cudaHostGetDevicePointer(&dp, sh, 0) == cudaSuccess) h->stats_host_devptr = reinterpret_cast<unsigned*>(dp);
+  else (void)cudaGetLastError();
   *out = h;
   return CSS_OK;
 }
 
-int css_index_destroy(css_index* h) {
-  if (!h) return CSS_OK;
-  {
-    DeviceGuard g(h->device);
-    cudaStreamSynchronize(h->stream);
-    batched_release(h);
-    cudaFree(h->x);
-    cudaFree(h->xb);
-    cudaFree(h->alive);
-    cudaFree(h->mask);
-    for (int c = 0; c < CSS_MAX_COLUMNS; ++c) cudaFree(h->cols[c]);
-    cudaFree(h->q_dev);
-    cudaFree(h->part);
-    cudaFree(h->ticket);
-    cudaFree(h->D_dev);
-    cudaFree(h->ovf_list);
-    cudaFree(h->ovf_count);
-    cudaFree(h->set_scratch);
-    cudaFree(h->rowmask_scratch);
-    cudaFree(h->n_pass_dev);
-    cudaFree(h->max_norm_dev);
-    if (h->pinned) cudaFreeHost(h->pinned);
-    cudaStreamDestroy(h->stream);
-  }
+void index_destroy_single(css_index* h) {
+  DeviceGuard g(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->scratch) free_scratch(&kv.second);
+  h->scratch.clear();
+  vmm_release(&h->vx);
+  vmm_release(&h->vxb);
+  vmm_release(&h->valive);
+  vmm_release(&h->vmask);
+  for (int c = 0; c < CSS_MAX_COLUMNS; ++c) vmm_release(&h->vcols[c]);
+  cudaFree(h->set_scratch);
+  cudaFree(h->rowmask_scratch);
+  cudaFree(h->n_pass_dev);
+  cudaFree(h->max_norm_dev);
+  cudaFree(h->max_err_dev);
+  cudaFree(h->stats_dev);
+  cudaFree(h->ids_scratch);
+  if (h->stats_host) cudaFreeHost(const_cast<unsigned*>(h->stats_host));
+  if (h->pinned) cudaFreeHost(h->pinned);
+  cudaStreamDestroy(h->stream);
   delete h;
+}
+
+// Overwrite / append rows [row0, row0+n) from HOST memory without a staging buffer: the bytes are
+// copied straight into x and finished in place (normalisation, bf16 shadow, maxima).  Asynchronous
+// on the handle's stream; the caller synchronises.  Rows beyond ntotal must fit the capacity.
+int put_rows_host_async(css_index* h, const float* x_host, int64_t row0, int64_t n, int normalize) {
+  float* dst = h->x + (size_t)row0 * h->dim;
+  CSS_CUDA(cudaMemcpyAsync(dst, x_host, (size_t)n * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
+  return finish_rows(h, dst, row0, n, normalize, h->stream);
+}
+
+int single_add(css_index* h, const float* x_host, int64_t n, int normalize, bool sync) {
+  CSS_REQUIRE(h->ntotal + n < ((int64_t)1 << 31) - 64, "index would exceed 2^31 rows per shard");
+  CSS_CHECK(ensure_room(h, n));
+  CSS_CHECK(put_rows_host_async(h, x_host, h->ntotal, n, normalize));
+  CSS_CHECK(mark_alive(h, h->ntotal, n, h->stream));
+  h->ntotal += n;
+  if (sync) CSS_CUDA(cudaStreamSynchronize(h->stream));
   return CSS_OK;
 }
 
-int css_index_dim(const css_index* h) { return h ? h->dim : CSS_ERR_INVALID; }
-int css_index_metric(const css_index* h) { return h ? h->metric : CSS_ERR_INVALID; }
-int64_t css_index_ntotal(const css_index* h) { return h ? h->ntotal : (int64_t)CSS_ERR_INVALID; }
-int64_t css_index_capacity(const css_index* h) { return h ? h->capacity : (int64_t)CSS_ERR_INVALID; }
-
-int css_index_reserve(css_index* h, int64_t capacity) {
-  CSS_REQUIRE(h != nullptr, "index is NULL");
-  CSS_REQUIRE(capacity >= 0 && capacity < ((int64_t)1 << 31), "capacity out of range");
-  std::lock_guard<std::mutex> lk(h->mu);
-  DeviceGuard g(h->device);
-  return grow(h, capacity);
-}
-
-int css_index_reset(css_index* h) {
-  CSS_REQUIRE(h != nullptr, "index is NULL");
-  std::lock_guard<std::mutex> lk(h->mu);
-  DeviceGuard g(h->device);
+int single_reset(css_index* h) {
   h->ntotal = 0;
   h->any_dead = false;
   CSS_CUDA(cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream));
+  CSS_CUDA(cudaMemsetAsync(h->max_err_dev, 0, sizeof(float), h->stream));
   if (h->capacity > 0) {
     CSS_CUDA(cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, h->stream));
     for (int c = 0; c < CSS_MAX_COLUMNS; ++c) {
@@ -490,22 +570,113 @@ int css_index_reset(css_index* h) {
       fill_i32_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->cols[c], h->capacity, CSS_NULL_VALUE);
       CSS_LAUNCHED();
     }
-    CSS_CUDA(cudaStreamSynchronize(h->stream));
   }
+  CSS_CUDA(cudaStreamSynchronize(h->stream));
   return CSS_OK;
+}
+
+int single_set_column(css_index* h, int column, const int32_t* values_host, int64_t start, int64_t n, bool sync) {
+  CSS_CHECK(ensure_column(h, column));
+  CSS_CUDA(cudaMemcpyAsync(h->cols[column] + start, values_host, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
+  if (sync) CSS_CUDA(cudaStreamSynchronize(h->stream));
+  return CSS_OK;
+}
+
+int single_set_alive_ids(css_index* h, const int64_t* ids_host, int64_t n, int alive) {
+  if (n == 0) return CSS_OK;
+  if (n > h->ids_scratch_n) {
+    cudaFree(h->ids_scratch);
+    h->ids_scratch_n = 0;
+    const int64_t want = std::max<int64_t>(n, 4096);
+    CSS_CHECK(dev_alloc(&h->ids_scratch, (size_t)want));
+    h->ids_scratch_n = want;
+  }
+  CSS_CUDA(cudaMemcpyAsync(h->ids_scratch, ids_host, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+  set_bits_by_id_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->alive, h->ids_scratch, n, h->ntotal,
+                                                                            alive ? 1 : 0);
+  CSS_LAUNCHED();
+  CSS_CUDA(cudaStreamSynchronize(h->stream));
+  if (!alive) h->any_dead = true;
+  return CSS_OK;
+}
+
+int single_grow(css_index* h, int64_t cap) { return grow(h, cap); }
+int single_ensure_room(css_index* h, int64_t extra) { return ensure_room(h, extra); }
+int single_mark_alive(css_index* h, int64_t row0, int64_t n) { return mark_alive(h, row0, n, h->stream); }
+
+}  // namespace css
+
+#define CSS_IS_COMPOSITE(h) (!(h)->shards.empty())
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int css_index_create(int dim, int metric, int device, css_index** out) {
+  CSS_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  CSS_REQUIRE(dim >= 1 && dim <= 65536, "dim %d out of range", dim);
+  CSS_REQUIRE(metric == CSS_METRIC_INNER_PRODUCT || metric == CSS_METRIC_L2, "unknown metric %d",
+              metric);
+  return index_create_single(dim, metric, device, out);
+}
+
+int css_index_destroy(css_index* h) {
+  if (!h) return CSS_OK;
+  if (CSS_IS_COMPOSITE(h)) return sharded_destroy(h);
+  index_destroy_single(h);
+  return CSS_OK;
+}
+
+int css_index_dim(const css_index* h) { return h ? h->dim : CSS_ERR_INVALID; }
+int css_index_metric(const css_index* h) { return h ? h->metric : CSS_ERR_INVALID; }
+int64_t css_index_ntotal(const css_index* h) {
+  if (!h) return (int64_t)CSS_ERR_INVALID;
+  return CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+}
+int64_t css_index_capacity(const css_index* h) {
+  if (!h) return (int64_t)CSS_ERR_INVALID;
+  if (!CSS_IS_COMPOSITE(h)) return h->capacity;
+  int64_t c = 0;
+  for (const css_index* s : h->shards) c += s->capacity;
+  return c;
+}
+int css_index_n_devices(const css_index* h) {
+  if (!h) return CSS_ERR_INVALID;
+  return CSS_IS_COMPOSITE(h) ? (int)h->shards.size() : 1;
+}
+
+int css_index_reserve(css_index* h, int64_t capacity) {
+  CSS_REQUIRE(h != nullptr, "index is NULL");
+  CSS_REQUIRE(capacity >= 0, "capacity out of range");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_reserve(h, capacity);
+  CSS_REQUIRE(capacity < ((int64_t)1 << 31) - 64, "capacity out of range (2^31 rows per shard)");
+  DeviceGuard g(h->device);
+  return grow(h, capacity);
+}
+
+int css_index_reset(css_index* h) {
+  CSS_REQUIRE(h != nullptr, "index is NULL");
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_reset(h);
+  DeviceGuard g(h->device);
+  return single_reset(h);
 }
 
 int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
   CSS_REQUIRE(n_keep >= 0 && (n_keep == 0 || keep_ids_host != nullptr), "bad keep list");
   std::lock_guard<std::mutex> lk(h->mu);
-  CSS_REQUIRE(n_keep <= h->ntotal, "keep list longer than the index (%lld > %lld)", (long long)n_keep,
-              (long long)h->ntotal);
+  const int64_t nt = CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+  CSS_REQUIRE(n_keep <= nt, "keep list longer than the index (%lld > %lld)", (long long)n_keep, (long long)nt);
   for (int64_t i = 0; i < n_keep; ++i) {
     const int64_t id = keep_ids_host[i];
-    CSS_REQUIRE(id >= 0 && id < h->ntotal && (i == 0 || id > keep_ids_host[i - 1]),
+    CSS_REQUIRE(id >= 0 && id < nt && (i == 0 || id > keep_ids_host[i - 1]),
                 "keep ids must be strictly ascending row ids (entry %lld = %lld)", (long long)i, (long long)id);
   }
+  if (CSS_IS_COMPOSITE(h)) return sharded_compact(h, keep_ids_host, n_keep);
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   const int d = h->dim;
@@ -578,39 +749,11 @@ int css_index_add(css_index* h, const float* x_host, int64_t n, int normalize, i
   CSS_REQUIRE(n >= 0, "n < 0");
   CSS_REQUIRE(n == 0 || x_host != nullptr, "x_host is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_add(h, x_host, n, normalize, first_id_out);
   DeviceGuard g(h->device);
-  CSS_REQUIRE(h->ntotal + n < ((int64_t)1 << 31), "index would exceed 2^31 rows per shard");
   if (first_id_out) *first_id_out = h->ntotal;
   if (n == 0) return CSS_OK;
-  CSS_CHECK(ensure_room(h, n));
-  // Stage through a bounded device buffer: rows are written in place by the
-  // append kernel (it normalises), so upload into the tail of x's own storage
-  // is not possible when normalising in a different layout; use chunks.
-  const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)64 << 20) / ((int64_t)h->dim * 4));
-  float* stage = nullptr;
-  CSS_CHECK(dev_alloc(&stage, (size_t)std::min(chunk_rows, n) * h->dim));
-  int rc = CSS_OK;
-  for (int64_t r0 = 0; r0 < n && rc == CSS_OK; r0 += chunk_rows) {
-    int64_t nr = std::min(chunk_rows, n - r0);
-    cudaError_t e = cudaMemcpyAsync(stage, x_host + (size_t)r0 * h->dim, (size_t)nr * h->dim * 4,
-                                    cudaMemcpyHostToDevice, h->stream);
-    if (e != cudaSuccess) {
-      set_error("H2D copy failed: %s", cudaGetErrorString(e));
-      rc = CSS_ERR_CUDA;
-      break;
-    }
-    rc = append_from_device(h, stage, nr, normalize, h->stream);
-    if (rc != CSS_OK) break;
-    e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) {
-      set_error("append failed: %s", cudaGetErrorString(e));
-      rc = CSS_ERR_CUDA;
-      break;
-    }
-    h->ntotal += nr;
-  }
-  cudaFree(stage);
-  return rc;
+  return single_add(h, x_host, n, normalize, /*sync=*/true);
 }
 
 int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normalize,
@@ -618,14 +761,18 @@ int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normal
   CSS_REQUIRE(h != nullptr, "index is NULL");
   CSS_REQUIRE(n >= 0, "n < 0");
   CSS_REQUIRE(n == 0 || x_dev != nullptr, "x_dev is NULL");
+  if (CSS_IS_COMPOSITE(h)) {
+    set_error("css_index_add_device: a multi-device index takes host rows (css_index_add)");
+    return CSS_ERR_UNSUPPORTED;
+  }
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  CSS_REQUIRE(h->ntotal + n < ((int64_t)1 << 31), "index would exceed 2^31 rows per shard");
+  CSS_REQUIRE(h->ntotal + n < ((int64_t)1 << 31) - 64, "index would exceed 2^31 rows per shard");
   if (first_id_out) *first_id_out = h->ntotal;
   if (n == 0) return CSS_OK;
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   if (h->ntotal + n > h->capacity) {
-    // growth reallocates: order it after the caller's stream work and before ours
+    // growth maps new memory on the handle's stream: order it after the caller's stream work
     CSS_CUDA(cudaStreamSynchronize(st));
     CSS_CHECK(ensure_room(h, n));
   }
@@ -636,10 +783,12 @@ int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normal
 
 int css_index_get_rows(css_index* h, int64_t start, int64_t n, float* out_host) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
-  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= h->ntotal, "row range out of bounds");
+  const int64_t nt = CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= nt, "row range out of bounds");
   if (n == 0) return CSS_OK;
   CSS_REQUIRE(out_host != nullptr, "out_host is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_get_rows(h, start, n, out_host);
   DeviceGuard g(h->device);
   CSS_CUDA(cudaMemcpyAsync(out_host, h->x + (size_t)start * h->dim, (size_t)n * h->dim * 4,
                            cudaMemcpyDeviceToHost, h->stream));
@@ -651,30 +800,24 @@ int css_index_set_column(css_index* h, int column, const int32_t* values_host, i
                          int64_t n) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
   CSS_REQUIRE(column >= 0 && column < CSS_MAX_COLUMNS, "column %d out of range", column);
-  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= h->ntotal, "row range out of bounds");
+  const int64_t nt = CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= nt, "row range out of bounds");
   if (n == 0) return CSS_OK;
   CSS_REQUIRE(values_host != nullptr, "values_host is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_set_column(h, column, values_host, start, n);
   DeviceGuard g(h->device);
-  if (!h->cols[column]) {
-    CSS_CHECK(dev_alloc(&h->cols[column], (size_t)h->capacity));
-    int64_t blocks = (h->capacity + 255) / 256;
-    fill_i32_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(h->cols[column], h->capacity,
-                                                             CSS_NULL_VALUE);
-    CSS_LAUNCHED();
-  }
-  CSS_CUDA(cudaMemcpyAsync(h->cols[column] + start, values_host, (size_t)n * 4,
-                           cudaMemcpyHostToDevice, h->stream));
-  CSS_CUDA(cudaStreamSynchronize(h->stream));
-  return CSS_OK;
+  return single_set_column(h, column, values_host, start, n, /*sync=*/true);
 }
 
 int css_index_set_alive(css_index* h, const uint8_t* alive_host, int64_t start, int64_t n) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
-  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= h->ntotal, "row range out of bounds");
+  const int64_t nt = CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+  CSS_REQUIRE(start >= 0 && n >= 0 && start + n <= nt, "row range out of bounds");
   if (n == 0) return CSS_OK;
   CSS_REQUIRE(alive_host != nullptr, "alive_host is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_set_alive(h, alive_host, start, n);
   DeviceGuard g(h->device);
   uint8_t* tmp = nullptr;
   CSS_CHECK(dev_alloc(&tmp, (size_t)n));
@@ -691,21 +834,27 @@ int css_index_set_alive(css_index* h, const uint8_t* alive_host, int64_t start, 
     rc = CSS_ERR_CUDA;
   }
   cudaFree(tmp);
-  if (rc == CSS_OK) {
-    for (int64_t i = 0; i < n; ++i)
-      if (!alive_host[i]) {
-        h->any_dead = true;
-        break;
-      }
-  }
+  if (rc == CSS_OK && memchr(alive_host, 0, (size_t)n) != nullptr) h->any_dead = true;
   return rc;
+}
+
+int css_index_set_alive_ids(css_index* h, const int64_t* ids_host, int64_t n, int alive) {
+  CSS_REQUIRE(h != nullptr, "index is NULL");
+  CSS_REQUIRE(n >= 0 && (n == 0 || ids_host != nullptr), "bad id list");
+  if (n == 0) return CSS_OK;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_set_alive_ids(h, ids_host, n, alive);
+  DeviceGuard g(h->device);
+  return single_set_alive_ids(h, ids_host, n, alive);
 }
 
 int css_index_filter_mask(css_index* h, const css_filter* f, uint32_t* mask_out_host,
                           int64_t* n_pass_out) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
-  CSS_REQUIRE(mask_out_host != nullptr || h->ntotal == 0, "mask_out_host is NULL");
+  const int64_t nt = CSS_IS_COMPOSITE(h) ? h->composite_ntotal : h->ntotal;
+  CSS_REQUIRE(mask_out_host != nullptr || nt == 0, "mask_out_host is NULL");
   std::lock_guard<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_filter_mask(h, f, mask_out_host, n_pass_out);
   DeviceGuard g(h->device);
   CSS_CHECK(ensure_device(h->device));
   const uint32_t* m = nullptr;
@@ -713,7 +862,7 @@ int css_index_filter_mask(css_index* h, const css_filter* f, uint32_t* mask_out_
   // force evaluation even for the trivial filter so the mask is materialised
   css_filter empty;
   memset(&empty, 0, sizeof(empty));
-  CSS_CHECK(eval_filter(h, f ? f : &empty, &m, &n_pass, /*need_count=*/true, h->stream));
+  CSS_CHECK(eval_filter(h, f ? f : &empty, &m, &n_pass, /*need_count=*/true, h->stream, nullptr));
   if (h->ntotal > 0) {
     CSS_CUDA(cudaMemcpyAsync(mask_out_host, h->mask, (size_t)words_for(h->ntotal) * 4,
                              cudaMemcpyDeviceToHost, h->stream));
@@ -728,21 +877,25 @@ int css_index_filter_mask_device(css_index* h, const css_filter* f, const uint32
                                  int64_t* n_pass_out, void* stream) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
   CSS_REQUIRE(mask_dev_out != nullptr, "mask_dev_out is NULL");
+  CSS_REQUIRE(!CSS_IS_COMPOSITE(h), "css_index_filter_mask_device: single-device indexes only");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st);
+  return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st, nullptr);
 }
 
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream) {
   CSS_REQUIRE(h != nullptr && q_dev != nullptr, "NULL argument");
   CSS_REQUIRE(nq >= 1 && nq <= 64, "nq=%d outside [1, 64]", nq);
-  CSS_REQUIRE(h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && h->ntotal > 0 && h->xb != nullptr,
-              "the two-phase scan needs a non-empty 768-d inner-product index");
+  CSS_REQUIRE(!CSS_IS_COMPOSITE(h) && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && h->ntotal > 0,
+              "the two-phase scan needs a non-empty single-device 768-d inner-product index");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
-  CSS_CHECK(ensure_query_scratch(h, nq));
-  return launch_phase1(h, q_dev, nq, h->any_dead ? h->alive : nullptr, nullptr, stream ? (cudaStream_t)stream : h->stream);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  css_scan_scratch* sc = nullptr;
+  CSS_CHECK(get_scratch(h, st, nq, &sc));
+  return launch_phase1(h, sc, q_dev, nq, 10, h->any_dead ? h->alive : nullptr, index_idmap(h, 0), nullptr, nullptr,
+                       nullptr, /*no_merge=*/1, st);
 }
 
 int css_index_search_device(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
@@ -752,15 +905,40 @@ int css_index_search_device(css_index* h, const float* q_dev, int nq, int k, con
   if (nq == 0) return CSS_OK;
   CSS_REQUIRE(q_dev && D_dev && I_dev, "NULL device buffer");
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
+  CSS_REQUIRE(!CSS_IS_COMPOSITE(h), "css_index_search_device: single-device indexes only (a multi-device index "
+              "is searched through css_index_search)");
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
   const uint32_t* m = mask_dev;
   if (!m && h->any_dead) m = h->alive;
-  if (nq >= CSS_BATCH_MIN_NQ && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim % 64 == 0 &&
-      h->ntotal >= 65536)
-    return batched_search(h, q_dev, nq, k, m, id_offset, D_dev, I_dev, st);
-  return scan_search(h, q_dev, nq, k, m, id_offset, D_dev, I_dev, st);
+  css_scan_scratch* sc = nullptr;
+  CSS_CHECK(get_scratch(h, st, std::min(nq, 1024), &sc));
+  return search_on_device(h, sc, q_dev, nq, k, m, index_idmap(h, id_offset), nullptr, D_dev, I_dev, st,
+                          /*defer_fallback=*/false, nullptr);
+}
+
+int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float* q_dev, int nq, int k,
+                                     const uint32_t* mask_dev, int64_t id_offset, float* D_dev, int64_t* I_dev,
+                                     void* stream) {
+  CSS_REQUIRE(h != nullptr && ex != nullptr, "NULL handle");
+  CSS_REQUIRE(!CSS_IS_COMPOSITE(h), "css_index_search_exchange_device: single-device indexes only");
+  CSS_REQUIRE(nq >= 1 && nq <= ex->max_nq, "nq=%d outside [1, %d] (larger batches: gather the lists with NCCL)", nq,
+              ex->max_nq);
+  CSS_REQUIRE(q_dev && D_dev && I_dev, "NULL device buffer");
+  CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
+  CSS_REQUIRE(ex->connected && ex->device == h->device, "exchange not connected / on another device");
+  std::lock_guard<std::mutex> lk(h->mu);
+  DeviceGuard g(h->device);
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  ExchangeDev xd;
+  CSS_CHECK(exchange_next(ex, &xd));
+  const uint32_t* m = mask_dev;
+  if (!m && h->any_dead) m = h->alive;
+  css_scan_scratch* sc = nullptr;
+  CSS_CHECK(get_scratch(h, st, nq, &sc));
+  return scan_search(h, sc, q_dev, nq, k, m, index_idmap(h, id_offset), &xd, D_dev, I_dev, st,
+                     /*defer_fallback=*/false, nullptr);
 }
 
 int css_index_search(css_index* h, const float* q_host, int nq, int k, const css_filter* filter,
@@ -770,39 +948,79 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   if (nq == 0) return CSS_OK;
   CSS_REQUIRE(q_host && D_host && I_host, "NULL host buffer");
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
-  CSS_CHECK(ensure_device(h->device));
   std::unique_lock<std::mutex> lk(h->mu);
+  if (CSS_IS_COMPOSITE(h)) return sharded_search(h, q_host, nq, k, filter, D_host, I_host);
+  CSS_CHECK(ensure_device(h->device));
   DeviceGuard g(h->device);
   cudaStream_t st = h->stream;
   const size_t qbytes = (size_t)nq * h->dim * 4;
   const size_t dbytes = (size_t)nq * k * 4, ibytes = (size_t)nq * k * 8;
-  CSS_CHECK(ensure_query_scratch(h, nq));
+  // queries are staged and answered in slices of at most 1024 (the scratch is sized for one slice)
+  if (nq > 1024) {
+    lk.unlock();
+    for (int q0 = 0; q0 < nq; q0 += 1024) {
+      const int n = std::min(1024, nq - q0);
+      CSS_CHECK(css_index_search(h, q_host + (size_t)q0 * h->dim, n, k, filter, D_host + (size_t)q0 * k,
+                                 I_host + (size_t)q0 * k));
+    }
+    return CSS_OK;
+  }
+  css_scan_scratch* sc = nullptr;
+  CSS_CHECK(get_scratch(h, st, nq, &sc));
   const uint32_t* m = nullptr;
-  CSS_CHECK(eval_filter(h, filter, &m, nullptr, false, st));
-  if (!m && h->any_dead) m = h->alive;
-  // pinned staging: [q | D | I]
-  CSS_CHECK(ensure_pinned(h, qbytes + dbytes + ibytes + 64));
+  bool ignore_alive = false;
+  CSS_CHECK(eval_filter(h, filter, &m, nullptr, false, st, &ignore_alive));
+  if (!m && h->any_dead && !ignore_alive) m = h->alive;
+  // pinned staging: [q | D | I | overflow count]
+  CSS_CHECK(ensure_pinned(h, qbytes + dbytes + ibytes + 128));
   unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
   // set bitsets staged in the same pinned block were consumed by an async copy: wait for it
   if (filter && filter->n_clauses) CSS_CUDA(cudaStreamSynchronize(st));
   memcpy(pin, q_host, qbytes);
   size_t d_off = (qbytes + 15) / 16 * 16;
   size_t i_off = (d_off + dbytes + 15) / 16 * 16;
-  CSS_CUDA(cudaMemcpyAsync(h->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
+  size_t c_off = (i_off + ibytes + 15) / 16 * 16;
+  CSS_CUDA(cudaMemcpyAsync(sc->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
   // results of this call: scores at D_dev, ids right behind them (same spacing as in the pinned block)
-  int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(h->D_dev) + (i_off - d_off));
-  int rc;
-  if (nq >= CSS_BATCH_MIN_NQ && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim % 64 == 0 &&
-      h->ntotal >= 65536)
-    rc = batched_search(h, h->q_dev, nq, k, m, 0, h->D_dev, I_dev, st);
-  else
-    rc = scan_search(h, h->q_dev, nq, k, m, 0, h->D_dev, I_dev, st);
-  if (rc != CSS_OK) return rc;
-  CSS_CUDA(cudaMemcpyAsync(pin + d_off, h->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
+  int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(sc->D_dev) + (i_off - d_off));
+  bool two_phase = false;
+  CSS_CHECK(search_on_device(h, sc, sc->q_dev, nq, k, m, index_idmap(h, 0), nullptr, sc->D_dev, I_dev, st,
+                             /*defer_fallback=*/true, &two_phase));
+  CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
+  if (two_phase) CSS_CUDA(cudaMemcpyAsync(pin + c_off, sc->ovf_count, sizeof(int), cudaMemcpyDeviceToHost, st));
   CSS_CUDA(cudaStreamSynchronize(st));
+  if (two_phase && *reinterpret_cast<const int*>(pin + c_off) > 0) {
+    // some queries could not be proven from the bf16 lists: the fp32 scan answers exactly those
+    CSS_CHECK(scan_fallback(h, sc, sc->q_dev, nq, k, m, index_idmap(h, 0), nullptr, sc->D_dev, I_dev, st));
+    CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
+    CSS_CUDA(cudaStreamSynchronize(st));
+  }
   memcpy(D_host, pin + d_off, dbytes);
   memcpy(I_host, pin + i_off, ibytes);
   return CSS_OK;
+}
+
+int css_index_scan_stats(css_index* h, int64_t out[4]) {
+  CSS_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
+  std::lock_guard<std::mutex> lk(h->mu);
+  out[0] = out[1] = out[2] = out[3] = 0;
+  auto one = [&](css_index* s) -> int {
+    DeviceGuard g(s->device);
+    unsigned v[2] = {0, 0};
+    CSS_CUDA(cudaMemcpy(v, s->stats_dev, sizeof(v), cudaMemcpyDeviceToHost));
+    out[0] += v[0];
+    out[1] += v[1];
+    out[2] += s->skip_two_phase > 0 ? 1 : 0;
+    float e = 0.f;
+    CSS_CUDA(cudaMemcpy(&e, s->max_err_dev, sizeof(e), cudaMemcpyDeviceToHost));
+    out[3] = std::max<int64_t>(out[3], (int64_t)(e * 1e9f));
+    return CSS_OK;
+  };
+  if (CSS_IS_COMPOSITE(h)) {
+    for (css_index* s : h->shards) CSS_CHECK(one(s));
+    return CSS_OK;
+  }
+  return one(h);
 }
 
 int css_topk_merge_strided_device(const float* D_in, int64_t d_list_stride, const int64_t* I_in, int64_t i_list_stride,
@@ -834,152 +1052,6 @@ int css_topk_merge_device(const float* D_in, const int64_t* I_in, int n_lists, i
                           int metric, float* D_out, int64_t* I_out, void* stream) {
   return css_topk_merge_strided_device(D_in, (int64_t)nq * k, I_in, (int64_t)nq * k, n_lists, nq, k, metric, D_out,
                                        I_out, stream);
-}
-
-// ---------------------------------------------------------------------------
-// faiss IndexFlat file format (faiss/impl/index_write.cpp, write_index_header +
-// IndexFlat codes; restated from the published format, faiss >= 1.7):
-//   u32  fourcc  "IxFI" (inner product) | "IxF2" (L2)
-//   i32  d
-//   i64  ntotal
-//   i64  dummy (1 << 20), i64 dummy (1 << 20)
-//   u8   is_trained (1)
-//   i32  metric_type (0 = IP, 1 = L2)
-//   u64  count = ntotal * d          (vector<float> xb / codes.size()/4)
-//   f32  data[count]
-// ---------------------------------------------------------------------------
-static uint32_t fourcc(const char s[4]) {
-  return (uint32_t)(unsigned char)s[0] | ((uint32_t)(unsigned char)s[1] << 8) |
-         ((uint32_t)(unsigned char)s[2] << 16) | ((uint32_t)(unsigned char)s[3] << 24);
-}
-
-int css_index_save(css_index* h, const char* path) {
-  CSS_REQUIRE(h != nullptr && path != nullptr, "NULL argument");
-  std::lock_guard<std::mutex> lk(h->mu);
-  DeviceGuard g(h->device);
-  std::string tmp = std::string(path) + ".tmp";
-  FILE* fp = fopen(tmp.c_str(), "wb");
-  if (!fp) {
-    set_error("cannot open %s for writing", tmp.c_str());
-    return CSS_ERR_IO;
-  }
-  bool ok = true;
-  auto W = [&](const void* p, size_t n) { ok = ok && (fwrite(p, 1, n, fp) == n); };
-  uint32_t cc = fourcc(h->metric == CSS_METRIC_INNER_PRODUCT ? "IxFI" : "IxF2");
-  int32_t d = h->dim;
-  int64_t nt = h->ntotal, dummy = (int64_t)1 << 20;
-  uint8_t trained = 1;
-  int32_t metric = h->metric;
-  uint64_t count = (uint64_t)h->ntotal * (uint64_t)h->dim;
-  W(&cc, 4); W(&d, 4); W(&nt, 8); W(&dummy, 8); W(&dummy, 8); W(&trained, 1); W(&metric, 4);
-  W(&count, 8);
-  int rc = CSS_OK;
-  if (h->ntotal > 0 && ok) {
-    const size_t chunk_bytes = (size_t)32 << 20;
-    rc = ensure_pinned(h, chunk_bytes);
-    const size_t total = (size_t)count * 4;
-    for (size_t off = 0; off < total && rc == CSS_OK && ok; off += chunk_bytes) {
-      size_t nb = std::min(chunk_bytes, total - off);
-      cudaError_t e = cudaMemcpyAsync(h->pinned, reinterpret_cast<const char*>(h->x) + off, nb,
-                                      cudaMemcpyDeviceToHost, h->stream);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) {
-        set_error("D2H copy failed: %s", cudaGetErrorString(e));
-        rc = CSS_ERR_CUDA;
-        break;
-      }
-      W(h->pinned, nb);
-    }
-  }
-  ok = ok && (fclose(fp) == 0);
-  if (rc == CSS_OK && !ok) {
-    set_error("write to %s failed", tmp.c_str());
-    rc = CSS_ERR_IO;
-  }
-  if (rc == CSS_OK && rename(tmp.c_str(), path) != 0) {
-    set_error("cannot rename %s to %s", tmp.c_str(), path);
-    rc = CSS_ERR_IO;
-  }
-  if (rc != CSS_OK) remove(tmp.c_str());
-  return rc;
-}
-
-int css_index_load(css_index* h, const char* path) {
-  CSS_REQUIRE(h != nullptr && path != nullptr, "NULL argument");
-  std::lock_guard<std::mutex> lk(h->mu);
-  DeviceGuard g(h->device);
-  FILE* fp = fopen(path, "rb");
-  if (!fp) {
-    set_error("cannot open %s", path);
-    return CSS_ERR_IO;
-  }
-  uint32_t cc = 0;
-  int32_t d = 0, metric = 0;
-  int64_t nt = 0, dummy = 0;
-  uint8_t trained = 0;
-  uint64_t count = 0;
-  bool ok = true;
-  auto R = [&](void* p, size_t n) { ok = ok && (fread(p, 1, n, fp) == n); };
-  R(&cc, 4); R(&d, 4); R(&nt, 8); R(&dummy, 8); R(&dummy, 8); R(&trained, 1); R(&metric, 4);
-  if (ok && metric > 1) {
-    float metric_arg;
-    R(&metric_arg, 4);
-  }
-  R(&count, 8);
-  int rc = CSS_OK;
-  if (!ok || (cc != fourcc("IxFI") && cc != fourcc("IxF2"))) {
-    set_error("%s is not a faiss IndexFlat file", path);
-    rc = CSS_ERR_IO;
-  } else if (d != h->dim) {
-    set_error("%s has d=%d, index has d=%d", path, d, h->dim);
-    rc = CSS_ERR_IO;
-  } else if (nt < 0 || nt >= ((int64_t)1 << 31) || count != (uint64_t)nt * (uint64_t)d) {
-    set_error("%s: inconsistent header (ntotal=%lld count=%llu)", path, (long long)nt,
-              (unsigned long long)count);
-    rc = CSS_ERR_IO;
-  }
-  if (rc == CSS_OK) {
-    h->ntotal = 0;
-    h->any_dead = false;
-    cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream);
-    h->metric = (cc == fourcc("IxF2")) ? CSS_METRIC_L2 : CSS_METRIC_INNER_PRODUCT;
-    if (h->capacity > 0)
-      cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, h->stream);
-    rc = ensure_room(h, nt);
-  }
-  if (rc == CSS_OK && nt > 0) {
-    const int64_t chunk_rows = std::max<int64_t>(1, ((int64_t)32 << 20) / ((int64_t)d * 4));
-    rc = ensure_pinned(h, (size_t)chunk_rows * d * 4);
-    float* stage = nullptr;
-    if (rc == CSS_OK) rc = dev_alloc(&stage, (size_t)std::min(chunk_rows, nt) * d);
-    for (int64_t r0 = 0; r0 < nt && rc == CSS_OK; r0 += chunk_rows) {
-      int64_t nr = std::min(chunk_rows, nt - r0);
-      size_t nb = (size_t)nr * d * 4;
-      if (fread(h->pinned, 1, nb, fp) != nb) {
-        set_error("%s: truncated", path);
-        rc = CSS_ERR_IO;
-        break;
-      }
-      cudaError_t e = cudaMemcpyAsync(stage, h->pinned, nb, cudaMemcpyHostToDevice, h->stream);
-      if (e != cudaSuccess) {
-        set_error("H2D copy failed: %s", cudaGetErrorString(e));
-        rc = CSS_ERR_CUDA;
-        break;
-      }
-      rc = append_from_device(h, stage, nr, /*normalize=*/0, h->stream);
-      if (rc != CSS_OK) break;
-      e = cudaStreamSynchronize(h->stream);
-      if (e != cudaSuccess) {
-        set_error("load failed: %s", cudaGetErrorString(e));
-        rc = CSS_ERR_CUDA;
-        break;
-      }
-      h->ntotal += nr;
-    }
-    cudaFree(stage);
-  }
-  fclose(fp);
-  return rc;
 }
 
 }  // extern "C"

@@ -130,6 +130,46 @@ struct WarpTopK {
   }
 };
 
+// Local row -> returned id.  One shard of a single-process multi-device index holds the row blocks
+// b with b % ndev == shard (block = 2^shift rows, block-cyclic over the devices, so that ids stay dense
+// and append-only like faiss's whatever the number of devices); ndev <= 1: id = offset + local row.
+struct IdMap {
+  long long offset;
+  int shift;
+  int ndev;
+  int shard;
+};
+__device__ __forceinline__ long long map_id(const IdMap& m, int local) {
+  if (m.ndev <= 1) return m.offset + local;
+  const long long l = local;
+  return m.offset + ((((l >> m.shift) * m.ndev + m.shard) << m.shift) | (l & ((1ll << m.shift) - 1)));
+}
+
+// ------------------------------------------------------------------------
+// Result exchange between the shards of one search (one exchange step), fused into the
+// kernel that produces the local top-k: the CTA that finishes a query's local list stores it into
+// every peer's receive area over NVLink (peer-mapped memory: cudaDeviceEnablePeerAccess in one
+// process, CUDA IPC between the ranks of a torchrun job), raises a per-(query, source) flag there,
+// waits for the flags of all sources in its OWN memory and merges the n_ranks lists -- no NCCL
+// call, no extra launch.  Receive areas and flags are double-buffered by the parity of `epoch`
+// (a rank cannot be two searches ahead of a peer: it needs that peer's list to finish a search).
+// ------------------------------------------------------------------------
+constexpr int kMaxRanks = CSS_MAX_RANKS;
+struct ExEntry {
+  float key;
+  int pad;
+  long long id;   // global id, -1 = unfilled slot
+};
+struct ExchangeDev {
+  int n_ranks;   // <= 1: no exchange
+  int rank;
+  unsigned epoch;
+  int max_nq;
+  ExEntry* slots[kMaxRanks];    // slots[r]: receive area of rank r, [2][max_nq][n_ranks][CSS_MAX_K]
+  unsigned* flags[kMaxRanks];   // flags[r]: flags of rank r, [2][max_nq][n_ranks]
+  int* status;                  // local; 1 = a peer's list did not arrive (timeout)
+};
+
 struct ScanParams {
   const float* x;        // [n, d]
   const __nv_bfloat16* xb;  // [n, d] bf16 shadow rows (two-phase scan only)
@@ -137,16 +177,26 @@ struct ScanParams {
   int d;
   const float* q;        // [nq, d]
   const uint32_t* mask;  // nullable bitmask over rows
-  int k;
+  int k;                 // entries kept per warp / per block list
+  int k_out;             // entries of the result (== k except in the two-phase scan, where k is the list length)
   KeyId* part;           // [nq][gridDim.x][k]
   unsigned int* ticket;  // [nq], zero on entry, zero on exit
-  int64_t id_offset;
-  float* D;              // [nq, k]
-  int64_t* I;            // [nq, k]
+  IdMap idmap;
+  float* D;              // [nq, k_out]
+  int64_t* I;            // [nq, k_out]
   const int* qlist;      // nullable: explicit list of query indices to scan (device)
   const int* qcount;     // number of entries of qlist (device)
-  int no_merge;          // 1: stop after the per-block lists (two-phase scan, phase 1)
-  int* zero_on_entry;    // nullable: one int cleared by the first thread of the grid (phase 2's overflow count)
+  int no_merge;          // 1: stop after the per-block lists (phase 1 timed alone)
+  int interleave;        // 1: dense bf16 sweep walks 8-row units block-cyclically over the grid
+  int* zero_on_entry;    // nullable: one int cleared by the first thread of the grid (the overflow count)
+  // two-phase scan
+  const float* max_norm; // largest stored row norm
+  const float* max_err;  // largest ||x - bf16(x)|| over the stored rows
+  int* ovf_list;         // queries handed to the fp32 scan
+  int* ovf_count;
+  unsigned* stats_dev;   // [2] two-phase queries, unproven queries (device counters)
+  volatile unsigned* stats_host;  // nullable: the same two counters mirrored into mapped host memory
+  ExchangeDev ex;
 };
 
 // Dot products (or negated squared distances) of up to 4 rows against the query.
@@ -243,6 +293,280 @@ __device__ __forceinline__ void score_rows_bf16(const ScanParams& p, const float
   for (int i = 0; i < kRowsPerUnit; ++i) acc[i] = warp_sum(acc[i]);
 }
 
+// ------------------------------------------------------------------------
+// Result of one query: s[0..k_out) is the local list, best first (unfilled slots carry kEmptyId).
+// Without an exchange it is written to D/I; with one it is published to every rank, the lists of
+// all ranks are awaited and merged (see ExchangeDev), and the merged list is written -- identical
+// on every rank.  Called by all threads of one CTA; s must have room for n_ranks * k_out 16-byte
+// entries (8 x 128 x 16 B = 16 KB of the 32 KB list buffer).
+// ------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <int METRIC>
+__device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, KeyId* s, const int tid, const int nthreads) {
+  const int k = p.k_out;
+  if (p.ex.n_ranks <= 1) {
+    for (int i = tid; i < k; i += nthreads) {
+      const KeyId e = s[i];
+      const bool empty = (e.id == kEmptyId);
+      float dval;
+      if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
+      else dval = empty ? FLT_MAX : -e.key;
+      p.D[(int64_t)qi * k + i] = dval;
+      p.I[(int64_t)qi * k + i] = empty ? (int64_t)-1 : (int64_t)map_id(p.idmap, e.id);
+    }
+    return;
+  }
+  const int R = p.ex.n_ranks;
+  const size_t cell = ((size_t)(p.ex.epoch & 1u) * p.ex.max_nq + qi) * R;   // [parity][query][source]
+  // 1. publish: my list into slot (parity, qi, my rank) of every rank
+  for (int idx = tid; idx < R * k; idx += nthreads) {
+    const int r = idx / k, i = idx - r * k;
+    const KeyId e = s[i];
+    const long long gid = (e.id == kEmptyId) ? -1ll : map_id(p.idmap, e.id);
+    int4 v;
+    v.x = __float_as_int(e.key);
+    v.y = 0;
+    v.z = (int)(gid & 0xffffffffll);
+    v.w = (int)(gid >> 32);
+    *reinterpret_cast<int4*>(p.ex.slots[r] + (cell + p.ex.rank) * CSS_MAX_K + i) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < R) {
+    st_release_sys(p.ex.flags[tid] + cell + p.ex.rank, p.ex.epoch);
+    // 2. wait for the list of source `tid` in my own memory (bounded: a missing peer is an error, not a hang)
+    const unsigned* f = p.ex.flags[p.ex.rank] + cell + tid;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys(f) != p.ex.epoch) {
+      __nanosleep(64);
+      if (global_timer_ns() - t0 > 10000000000ull) {   // 10 s
+        *p.ex.status = 1;
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  // 3. merge the R lists
+  KeyId64* m = reinterpret_cast<KeyId64*>(s);
+  const ExEntry* mine = p.ex.slots[p.ex.rank] + cell * CSS_MAX_K;
+  const int total = R * k;
+  int n_sort = 32;
+  while (n_sort < total) n_sort <<= 1;
+  for (int i = tid; i < n_sort; i += nthreads) {
+    KeyId64 e;
+    e.key = -INFINITY;
+    e.pad = 0;
+    e.id = LLONG_MAX;
+    if (i < total) {
+      const int r = i / k, j = i - r * k;
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(mine + (size_t)r * CSS_MAX_K + j));
+      const long long gid = ((long long)v.w << 32) | (unsigned)v.z;
+      if (gid >= 0) {
+        e.key = __int_as_float(v.x);
+        e.id = gid;
+      }
+    }
+    m[i] = e;
+  }
+  bitonic_sort_desc(m, n_sort, tid, nthreads);
+  for (int i = tid; i < k; i += nthreads) {
+    const KeyId64 e = m[i];
+    const bool empty = (e.id == LLONG_MAX);
+    float dval;
+    if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
+    else dval = empty ? FLT_MAX : -e.key;
+    p.D[(int64_t)qi * k + i] = dval;
+    p.I[(int64_t)qi * k + i] = empty ? (int64_t)-1 : (int64_t)e.id;
+  }
+}
+
+// ------------------------------------------------------------------------
+// Two-phase scan, phase 2, run by the last CTA of a query's phase-1 grid (no extra launch).  Phase 1
+// (BF16 scan) left, per scan block, the kp best rows of that block's rows by their score against the
+// bf16 shadow copy (sorted; `part`).  Rounding a row to bf16 (the query stays fp32) moves its score by
+//   |x.q - bf16(x).q| <= ||x - bf16(x)|| ||q|| <= max_err ||q||      (Cauchy-Schwarz; max_err is the
+// largest rounding-error norm of any stored row, tracked exactly at add time: about 0.4 * 2^-8 ||x||
+// for dense rows, against the worst case 2^-8 ||x|| of round-to-nearest with an 8-bit significand)
+// and the two fp32 summations (24 FMAs per lane + 5 shuffle adds each) by <= 4e-6 ||x|| ||q||, so
+//   eps = ||q|| (1.001 max_err + 4e-6 max_norm).
+// With t = the k-th best bf16 score over ALL list entries (exactly the k-th best bf16 score of the
+// corpus unless a list is cut short, in which case it is a lower bound), the true k-th best score is
+// >= t - eps and every row of the true top-k has a bf16 score >= t - 2 eps =: thr.  A block list
+// whose last entry is still >= thr may have dropped such a row: the query is queued for the fp32 scan
+// (ovf_list), as it is when more than kRescoreCap rows pass -- never answered approximately.
+// Otherwise every row with bf16 score >= thr is in the lists: they are re-scored in fp32 with the
+// arithmetic of the fp32 scan (bit-identical scores) and the best k are the exact result.
+// Selection is by rank counting (no sorting network: one barrier per step); s: kMergeCap entries.
+// Returns true when the result was emitted.
+// ------------------------------------------------------------------------
+constexpr int kRescoreCap = 2048;    // candidates re-scored per query at most (second half of s: rank-sort output)
+constexpr int kTwoPhaseMaxK = 32;    // largest k the two-phase scan serves
+constexpr int kRankSortMax = 1024;   // above this many candidates: bitonic sort instead of rank counting
+
+__device__ __forceinline__ KeyId ldcg_keyid(const KeyId* p) {
+  const unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(p));
+  KeyId e;
+  e.key = __uint_as_float((unsigned)(raw & 0xffffffffull));
+  e.id = (int)(raw >> 32);
+  return e;
+}
+
+__device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid) {
+  __shared__ float s_qn, s_t;
+  __shared__ int s_cnt, s_unproven;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int kp = p.k, k = p.k_out, blocks = gridDim.x;
+  const KeyId* lists = p.part + (size_t)qi * blocks * kp;
+  const float* q = p.q + (size_t)qi * 768;
+  if (warp == 0) {
+    float ss = 0.f;
+    for (int j = lane; j < 768; j += 32) ss = fmaf(q[j], q[j], ss);
+    ss = warp_sum(ss);
+    if (lane == 0) {
+      s_qn = sqrtf(ss);
+      s_t = -INFINITY;
+      s_cnt = 0;
+      s_unproven = 0;
+    }
+  }
+  // (A) t0 = k-th best list head (k distinct rows score at least that); with fewer than k lists the
+  //     k-th best of their first k entries.
+  const int per = blocks >= k ? 1 : k;
+  const int nsel = blocks * per;
+  for (int i = tid; i < nsel; i += kScanThreads) s[i] = ldcg_keyid(lists + (i / per) * kp + (i % per));
+  __syncthreads();
+  for (int i = tid; i < nsel; i += kScanThreads) {
+    const KeyId e = s[i];
+    if (e.id == kEmptyId) continue;
+    int rank = 0;
+    for (int j = 0; j < nsel; ++j) rank += better(s[j], e) ? 1 : 0;
+    if (rank == k - 1) s_t = e.key;
+  }
+  __syncthreads();
+  const float t0 = s_t;
+  // (B) tighten: the k-th best over all entries >= t0 (there are at least k of them)
+  if (t0 > -INFINITY) {
+    for (int i = tid; i < blocks * kp; i += kScanThreads) {
+      const KeyId e = ldcg_keyid(lists + i);
+      if (e.id != kEmptyId && e.key >= t0) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < kRankSortMax) s[pos] = e;
+      }
+    }
+    __syncthreads();
+    const int c = s_cnt;
+    if (c <= kRankSortMax) {
+      for (int i = tid; i < c; i += kScanThreads) {
+        const KeyId e = s[i];
+        int rank = 0;
+        for (int j = 0; j < c; ++j) rank += better(s[j], e) ? 1 : 0;
+        if (rank == k - 1) s_t = e.key;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_cnt = 0;
+  }
+  __syncthreads();
+  const float eps = s_qn * (1.001f * (*p.max_err) + 4e-6f * (*p.max_norm));
+  const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
+  // (C) proof + candidates over the full lists
+  for (int i = tid; i < blocks * kp; i += kScanThreads) {
+    const KeyId e = ldcg_keyid(lists + i);
+    if (e.id != kEmptyId && e.key >= thr) {
+      if (i % kp == kp - 1) s_unproven = 1;
+      const int pos = atomicAdd(&s_cnt, 1);
+      if (pos < kRescoreCap) s[pos] = e;
+    }
+  }
+  __syncthreads();
+  const int keep = s_cnt;
+  if (tid == 0) {
+    const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
+    if (p.stats_host) p.stats_host[0] = nq_seen;
+  }
+  if (s_unproven || keep > kRescoreCap) {
+    if (tid == 0) {
+      p.ovf_list[atomicAdd(p.ovf_count, 1)] = qi;
+      const unsigned nu = atomicAdd(p.stats_dev + 1, 1u) + 1u;
+      if (p.stats_host) p.stats_host[1] = nu;
+    }
+    return false;
+  }
+  // (D) exact fp32 scores, two candidates in flight per warp (the arithmetic of score_rows)
+  for (int i0 = warp * 2; i0 < keep; i0 += kScanWarps * 2) {
+    const int i1 = min(i0 + 1, keep - 1);
+    const float4* r0 = reinterpret_cast<const float4*>(p.x + (size_t)s[i0].id * 768);
+    const float4* r1 = reinterpret_cast<const float4*>(p.x + (size_t)s[i1].id * 768);
+    float4 v0[6], v1[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      v0[j] = ld_stream_f4(r0 + j * 32 + lane);
+      v1[j] = ld_stream_f4(r1 + j * 32 + lane);
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
+      a0 = fmaf(v0[j].x, qv.x, a0); a0 = fmaf(v0[j].y, qv.y, a0); a0 = fmaf(v0[j].z, qv.z, a0); a0 = fmaf(v0[j].w, qv.w, a0);
+      a1 = fmaf(v1[j].x, qv.x, a1); a1 = fmaf(v1[j].y, qv.y, a1); a1 = fmaf(v1[j].z, qv.z, a1); a1 = fmaf(v1[j].w, qv.w, a1);
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
+    __syncwarp();
+    if (lane == 0) {
+      s[i0].key = a0;
+      if (i1 != i0) s[i1].key = a1;
+    }
+  }
+  __syncthreads();
+  // (E) order by (score desc, id asc)
+  KeyId* out = s;
+  if (keep <= kRankSortMax) {
+    out = s + kRescoreCap;
+    for (int i = tid; i < keep; i += kScanThreads) {
+      const KeyId e = s[i];
+      int rank = 0;
+      for (int j = 0; j < keep; ++j) rank += better(s[j], e) ? 1 : 0;
+      out[rank] = e;
+    }
+    for (int i = keep + tid; i < k; i += kScanThreads) {
+      out[i].key = -INFINITY;
+      out[i].id = kEmptyId;
+    }
+    __syncthreads();
+  } else {
+    int n2 = 32;
+    while (n2 < keep) n2 <<= 1;
+    for (int i = keep + tid; i < n2; i += kScanThreads) {
+      s[i].key = -INFINITY;
+      s[i].id = kEmptyId;
+    }
+    bitonic_sort_desc(s, n2, tid, kScanThreads);
+  }
+  if (out != s) {   // emit_topk reuses s as its merge buffer: hand it the list at the front
+    KeyId e;
+    if (tid < k) e = out[tid];
+    __syncthreads();
+    if (tid < k) s[tid] = e;
+    __syncthreads();
+  }
+  emit_topk<CSS_METRIC_INNER_PRODUCT>(p, qi, s, tid, kScanThreads);
+  return true;
+}
+
 // grid = (blocks, nq).  Each warp owns a contiguous range of 8-row units, keeps
 // a register top-k, the block merges its 16 warps in shared memory, and the last
 // block to finish (atomic ticket) merges the per-block lists into D/I.
@@ -286,7 +610,30 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   const int64_t u_end = (units * (gw + 1)) / nwarps;
   const unsigned char* mask8 = reinterpret_cast<const unsigned char*>(p.mask);
 
-  for (int64_t ub = u_begin; ub < u_end; ub += 32) {
+  bool swept = false;
+  if constexpr (BF16) {
+    if (mask8 == nullptr && p.interleave) {
+      // Dense sweep, 8-row units dealt block-cyclically: unit u belongs to block u % gridDim.x, warp
+      // (u / gridDim.x) % 16.  Neighbouring rows -- the chunks of one session, which are each other's
+      // nearest neighbours -- land in different blocks, so no single block list fills up with the rows
+      // around the k-th score (the proof of two_phase_finish fails when one does).
+      const int64_t stride = (int64_t)gridDim.x * kScanWarps;
+      for (int64_t u = blockIdx.x + (int64_t)gridDim.x * warp; u < units; u += stride) {
+        const int64_t row0 = u * kRowsPerUnit;
+        const int valid = (int)min((int64_t)kRowsPerUnit, p.n - row0);
+        int64_t r[kRowsPerUnit];
+#pragma unroll
+        for (int i = 0; i < kRowsPerUnit; ++i) r[i] = row0 + (i < valid ? i : 0);
+        float acc[kRowsPerUnit];
+        score_rows_bf16(p, qreg, r, lane, acc);
+#pragma unroll
+        for (int i = 0; i < kRowsPerUnit; ++i)
+          if (i < valid) top.consider(acc[i], (int)(row0 + i), lane);
+      }
+      swept = true;
+    }
+  }
+  for (int64_t ub = swept ? u_end : u_begin; ub < u_end; ub += 32) {
     // one coalesced mask fetch for the next 32 units (256 rows)
     unsigned mb = 0;
     {
@@ -415,6 +762,13 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   __syncthreads();
   if (!s_is_last) return;
   __threadfence();
+  if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
+
+  if constexpr (BF16) {
+    // two-phase scan: prove + re-score in fp32 (or queue the query for the fp32 scan)
+    two_phase_finish(p, qi, s_list, tid);
+    return;
+  }
 
   const KeyId* all = p.part + (int64_t)qi * gridDim.x * p.k;
   const int total = gridDim.x * p.k;
@@ -429,9 +783,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     for (int i = tid; i < kMergeCap - keep; i += kScanThreads) {
       KeyId e;
       if (i < take) {
-        unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(all + consumed + i));
-        e.key = __uint_as_float((unsigned)(raw & 0xffffffffull));
-        e.id = (int)(raw >> 32);
+        e = ldcg_keyid(all + consumed + i);
       } else {
         e.key = -INFINITY;
         e.id = kEmptyId;
@@ -445,16 +797,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     consumed += take;
     first = false;
   }
-  for (int i = tid; i < p.k; i += kScanThreads) {
-    KeyId e = s_list[i];
-    bool empty = (e.id == kEmptyId);
-    float dval;
-    if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
-    else dval = empty ? FLT_MAX : -e.key;
-    p.D[(int64_t)qi * p.k + i] = dval;
-    p.I[(int64_t)qi * p.k + i] = empty ? (int64_t)-1 : (int64_t)e.id + p.id_offset;
-  }
-  if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
+  emit_topk<METRIC>(p, qi, s_list, tid, kScanThreads);
 }
 
 // grid = (blocks, nq) scans query blockIdx.y; with p.qlist set, grid = (blocks, F) and
@@ -474,126 +817,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p
 }
 
 // ------------------------------------------------------------------------
-// Two-phase scan, phase 2.  Phase 1 (scan_topk_kernel<.., BF16> with no_merge) left, per query and per
-// scan block, the kp = 32 best rows of that block's slice by their score against the bf16 shadow copy
-// (sorted; `part`).  Rounding a row to bf16 (the query stays fp32) moves its score by at most
-//   eps = eps_scale * ||q|| * max_row_norm        (u = 2^-9, |x.q| <= ||x|| ||q||, 10 % slack for the fp32 sums)
-// so with t <= the k-th best bf16 score overall (k rows are known to score at least t) the true k-th best
-// score is >= t - eps and every row of the true top-k has a bf16 score >= t - 2 eps =: thr.
-// A block list whose last entry is still >= thr may have dropped such a row: the query is then queued for
-// the fp32 scan (ovf_list), as it is when more than kRescoreCap rows pass -- never answered approximately.
-// Otherwise every row with bf16 score >= thr is in the lists: they are re-scored in fp32 with the
-// arithmetic of the fp32 scan (bit-identical scores) and the best k are the exact result.
-// One CTA per query; dynamic shared memory: kRescoreSort KeyId entries.
-// ------------------------------------------------------------------------
-constexpr int kRescoreThreads = 512;
-constexpr int kRescoreSort = 8192;   // >= scan blocks * k for k <= 32
-constexpr int kRescoreCap = 4096;    // candidates re-scored per query at most
-constexpr int kTwoPhaseMaxK = 32;    // = the per-block list length of phase 1 (KPL = 1)
-
-struct RescoreParams {
-  const float* x;
-  const float* q;
-  int k, kp, blocks;
-  float eps_scale;
-  const float* max_norm;
-  const KeyId* part;      // [nq][blocks][kp]
-  int64_t id_offset;
-  float* D;
-  int64_t* I;
-  int* ovf_list;
-  int* ovf_count;
-};
-
-static __global__ void __launch_bounds__(kRescoreThreads) rescore768_kernel(RescoreParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  KeyId* s = reinterpret_cast<KeyId*>(smem_raw);
-  __shared__ float s_qn;
-  __shared__ int s_count, s_unproven;
-  const int qi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* q = p.q + (size_t)qi * 768;
-  const KeyId* lists = p.part + (size_t)qi * p.blocks * p.kp;
-  if (warp == 0) {
-    float ss = 0.f;
-    for (int j = lane; j < 768; j += 32) ss = fmaf(q[j], q[j], ss);
-    ss = warp_sum(ss);
-    if (lane == 0) {
-      s_qn = sqrtf(ss);
-      s_count = 0;
-      s_unproven = 0;
-    }
-  }
-  // t: a lower bound of the k-th best bf16 score overall.  With at least k block lists, the k-th largest of
-  // their heads (k distinct rows score at least that; ~150 values to sort instead of blocks * k -- the
-  // looser bound admits a few more candidates); otherwise the exact k-th best, which lies among the
-  // first k entries of the lists.
-  const int per = p.blocks >= p.k ? 1 : p.k;
-  const int nsel = p.blocks * per;
-  int n_sort = 32;
-  while (n_sort < nsel) n_sort <<= 1;
-  for (int i = tid; i < n_sort; i += kRescoreThreads) {
-    KeyId e;
-    e.key = -INFINITY;
-    e.id = kEmptyId;
-    if (i < nsel) e = lists[(i / per) * p.kp + (i % per)];
-    s[i] = e;
-  }
-  bitonic_sort_desc(s, n_sort, tid, kRescoreThreads);
-  const float eps = p.eps_scale * s_qn * (*p.max_norm);
-  const float thr = (s[p.k - 1].id != kEmptyId) ? s[p.k - 1].key - 2.f * eps : -INFINITY;
-  __syncthreads();
-  // proof + candidates over the full lists (s[] is free again)
-  for (int i = tid; i < p.blocks * p.kp; i += kRescoreThreads) {
-    const KeyId e = lists[i];
-    if (e.id != kEmptyId && e.key >= thr) {
-      if (i % p.kp == p.kp - 1) s_unproven = 1;
-      const int pos = atomicAdd(&s_count, 1);
-      if (pos < kRescoreCap) s[pos] = e;
-    }
-  }
-  __syncthreads();
-  const int keep = s_count;
-  if (s_unproven || keep > kRescoreCap) {
-    if (tid == 0) p.ovf_list[atomicAdd(p.ovf_count, 1)] = qi;
-    return;
-  }
-  for (int i = warp; i < keep; i += kRescoreThreads / 32) {
-    const float4* row = reinterpret_cast<const float4*>(p.x + (size_t)s[i].id * 768);
-    float a = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const float4 xv = ld_stream_f4(row + j * 32 + lane);
-      const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
-      a = fmaf(xv.x, qv.x, a);
-      a = fmaf(xv.y, qv.y, a);
-      a = fmaf(xv.z, qv.z, a);
-      a = fmaf(xv.w, qv.w, a);
-    }
-    a = warp_sum(a);
-    if (lane == 0) s[i].key = a;
-  }
-  int n2 = 32;
-  while (n2 < keep) n2 <<= 1;
-  __syncthreads();
-  for (int i = keep + tid; i < n2; i += kRescoreThreads) {
-    s[i].key = -INFINITY;
-    s[i].id = kEmptyId;
-  }
-  bitonic_sort_desc(s, n2, tid, kRescoreThreads);
-  for (int i = tid; i < p.k; i += kRescoreThreads) {
-    const bool empty = s[i].id == kEmptyId;
-    p.D[(size_t)qi * p.k + i] = empty ? -FLT_MAX : s[i].key;
-    p.I[(size_t)qi * p.k + i] = empty ? (int64_t)-1 : (int64_t)s[i].id + p.id_offset;
-  }
-}
-
-// ------------------------------------------------------------------------
 // S1: append rows.  One warp per row: optional L2 normalisation with the
 // reference's epsilon (x / (||x|| + 1e-8)), fp32 store + bf16 shadow store.
 // ------------------------------------------------------------------------
 static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t n, int d, int normalize,
                                    float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16,
-                                   float* __restrict__ max_norm) {
+                                   float* __restrict__ max_norm, float* __restrict__ max_err) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -610,15 +839,25 @@ static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t
     denom = nrm + 1e-8f;
     nrm = nrm / denom;
   }
-  // largest stored row norm: the batched search derives its bf16 error bound from it
-  // (non-negative floats order like their bit patterns)
-  if (lane == 0 && max_norm && nrm == nrm) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm * 1.0001f));
+  float es = 0.f;   // ||v - bf16(v)||^2 of the stored row
   for (int j = lane; j < d; j += 32) {
     // numpy computes x / (norm + 1e-8); a true division keeps the last bit identical
     float v = normalize ? s[j] / denom : s[j];
-    dst[row * d + j] = v;
-    if (dst_bf16) dst_bf16[row * d + j] = __float2bfloat16_rn(v);
+    if (dst != src || normalize) dst[row * d + j] = v;
+    if (dst_bf16) {
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      dst_bf16[row * d + j] = b;
+      const float e = v - __bfloat162float(b);   // exact in fp32
+      es = fmaf(e, e, es);
+    }
   }
+  es = warp_sum(es);
+  // largest stored row norm and largest bf16 rounding-error norm: the error bounds of the two-phase scan
+  // and of the batched search derive from them (non-negative floats order like their bit patterns;
+  // the 1.0001 covers the rounding of the fp32 sums, non-finite rows poison neither)
+  if (lane == 0 && max_norm && nrm == nrm) atomicMax(reinterpret_cast<int*>(max_norm), __float_as_int(nrm * 1.0001f));
+  if (lane == 0 && max_err && es == es && es < INFINITY)
+    atomicMax(reinterpret_cast<int*>(max_err), __float_as_int(sqrtf(es) * 1.0001f));
 }
 
 // ------------------------------------------------------------------------
@@ -674,6 +913,18 @@ static __global__ void set_bits_kernel(uint32_t* bits, int64_t start, int64_t n,
   uint32_t m = (hi >= 32 ? 0xffffffffu : ((1u << hi) - 1u)) & ~((lo == 0) ? 0u : ((1u << lo) - 1u));
   if (value) atomicOr(bits + word, m);
   else atomicAnd(bits + word, ~m);
+}
+
+// Set / clear the bits of n listed rows (HybridStorage._kill_rows: one call per deletion batch).
+static __global__ void set_bits_by_id_kernel(uint32_t* bits, const int64_t* __restrict__ ids, int64_t n, int64_t limit,
+                                             int value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t row = ids[i];
+  if (row < 0 || row >= limit) return;
+  const uint32_t bit = 1u << (row & 31);
+  if (value) atomicOr(bits + (row >> 5), bit);
+  else atomicAnd(bits + (row >> 5), ~bit);
 }
 
 // alive bytes (0/1 per row) -> bits

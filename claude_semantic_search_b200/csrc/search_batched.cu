@@ -14,9 +14,11 @@
 //   4. the final kernel re-scores the surviving candidates in fp32 with the arithmetic of the
 //      streaming scan (bit-identical scores to the batch-1 path) and writes the top-k.
 //
-// Exactness.  bf16 rounding of both operands perturbs a score by at most
-//   eps_q = 2^-8 * 1.05 * ||q|| * max_row_norm          (|x.q| <= ||x|| ||q||, u = 2^-9)
-// so every row of the true top-k has a bf16 score >= (true k-th bf16 score) - 2 eps_q, which
+// Exactness.  With xb = bf16(x), qb = bf16(q):  x.q - xb.qb = (x - xb).qb + x.(q - qb), so
+//   |x.q - xb.qb| <= max_err ||qb|| + max_norm ||q - qb||  (+ fp32 summation, d 1.3e-7 max_norm ||q||) =: eps_q
+// with max_err the largest ||x - bf16(x)|| of any stored row (tracked exactly at add time; the worst
+// case of round-to-nearest with bf16's 8-bit significand is 2^-8 ||x||) and ||q - qb|| computed per
+// query.  Every row of the true top-k has a bf16 score >= (true k-th bf16 score) - 2 eps_q, which
 // is never below the running threshold: no true neighbour is ever filtered.  A candidate
 // list that would exceed its capacity flags the query, and flagged queries are re-run by
 // the exact streaming scan (never truncated silently).
@@ -45,7 +47,7 @@ struct Cand {
 struct BatchedState {
   int max_nq = 0;
   __nv_bfloat16* qb = nullptr;   // [max_nq, dim] bf16 queries
-  float* qnorm = nullptr;        // [max_nq]
+  float* qnorm = nullptr;        // [3][nq]: ||q||, ||bf16(q)||, ||q - bf16(q)|| (stride = the chunk's nq)
   float* thr = nullptr;          // [max_nq] threshold of the current pass
   unsigned* count = nullptr;     // [max_nq]
   Cand* cand = nullptr;          // [max_nq][kCap]
@@ -63,15 +65,23 @@ __global__ void prep_queries_kernel(const float* __restrict__ q, int nq, int d, 
   if (blockIdx.x == 0 && threadIdx.x == 0) *ovf_count = 0;
   if (qi >= nq) return;
   const float* src = q + (size_t)qi * d;
-  float ss = 0.f;
+  float ss = 0.f, sb = 0.f, se = 0.f;
   for (int j = lane; j < d; j += 32) {
     const float v = src[j];
     ss = fmaf(v, v, ss);
-    qb[(size_t)qi * d + j] = __float2bfloat16_rn(v);
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    qb[(size_t)qi * d + j] = b;
+    const float bv = __bfloat162float(b), e = v - bv;
+    sb = fmaf(bv, bv, sb);
+    se = fmaf(e, e, se);
   }
   ss = warp_sum(ss);
+  sb = warp_sum(sb);
+  se = warp_sum(se);
   if (lane == 0) {
     qnorm[qi] = sqrtf(ss);
+    qnorm[nq + qi] = sqrtf(sb) * 1.0001f;   // ||bf16(q)||
+    qnorm[2 * nq + qi] = sqrtf(se) * 1.0001f;   // ||q - bf16(q)||
     thr[qi] = -INFINITY;
     count[qi] = 0;
     ovf_flag[qi] = 0;
@@ -200,8 +210,9 @@ struct SelectParams {
   const float* q;       // fp32 queries [nq, d]
   int d;
   int k;
-  float eps_scale;      // 2^-8 * 1.05
+  int nq;               // stride of the qnorm planes
   const float* max_norm;
+  const float* max_err;
   const float* qnorm;
   float* thr;
   unsigned* count;
@@ -209,7 +220,7 @@ struct SelectParams {
   int* ovf_flag;
   int* ovf_list;
   int* ovf_count;
-  int64_t id_offset;
+  IdMap idmap;
   float* D;
   int64_t* I;
   int seed;             // 1: this call follows the seed pass -> only the threshold survives
@@ -245,7 +256,10 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
     s[i] = c;
   }
   sort_cands(s, n_sort, tid);
-  const float eps = p.eps_scale * p.qnorm[qi] * (*p.max_norm);
+  const float mn = *p.max_norm;
+  // last term: fp32 accumulation of d products on the tensor cores (truncating adds: <= d 2^-23 sum|x_i q_i|) and in the re-score
+  const float eps = 1.001f * (*p.max_err) * p.qnorm[p.nq + qi] + mn * p.qnorm[2 * p.nq + qi] +
+                    (float)p.d * 1.3e-7f * mn * p.qnorm[qi];
   float thr = -INFINITY;
   if ((int)cnt >= p.k) thr = s[p.k - 1].score - 2.f * eps;
   // survivors: sorted prefix with score >= thr
@@ -310,7 +324,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(SelectParams p) {
   for (int i = tid; i < p.k; i += kSelThreads) {
     const bool filled = i < keep && s[i].row != INT_MAX;
     p.D[(size_t)qi * p.k + i] = filled ? s[i].score : -FLT_MAX;
-    p.I[(size_t)qi * p.k + i] = filled ? (int64_t)s[i].row + p.id_offset : (int64_t)-1;
+    p.I[(size_t)qi * p.k + i] = filled ? (int64_t)map_id(p.idmap, s[i].row) : (int64_t)-1;
   }
 }
 
@@ -322,15 +336,15 @@ int64_t env_rows(const char* name, int64_t dflt) {
   return x >= 2048 ? (int64_t)(x / 256 * 256) : dflt;
 }
 
-int ensure_state(css_index* h, int nq) {
-  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+int ensure_state(css_index* h, css_scan_scratch* sc, int nq) {
+  BatchedState* st = reinterpret_cast<BatchedState*>(sc->batched);
   if (!st) {
     st = new (std::nothrow) BatchedState();
     if (!st) {
       set_error("out of host memory");
       return CSS_ERR_OOM;
     }
-    h->batched = st;
+    sc->batched = st;
   }
   if (nq <= st->max_nq) return CSS_OK;
   cudaFree(st->qb); cudaFree(st->qnorm); cudaFree(st->thr); cudaFree(st->count); cudaFree(st->cand);
@@ -347,7 +361,7 @@ int ensure_state(css_index* h, int nq) {
     return (int)CSS_OK;
   };
   CSS_CHECK(A((void**)&st->qb, n * h->dim * 2));
-  CSS_CHECK(A((void**)&st->qnorm, n * 4));
+  CSS_CHECK(A((void**)&st->qnorm, n * 12));
   CSS_CHECK(A((void**)&st->thr, n * 4));
   CSS_CHECK(A((void**)&st->count, n * 4));
   CSS_CHECK(A((void**)&st->cand, n * kCap * sizeof(Cand)));
@@ -378,13 +392,13 @@ int launch_fallback(css_index* h, const ScanParams& p, cudaStream_t st) {
 
 }  // namespace
 
-int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev, int64_t id_offset,
-                   float* D_dev, int64_t* I_dev, cudaStream_t stream) {
+int batched_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
+                   const IdMap& idmap, float* D_dev, int64_t* I_dev, cudaStream_t stream) {
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
   CSS_REQUIRE(h->dim % gemm::BK == 0, "batched search needs dim %% 64 == 0");
-  CSS_CHECK(ensure_state(h, std::min(nq, kQChunk)));
-  CSS_CHECK(ensure_query_scratch(h, std::min(nq, kQChunk)));
-  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+  CSS_REQUIRE(sc->max_nq >= std::min(nq, kQChunk), "scratch too small");
+  CSS_CHECK(ensure_state(h, sc, std::min(nq, kQChunk)));
+  BatchedState* st = reinterpret_cast<BatchedState*>(sc->batched);
   const int d = h->dim;
   const int64_t N = h->ntotal;
 
@@ -399,8 +413,9 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
     sp.q = qc;
     sp.d = d;
     sp.k = k;
-    sp.eps_scale = 1.05f / 256.f;
+    sp.nq = nqc;
     sp.max_norm = h->max_norm_dev;
+    sp.max_err = h->max_err_dev;
     sp.qnorm = st->qnorm;
     sp.thr = st->thr;
     sp.count = st->count;
@@ -408,7 +423,7 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
     sp.ovf_flag = st->ovf_flag;
     sp.ovf_list = st->ovf_list;
     sp.ovf_count = st->ovf_count;
-    sp.id_offset = id_offset;
+    sp.idmap = idmap;
     sp.D = D_dev + (size_t)q0 * k;
     sp.I = I_dev + (size_t)q0 * k;
     sp.seed = 0;
@@ -458,18 +473,17 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
 
     // overflowed queries (if any): exact streaming scan, driven by the device-side list
     ScanParams p;
+    memset(&p, 0, sizeof(p));
     p.x = h->x;
-    p.xb = nullptr;
-    p.no_merge = 0;
-    p.zero_on_entry = nullptr;
     p.n = N;
     p.d = d;
     p.q = qc;
     p.mask = mask_dev;
     p.k = k;
-    p.part = h->part;
-    p.ticket = h->ticket;
-    p.id_offset = id_offset;
+    p.k_out = k;
+    p.part = sc->part;
+    p.ticket = sc->ticket;
+    p.idmap = idmap;
     p.D = sp.D;
     p.I = sp.I;
     p.qlist = st->ovf_list;
@@ -481,13 +495,13 @@ int batched_search(css_index* h, const float* q_dev, int nq, int k, const uint32
   return CSS_OK;
 }
 
-void batched_release(css_index* h) {
-  BatchedState* st = reinterpret_cast<BatchedState*>(h->batched);
+void batched_release(css_scan_scratch* sc) {
+  BatchedState* st = reinterpret_cast<BatchedState*>(sc->batched);
   if (!st) return;
   cudaFree(st->qb); cudaFree(st->qnorm); cudaFree(st->thr); cudaFree(st->count); cudaFree(st->cand);
   cudaFree(st->ovf_flag); cudaFree(st->ovf_list); cudaFree(st->ovf_count);
   delete st;
-  h->batched = nullptr;
+  sc->batched = nullptr;
 }
 
 }  // namespace css

@@ -26,11 +26,11 @@ class Index:
 
     metric_type = METRIC_INNER_PRODUCT
 
-    def __init__(self, d: int, metric: int, device: int = 0):
+    def __init__(self, d: int, metric: int, device: int = 0, devices=None):
         self.d = int(d)
         self.metric_type = metric
         self.is_trained = True
-        self._native = _native.Index(self.d, metric, device)
+        self._native = _native.Index(self.d, metric, device, devices=devices)
 
     @property
     def ntotal(self) -> int:
@@ -46,10 +46,7 @@ class Index:
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 2 or x.shape[1] != self.d:
             raise AssertionError(f"search expects [nq, {self.d}] float32")
-        k = int(k)
-        if k <= _native.MAX_K:
-            return self._native.search(x, k)
-        raise NotImplementedError(f"k={k} > {_native.MAX_K}")
+        return self._native.search(x, int(k))   # k > CSS_MAX_K: repeated exact passes (see _native.Index)
 
     def reset(self) -> None:
         self._native.reset()
@@ -66,13 +63,13 @@ class IndexFlat(Index):
 
 
 class IndexFlatIP(IndexFlat):
-    def __init__(self, d: int, device: int = 0):
-        super().__init__(d, METRIC_INNER_PRODUCT, device)
+    def __init__(self, d: int, device: int = 0, devices=None):
+        super().__init__(d, METRIC_INNER_PRODUCT, device, devices)
 
 
 class IndexFlatL2(IndexFlat):
-    def __init__(self, d: int, device: int = 0):
-        super().__init__(d, METRIC_L2, device)
+    def __init__(self, d: int, device: int = 0, devices=None):
+        super().__init__(d, METRIC_L2, device, devices)
 
 
 class IndexIVFFlat(Index):
@@ -89,14 +86,14 @@ def write_index(index: Index, path: str) -> None:
     index._native.save(path)
 
 
-def read_index(path: str, device: int = 0) -> Index:
+def read_index(path: str, device: int = 0, devices=None) -> Index:
     # peek at fourcc + d to build the right class (faiss IndexFlat header)
     with open(path, "rb") as fh:
         head = fh.read(8)
     if len(head) < 8 or head[:4] not in (b"IxFI", b"IxF2"):
         raise RuntimeError(f"{path}: not a flat faiss index")
     d = int(np.frombuffer(head[4:8], dtype=np.int32)[0])
-    idx = IndexFlatIP(d, device) if head[:4] == b"IxFI" else IndexFlatL2(d, device)
+    idx = IndexFlatIP(d, device, devices) if head[:4] == b"IxFI" else IndexFlatL2(d, device, devices)
     idx._native.load(path)
     return idx
 

@@ -435,6 +435,14 @@ class ColumnStore:
             codec.append([m.get(codec.name) for m in metas])
         self.n += len(metas)
 
+    def append_columns(self, n: int, columns: Dict[str, Sequence[Any]]) -> None:
+        """Column-wise append of n rows (index reload: one SELECT, no per-row dict); a column that is
+        missing from `columns` is NULL for these rows."""
+        for codec in self.codecs:
+            vals = columns.get(codec.name)
+            codec.append(list(vals) if vals is not None else [None] * n)
+        self.n += n
+
     def set_row(self, row: int, meta: Dict[str, Any], index: Optional[_native.Index]) -> None:
         for ci, codec in enumerate(self.codecs):
             codec.set_row(row, meta.get(codec.name))

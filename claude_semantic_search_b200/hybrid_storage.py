@@ -56,6 +56,7 @@ class StorageConfig:
     use_gpu: bool = False
     gpu_memory_fraction: float = 0.8
     device: int = 0
+    devices: Optional[List[int]] = None  # several GPUs of this box: ONE index row-sharded over them (css_index_create_sharded)
     filter_mode: str = "prefilter"  # "prefilter" | "reference"
 
 
@@ -160,7 +161,7 @@ class HybridStorage:
         kind = self.config.index_type
         if kind == "flat":
             cls = faiss_compat.IndexFlatIP if self.config.normalize_embeddings else faiss_compat.IndexFlatL2
-            return cls(self.embedding_dim, self.config.device)
+            return cls(self.embedding_dim, self.config.device, devices=self.config.devices)
         if kind in ("ivf", "hnsw"):
             raise NotImplementedError(f"index_type={kind!r}: only the flat index is served by the B200 path")
         raise ValueError(f"Unknown index type: {kind}")
@@ -207,16 +208,28 @@ class HybridStorage:
         self._columns.reset()
         if n == 0:
             return
-        metas: List[Dict[str, Any]] = [{} for _ in range(n)]
+        # one SELECT, transposed at C speed; no per-row Python work (the reload of a 10 M-row index would
+        # otherwise spend minutes here)
+        q = f"SELECT faiss_id, {', '.join(_META_COLS)} FROM chunks WHERE faiss_id IS NOT NULL ORDER BY faiss_id"
+        rows = self.db.execute(q).fetchall()
         alive = np.zeros(n, dtype=np.uint8)
-        q = f"SELECT faiss_id, {', '.join(_META_COLS)} FROM chunks WHERE faiss_id IS NOT NULL"
-        for row in self.db.execute(q):
-            fid = row[0]
-            if fid is None or not (0 <= fid < n):
-                continue
-            metas[fid] = {name: row[i + 1] for i, name in enumerate(_META_COLS)}
-            alive[fid] = 1
-        self._columns.append_rows(metas)
+        columns: Dict[str, Any] = {}
+        if rows:
+            cols = list(zip(*rows))
+            fids = np.asarray(cols[0], dtype=np.int64)
+            ok = (fids >= 0) & (fids < n)
+            dense = bool(ok.all()) and fids.shape[0] == n and bool((fids == np.arange(n)).all())
+            alive[fids[ok]] = 1
+            for i, name in enumerate(_META_COLS):
+                if dense:
+                    columns[name] = cols[i + 1]
+                else:
+                    vals = np.empty(n, dtype=object)      # None = SQL NULL for the orphaned rows
+                    src = np.empty(len(rows), dtype=object)
+                    src[:] = cols[i + 1]
+                    vals[fids[ok]] = src[ok]
+                    columns[name] = vals.tolist()
+        self._columns.append_columns(n, columns)
         self._columns.sync(self.faiss_index._native)
         if not alive.all():
             self.faiss_index._native.set_alive(alive, 0)
@@ -238,20 +251,20 @@ class HybridStorage:
             x = np.stack(embs)   # ndarray rows (EmbeddingConfig.embedding_as_ndarray): one 3 KB memcpy per chunk
         else:
             x = np.asarray(embs, dtype=np.float32)
-        # normalisation x / (||x|| + 1e-8) happens on the device (S1)
-        first = self.faiss_index._native.add(x, normalize=self.config.normalize_embeddings)
-
+        # SQLite rows and metadata first (json.dumps may raise): nothing has touched the device yet
+        native = self.faiss_index._native
+        first = native.ntotal
         now = datetime.now().isoformat()
         rows, metas = [], []
         rebinds = []
+        new_ids: Dict[str, int] = {}
         for i, c in enumerate(todo):
             fid = first + i
             md = c.metadata
-            old = self.chunk_id_to_faiss_id.get(c.id)
+            old = new_ids.get(c.id, self.chunk_id_to_faiss_id.get(c.id))
             if old is not None and old != fid:
                 rebinds.append((old, md))
-            self.chunk_id_to_faiss_id[c.id] = fid
-            self.faiss_id_to_chunk_id[fid] = c.id
+            new_ids[c.id] = fid
             meta_row = {
                 "session_id": md.get("session_id"), "project_name": md.get("project_name"),
                 "file_path": md.get("file_path"), "chunk_type": md.get("chunk_type"),
@@ -261,10 +274,25 @@ class HybridStorage:
             }
             metas.append(meta_row)
             rows.append((c.id, c.text, json.dumps(md), fid, *[meta_row[k] for k in _META_COLS], now))
-        self.db.executemany(
-            "INSERT OR REPLACE INTO chunks (id, text, metadata, faiss_id, " + ", ".join(_META_COLS) +
-            ", updated_at) VALUES (" + ", ".join("?" * (5 + len(_META_COLS))) + ")", rows)
-        self.db.commit()
+        # normalisation x / (||x|| + 1e-8) happens on the device (S1)
+        got = native.add(x, normalize=self.config.normalize_embeddings)
+        assert got == first, (got, first)
+        try:
+            self.db.executemany(
+                "INSERT OR REPLACE INTO chunks (id, text, metadata, faiss_id, " + ", ".join(_META_COLS) +
+                ", updated_at) VALUES (" + ", ".join("?" * (5 + len(_META_COLS))) + ")", rows)
+            self.db.commit()
+        except Exception:
+            # the vectors are on the device but their rows are not in SQLite: keep the device columns
+            # aligned with the vector rows (NULL metadata) and orphan the rows, like a deleted chunk
+            self.db.rollback()
+            self._columns.append_rows([{} for _ in todo])
+            native.set_alive_ids(np.arange(first, first + len(todo), dtype=np.int64), False)
+            raise
+        for cid, fid in new_ids.items():
+            self.chunk_id_to_faiss_id[cid] = fid
+        for i, c in enumerate(todo):
+            self.faiss_id_to_chunk_id[first + i] = c.id
         self._columns.append_rows(metas)
         # a re-added chunk id keeps its old faiss row bound to the (replaced) SQLite row in the
         # reference: mirror by giving the old row the new metadata
@@ -324,7 +352,7 @@ class HybridStorage:
             pairs = self._search_reference_mode(native, q, k_ref, cfg, filters)
         else:
             flt = self._compile_filter(filters)
-            k = min(cfg.top_k, _native.MAX_K, n)
+            k = min(cfg.top_k, n)   # top_k > CSS_MAX_K: repeated exact passes inside _native.Index.search
             D, I = native.search(q, k, flt)
             pairs = [(int(i), float(d)) for d, i in zip(D[0], I[0])
                      if i >= 0 and float(d) >= cfg.similarity_threshold]
@@ -374,7 +402,6 @@ class HybridStorage:
     def _search_reference_mode(self, native, q, k_ref, cfg, filters):
         """R = (global top-k' incl. orphans) walked best-first with threshold, orphan and
         filter checks: the reference's exact result (src/storage.py:432-490)."""
-        k_ref = min(k_ref, _native.MAX_K)
         raw = _native.Filter(ignore_alive=True)
         D, I = native.search(q, k_ref, raw)
         words = None
@@ -452,11 +479,8 @@ class HybridStorage:
         """Orphaned vectors stay in the index (as in faiss) but are masked out."""
         if not faiss_ids or not self.faiss_index:
             return
-        native = self.faiss_index._native
-        zero = np.zeros(1, dtype=np.uint8)
-        for fid in faiss_ids:
-            if 0 <= fid < native.ntotal:
-                native.set_alive(zero, fid)
+        # one device call for the whole batch (css_index_set_alive_ids)
+        self.faiss_index._native.set_alive_ids(np.asarray(faiss_ids, dtype=np.int64), False)
 
     def delete_chunk(self, chunk_id: str) -> bool:
         fid = self.chunk_id_to_faiss_id.get(chunk_id)
@@ -622,7 +646,7 @@ class HybridStorage:
         src = Path(backup_dir)
         idx = src / self.config.index_name
         if idx.exists():
-            self.faiss_index = faiss_compat.read_index(str(idx), self.config.device)
+            self.faiss_index = faiss_compat.read_index(str(idx), self.config.device, self.config.devices)
             self._disk_appendable = False
         dbf = src / self.config.db_name
         if dbf.exists():

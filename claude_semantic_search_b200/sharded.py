@@ -2,9 +2,13 @@
 `torch.distributed` for the plumbing.
 
   * search: the corpus is row-sharded contiguously (global id = id_offset + local row),
-    queries are replicated, every rank scans its shard (css_index_search_device), the local
-    top-k lists (k x 12 B per query and rank) are all-gathered and merged on every rank
-    (css_topk_merge_device).  One exchange step, no other collective.
+    queries are replicated, every rank scans its shard.  One exchange step, no other collective:
+      - nq <= 64 (streaming scan): the exchange is fused into the scan kernel
+        (css_index_search_exchange_device): the CTA that finishes the local top-k stores it into
+        every peer's memory over NVLink (CUDA IPC mappings, set up once with one all-gather of the
+        64-byte handles), waits for the peers' lists and merges -- no NCCL call, no extra launch;
+      - larger batches (tensor-core path): one all-gather of the packed lists (k x 12 B per query and
+        rank) + css_topk_merge_device on every rank.
   * encode: sequences are split contiguously across ranks; no collective (each rank's rows
     can be appended to its own corpus shard).
 """
@@ -53,8 +57,37 @@ class ShardedSearch:
         self.id_offset = int(id_offset)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        # CSS_EXCHANGE=nccl keeps the all-gather + merge-kernel exchange for every nq
+        import os
+        self.use_exchange = os.environ.get("CSS_EXCHANGE", "p2p") != "nccl"
         self.local_search = local_search  # CPU/gloo tests inject a host search; None = the device index
         self._bufs = {}
+        self._ex = None
+        self._pin = {}
+
+    def _exchange(self):
+        """The in-kernel exchange of this rank, connected to all peers on first use (NCCL groups only)."""
+        if self._ex is None:
+            import torch
+            ex = _native.Exchange(self.index.device, self.world, self.dist.get_rank(self.group))
+            dev = torch.device("cuda", self.index.device)
+            mine = torch.frombuffer(bytearray(ex.handle), dtype=torch.uint8).to(dev)
+            allh = torch.empty(self.world * _native.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            self.dist.all_gather_into_tensor(allh, mine, group=self.group)
+            blob = bytes(allh.cpu().numpy().tobytes())
+            ex.connect([blob[i * _native.IPC_HANDLE_BYTES:(i + 1) * _native.IPC_HANDLE_BYTES] for i in range(self.world)])
+            self.dist.barrier(group=self.group)
+            self._ex = ex
+        return self._ex
+
+    def close(self):
+        if self._ex is not None:
+            import torch
+            torch.cuda.synchronize(self.index.device)
+            if self.dist.is_initialized():
+                self.dist.barrier(group=self.group)   # nobody unmaps memory a peer's kernel may still write
+            self._ex.close()
+            self._ex = None
 
     def _device_bufs(self, torch, dev, nq, k):
         key = (nq, k)
@@ -68,8 +101,9 @@ class ShardedSearch:
                 loc=loc, all=allb, stride=stride, d_bytes=d_bytes,
                 D_loc=loc[:nq * k * 4].view(torch.float32).view(nq, k),
                 I_loc=loc[d_bytes:].view(torch.int64).view(nq, k),
-                D_out=torch.empty((nq, k), device=dev, dtype=torch.float32),
-                I_out=torch.empty((nq, k), device=dev, dtype=torch.int64))
+                outp=(outp := torch.empty(stride, device=dev, dtype=torch.uint8)),   # merged result, same packing
+                D_out=outp[:nq * k * 4].view(torch.float32).view(nq, k),
+                I_out=outp[d_bytes:].view(torch.int64).view(nq, k))
         return self._bufs[key]
 
     def search_device(self, q, k: int, mask_ptr: int = 0):
@@ -80,6 +114,10 @@ class ShardedSearch:
         nq = q.shape[0]
         b = self._device_bufs(torch, dev, nq, k)
         sp = torch.cuda.current_stream(dev).cuda_stream
+        if self.world > 1 and self.use_exchange and nq <= _native.EXCHANGE_MAX_NQ:
+            self.index.search_exchange_device(self._exchange(), q.data_ptr(), nq, k, b["D_out"].data_ptr(),
+                                              b["I_out"].data_ptr(), mask_ptr, self.id_offset, sp)
+            return b["D_out"], b["I_out"]
         self.index.search_device(q.data_ptr(), nq, k, b["D_loc"].data_ptr(), b["I_loc"].data_ptr(), mask_ptr,
                                  self.id_offset, sp)
         if self.world == 1:
@@ -96,10 +134,25 @@ class ShardedSearch:
         import torch
         q = np.ascontiguousarray(q, np.float32).reshape(-1, q.shape[-1])
         if self.local_search is None and self.world > 1 and self.dist.get_backend(self.group) == "nccl":
+            # one pinned block per (nq, k): query in, [scores | ids] out -- one H2D, one D2H, one sync
             dev = torch.device("cuda", self.index.device)
-            qd = torch.from_numpy(q).to(dev, non_blocking=True)
-            D, I = self.search_device(qd, k)
-            return D.cpu().numpy(), I.cpu().numpy()
+            nq = q.shape[0]
+            key = (nq, k, q.shape[1])
+            b = self._device_bufs(torch, dev, nq, k)
+            if key not in self._pin:
+                self._pin[key] = dict(
+                    q=torch.empty((nq, q.shape[1]), dtype=torch.float32).pin_memory(),
+                    qd=torch.empty((nq, q.shape[1]), dtype=torch.float32, device=dev),
+                    out=torch.empty(b["stride"], dtype=torch.uint8).pin_memory())
+            pb = self._pin[key]
+            pb["q"].numpy()[...] = q
+            pb["qd"].copy_(pb["q"], non_blocking=True)
+            self.search_device(pb["qd"], k)          # merged lists land in b["outp"] (scores | ids)
+            pb["out"].copy_(b["outp"], non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            o = pb["out"].numpy()
+            return (o[:nq * k * 4].view(np.float32).reshape(nq, k).copy(),
+                    o[b["d_bytes"]:].view(np.int64).reshape(nq, k).copy())
         if self.local_search is not None:
             D, I = self.local_search(q, k)
         else:

@@ -14,7 +14,10 @@
  *   - "_device" variants take device pointers + a CUDA stream (as void*) and do
  *     not synchronise; the plain variants take HOST buffers, copy in/out and
  *     return when the result is in the host buffer.
- *   - handles are internally locked: add/save/reset exclude search.
+ *   - handles are internally locked: add/save/reset exclude search.  "_device" searches issued on
+ *     different streams use separate scratch buffers and may overlap on the device.
+ *   - a shard (one device) holds fewer than 2^31 rows: row ids are 32-bit inside the kernels and
+ *     widened (+ id_offset / the multi-device id map) on output.
  *   - there is no CPU fallback: without an sm_100 device every compute entry
  *     point fails with CSS_ERR_NO_DEVICE.
  *
@@ -77,6 +80,16 @@ typedef struct css_index css_index;
 #define CSS_MAX_CLAUSES 16
 
 int css_index_create(int dim, int metric, int device, css_index** out);
+/* The same index row-sharded over n_dev GPUs of this box inside ONE process (north_star: the corpus
+ * sharded over the 8 GPUs behind the unchanged HybridStorage API; the reference hard-codes device 0,
+ * src/storage.py:269-284).  Every css_index_* entry point below works on the returned handle except the
+ * "_device" variants: rows are dealt to the devices in 4096-row blocks (ids stay dense and append-only),
+ * a search runs on all devices at once and the per-device top-k lists are merged inside the scan
+ * kernels over NVLink peer memory (no NCCL, no extra launch); css_index_compact resets alive bits and
+ * metadata columns (re-upload them afterwards). */
+#define CSS_MAX_RANKS 8
+int css_index_create_sharded(int dim, int metric, const int* devices, int n_dev, css_index** out);
+int css_index_n_devices(const css_index* h);
 int css_index_destroy(css_index* h);
 int css_index_dim(const css_index* h);
 int css_index_metric(const css_index* h);
@@ -113,6 +126,9 @@ int css_index_set_column(css_index* h, int column, const int32_t* values_host,
  * whose chunk was deleted/re-indexed are orphans in the reference
  * (src/storage.py:449-451,836-846) and are cleared here. */
 int css_index_set_alive(css_index* h, const uint8_t* alive_host, int64_t start, int64_t n);
+/* The same for a list of row ids in ONE device call (remove_chunks_for_file / delete_chunks_by_session,
+ * src/storage.py:817-846: hundreds of orphaned rows per file); ids outside [0, ntotal) are ignored. */
+int css_index_set_alive_ids(css_index* h, const int64_t* ids_host, int64_t n, int alive);
 
 typedef enum css_clause_kind {
   CSS_CLAUSE_RANGE = 0, /* lo <= v <= hi (inclusive, on the int32 column value) */
@@ -147,7 +163,8 @@ int css_index_filter_mask(css_index* h, const css_filter* f, uint32_t* mask_out_
  * both HOST.  Rows are ordered best first (IP: score descending; L2: squared
  * distance ascending), ties broken by ascending id; unfilled slots carry
  * id -1 and score -FLT_MAX (IP) / FLT_MAX (L2) like faiss.
- * nq < CSS_BATCH_MIN_NQ runs the HBM-bound fp32 streaming scan; larger batches
+ * nq < CSS_BATCH_MIN_NQ runs the HBM-bound streaming scan (inner product, d = 768, k <= 32: the two-phase
+ * exact scan -- bf16 shadow sweep, proof, fp32 re-score -- otherwise one fp32 sweep); larger batches
  * run the tcgen05 score GEMM with in-epilogue candidate selection followed by
  * an exact fp32 re-score of the candidates. */
 int css_index_search(css_index* h, const float* q_host, int nq, int k,
@@ -160,6 +177,28 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k,
 int css_index_search_device(css_index* h, const float* q_dev, int nq, int k,
                             const uint32_t* mask_dev, int64_t id_offset,
                             float* D_dev, int64_t* I_dev, void* stream);
+/* Result exchange between the row shards of one search, fused into the scan kernel (SURVEY 8e's one
+ * exchange step without NCCL): every rank creates one css_exchange on its GPU, the ranks all-gather the
+ * CSS_IPC_HANDLE_BYTES-byte handles (rank order) and connect.  css_index_search_exchange_device is then
+ * a COLLECTIVE: every rank calls it with the same queries / nq / k in the same order; the CTA that
+ * finishes a query's local top-k stores it into every peer's memory over NVLink, waits for the peers'
+ * lists and merges, so D_dev / I_dev hold the merged GLOBAL top-k on every rank when the kernel ends.
+ * nq <= 64 (streaming-scan sizes; larger batches gather their lists with NCCL + css_topk_merge_device). */
+typedef struct css_exchange css_exchange;
+#define CSS_IPC_HANDLE_BYTES 64
+int css_exchange_create(int device, int n_ranks, int rank, css_exchange** out,
+                        unsigned char* handle_out /* CSS_IPC_HANDLE_BYTES, nullable */);
+int css_exchange_connect(css_exchange* ex, const unsigned char* handles /* n_ranks x CSS_IPC_HANDLE_BYTES */);
+int css_exchange_destroy(css_exchange* ex);
+int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float* q_dev, int nq, int k,
+                                     const uint32_t* mask_dev, int64_t id_offset, float* D_dev,
+                                     int64_t* I_dev, void* stream);
+
+/* Counters of the two-phase batch-1 scan since the index was created: out = {queries answered by it,
+ * queries it could not prove from the bf16 lists (re-run by the fp32 sweep), 1 if the adaptive switch
+ * currently bypasses it, largest ||x - bf16(x)|| of a stored row x 1e9}. */
+int css_index_scan_stats(css_index* h, int64_t out[4]);
+
 /* Evaluate a filter into the index's internal device mask and return its
  * device address (valid until the next call that changes the index/mask). */
 int css_index_filter_mask_device(css_index* h, const css_filter* f,

@@ -16,6 +16,7 @@ class _FakeNative:
         self.x = np.zeros((0, dim), np.float32)
         self.alive = np.zeros(0, bool)
         self.calls = 0
+        self.alive_calls = 0
 
     @property
     def ntotal(self):
@@ -33,6 +34,10 @@ class _FakeNative:
     def set_alive(self, alive, start=0):
         a = np.asarray(alive).astype(bool)
         self.alive[start:start + a.shape[0]] = a
+
+    def set_alive_ids(self, ids, alive):
+        self.alive_calls += 1
+        self.alive[np.asarray(ids, np.int64)] = bool(alive)
 
     def search(self, q, k, flt=None):
         self.calls += 1
@@ -103,8 +108,10 @@ def test_add_search_delete_roundtrip(storage, as_array):
     assert [r.chunk_id for r in cut] == [r.chunk_id for r in res[:5]]
     # deletions: the row is orphaned (alive bit cleared, maps updated), later hits move up
     assert storage.delete_chunk("c0042") and not storage.delete_chunk("c0042")
+    calls0 = storage.faiss_index._native.alive_calls
     removed = storage.remove_chunks_for_file("/f/3.jsonl")
     assert removed == 30
+    assert storage.faiss_index._native.alive_calls == calls0 + 1       # ONE device call for the 30 orphaned rows
     res2 = storage.search(q, SearchConfig(top_k=10))
     gone = {"c0042"} | {f"c{i:04d}" for i in range(300) if i % 10 == 3}
     want2 = [f"c{i:04d}" for i in np.argsort(-(x @ (q / (np.linalg.norm(q) + 1e-8))), kind="stable") if f"c{i:04d}" not in gone][:10]
