@@ -127,6 +127,7 @@ SIGNATURES = {
     "css_index_save": (c_int, [c_void_p, c_char_p]),
     "css_index_load": (c_int, [c_void_p, c_char_p]),
     "css_kernel_launch_count": (c_int64, []),
+    "css_set_option": (c_int, [c_char_p, c_int]),
     "css_mpnet_relative_bucket": (c_int, [c_int, c_int, c_int]),
     "css_encoder_create": (c_int, [POINTER(css_mpnet_config), POINTER(css_mpnet_weights), c_int, c_int64,
                                    POINTER(c_void_p)]),
@@ -205,6 +206,11 @@ def device_info(device: int = 0) -> dict:
     info = (c_int64 * 5)()
     check(load().css_device_info(device, info))
     return {"sm_count": info[0], "hbm_total": info[1], "hbm_free": info[2], "cc": (info[3], info[4])}
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide switch of libcss_b200 (css_set_option): scan_bf16, scan_interleave, scan_list, scan_adaptive."""
+    check(load().css_set_option(name.encode(), int(value)))
 
 
 def kernel_launch_count() -> int:

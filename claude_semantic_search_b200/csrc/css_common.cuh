@@ -69,6 +69,17 @@ struct DeviceGuard {
   }
 };
 
+// Process-wide switches, initialised from the environment (CSS_SCAN_BF16, CSS_SCAN_INTERLEAVE, CSS_SCAN_LIST,
+// CSS_SCAN_ADAPTIVE) and changeable at run time through css_set_option (benchmarks compare the paths in one run).
+struct Options {
+  std::atomic<int> scan_bf16{1};        // two-phase batch-1 scan (0: single fp32 sweep)
+  std::atomic<int> scan_interleave{1};  // dense bf16 sweep deals 8-row units block-cyclically
+  std::atomic<int> scan_list{0};        // per-block list length 32 | 64 (0: by k)
+  std::atomic<int> scan_adaptive{1};    // bypass phase 1 while most queries cannot be proven
+  std::atomic<int> scan_pdl{1};         // fp32-fallback launch as a programmatic dependent of the bf16 sweep
+};
+Options& options();
+
 int ensure_device(int device);  // CSS_OK iff `device` is an sm_100 GPU
 int sm_count(int device);
 

@@ -42,6 +42,7 @@ int exchange_next(css_exchange* ex, ExchangeDev* out) {
   out->epoch = ex->epoch;
   out->max_nq = ex->max_nq;
   out->status = ex->status;
+  out->no_pdl = ex->shared_device ? 1 : 0;
   for (int r = 0; r < ex->n_ranks; ++r) {
     out->slots[r] = ex->slots[r];
     out->flags[r] = ex->flags[r];
@@ -53,6 +54,7 @@ int exchange_connect_local(css_exchange** exs, int n) {
   for (int a = 0; a < n; ++a) {
     DeviceGuard g(exs[a]->device);
     for (int b = 0; b < n; ++b) {
+      if (a != b && exs[a]->device == exs[b]->device) exs[a]->shared_device = true;
       if (a == b || exs[a]->device == exs[b]->device) continue;
       int can = 0;
       CSS_CUDA(cudaDeviceCanAccessPeer(&can, exs[a]->device, exs[b]->device));

@@ -135,7 +135,21 @@ int launch_scan_kd(css_index* h, const ScanParams& p, int nq, cudaStream_t st) {
   if (d768) {
     auto kern = scan_topk_kernel<KPL, METRIC, true>;
     CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kScanThreads, smem, st>>>(p);
+    if (p.pdl_wait) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(kScanThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      CSS_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+    } else {
+      kern<<<grid, kScanThreads, smem, st>>>(p);
+    }
   } else {
     auto kern = scan_topk_kernel<KPL, METRIC, false>;
     CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -150,11 +164,6 @@ int launch_scan_m(css_index* h, const ScanParams& p, int nq, cudaStream_t st) {
   if (p.k <= 32) return launch_scan_kd<1, METRIC>(h, p, nq, st);
   if (p.k <= 64) return launch_scan_kd<2, METRIC>(h, p, nq, st);
   return launch_scan_kd<4, METRIC>(h, p, nq, st);
-}
-
-int env_int(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
 }
 
 // Compile a host css_filter into device FilterParams (uploads bitsets / row mask).
@@ -367,8 +376,8 @@ static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const
 static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
                          const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, int no_merge,
                          cudaStream_t st) {
-  static const int list_env = env_int("CSS_SCAN_LIST", 0);
-  static const int interleave = env_int("CSS_SCAN_INTERLEAVE", 1);
+  const int list_env = options().scan_list.load();
+  const int interleave = options().scan_interleave.load();
   const int kp = list_env == 32 || list_env == 64 ? list_env : (k <= 16 ? 32 : 64);
   ScanParams p;
   fill_common(h, sc, &p, q_dev, mask_dev, idmap, ex, D_dev, I_dev);
@@ -394,13 +403,14 @@ static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev,
 }
 
 int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
-                  const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st) {
+                  const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st, bool pdl_ok) {
   ScanParams f;
   fill_common(h, sc, &f, q_dev, mask_dev, idmap, ex, D_dev, I_dev);
   f.k = k;
   f.k_out = k;
   f.qlist = sc->ovf_list;
   f.qcount = sc->ovf_count;
+  f.pdl_wait = options().scan_pdl.load() != 0 && pdl_ok ? 1 : 0;
   // an empty list costs one idle launch; few slices: unproven queries are rare
   return launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, f, std::min(nq, 8), st);
 }
@@ -410,8 +420,7 @@ int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq
 // rounding error of each other), phase 1 is wasted work and the next calls go straight to the fp32 sweep,
 // with a new probe every 4096 queries.  Exactness never depends on this choice.
 static bool two_phase_wanted(css_index* h, int nq) {
-  static const bool adaptive = env_int("CSS_SCAN_ADAPTIVE", 1) != 0;
-  if (!adaptive || !h->stats_host) return true;
+  if (!options().scan_adaptive.load() || !h->stats_host) return true;
   if (h->skip_two_phase > 0) {
     h->skip_two_phase -= nq;
     return false;
@@ -434,13 +443,23 @@ int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, 
                 bool defer_fallback, bool* two_phase_used) {
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
   if (two_phase_used) *two_phase_used = false;
-  static const bool bf16_phase = env_int("CSS_SCAN_BF16", 1) != 0;
+  const bool bf16_phase = options().scan_bf16.load() != 0;
   if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK && nq <= 64 &&
-      h->ntotal > 0 && two_phase_wanted(h, nq)) {
+      h->ntotal > 0 && h->scan_blocks <= kTwoPhaseMaxBlocks && two_phase_wanted(h, nq)) {
+    // Exchange + several queries in one launch: a CTA that waited for its peers inside phase 1 would hold up the
+    // fallback launch behind it, which a peer's phase 1 may in turn be waiting for (query u unproven here, query v
+    // unproven there).  So with nq > 1 the producers only publish and the fallback launch awaits + merges.
+    ExchangeDev xd;
+    if (ex) {
+      xd = *ex;
+      xd.deferred = nq > 1 ? 1 : 0;
+      xd.nq = nq;
+      ex = &xd;
+    }
     CSS_CHECK(launch_phase1(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, 0, st));
     if (two_phase_used) *two_phase_used = true;
     if (defer_fallback) return CSS_OK;   // the caller reads the overflow count with the result
-    return scan_fallback(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, st);
+    return scan_fallback(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, st, /*pdl_ok=*/!(ex && ex->no_pdl));
   }
   // gridDim.y is limited to 65535; chunk the query batch
   const int chunk = 4096;
@@ -991,7 +1010,7 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   CSS_CUDA(cudaStreamSynchronize(st));
   if (two_phase && *reinterpret_cast<const int*>(pin + c_off) > 0) {
     // some queries could not be proven from the bf16 lists: the fp32 scan answers exactly those
-    CSS_CHECK(scan_fallback(h, sc, sc->q_dev, nq, k, m, index_idmap(h, 0), nullptr, sc->D_dev, I_dev, st));
+    CSS_CHECK(scan_fallback(h, sc, sc->q_dev, nq, k, m, index_idmap(h, 0), nullptr, sc->D_dev, I_dev, st, /*pdl_ok=*/false));
     CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
     CSS_CUDA(cudaStreamSynchronize(st));
   }

@@ -50,6 +50,7 @@ struct css_exchange {
   unsigned* flags[css::kMaxRanks] = {};
   bool opened[css::kMaxRanks] = {};  // peer mappings opened through CUDA IPC (to be closed)
   bool connected = false;
+  bool shared_device = false;        // another shard of this process lives on the same GPU
   std::mutex mu;
 };
 
@@ -114,7 +115,7 @@ int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, 
                 bool defer_fallback, bool* two_phase_used);
 // fp32 scan of the queries the two-phase scan queued (ovf_list of the scratch).
 int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
-                  const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st);
+                  const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st, bool pdl_ok);
 // tcgen05 batched search (search_batched.cu).
 int batched_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
                    const IdMap& idmap, float* D_dev, int64_t* I_dev, cudaStream_t st);

@@ -168,6 +168,11 @@ struct ExchangeDev {
   ExEntry* slots[kMaxRanks];    // slots[r]: receive area of rank r, [2][max_nq][n_ranks][CSS_MAX_K]
   unsigned* flags[kMaxRanks];   // flags[r]: flags of rank r, [2][max_nq][n_ranks]
   int* status;                  // local; 1 = a peer's list did not arrive (timeout)
+  int deferred;                 // 1: the producing CTA only publishes; the lists are awaited and merged by the
+                                //    fp32-fallback launch that follows in the stream (two-phase scan, nq > 1)
+  int nq;                       // queries of this search (deferred merge loop)
+  int no_pdl;                   // 1: several shards of this process share a GPU (tests): a dependent launch parked on the
+                                //    SMs would starve the peer shard's kernel this one is waiting for
 };
 
 struct ScanParams {
@@ -189,6 +194,7 @@ struct ScanParams {
   int no_merge;          // 1: stop after the per-block lists (phase 1 timed alone)
   int interleave;        // 1: dense bf16 sweep walks 8-row units block-cyclically over the grid
   int* zero_on_entry;    // nullable: one int cleared by the first thread of the grid (the overflow count)
+  int pdl_wait;          // 1: launched as a programmatic dependent of the previous kernel (griddepcontrol.wait first)
   // two-phase scan
   const float* max_norm; // largest stored row norm
   const float* max_err;  // largest ||x - bf16(x)|| over the stored rows
@@ -315,52 +321,34 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 template <int METRIC>
-__device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, KeyId* s, const int tid, const int nthreads) {
-  const int k = p.k_out;
-  if (p.ex.n_ranks <= 1) {
-    for (int i = tid; i < k; i += nthreads) {
-      const KeyId e = s[i];
-      const bool empty = (e.id == kEmptyId);
-      float dval;
-      if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
-      else dval = empty ? FLT_MAX : -e.key;
-      p.D[(int64_t)qi * k + i] = dval;
-      p.I[(int64_t)qi * k + i] = empty ? (int64_t)-1 : (int64_t)map_id(p.idmap, e.id);
-    }
-    return;
-  }
-  const int R = p.ex.n_ranks;
+__device__ __forceinline__ void write_result(const ScanParams& p, const int qi, const int i, const float key, const long long gid,
+                                             const bool empty) {
+  float dval;
+  if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : key;
+  else dval = empty ? FLT_MAX : -key;
+  p.D[(int64_t)qi * p.k_out + i] = dval;
+  p.I[(int64_t)qi * p.k_out + i] = empty ? (int64_t)-1 : (int64_t)gid;
+}
+
+// Wait for the lists of all ranks for query qi (own memory; bounded) and merge them into D/I.
+// `m`: shared memory for n_ranks * k_out 16-byte entries.  All threads of the CTA.
+template <int METRIC>
+__device__ __forceinline__ void await_and_merge(const ScanParams& p, const int qi, KeyId64* m, const int tid,
+                                                const int nthreads) {
+  const int k = p.k_out, R = p.ex.n_ranks;
   const size_t cell = ((size_t)(p.ex.epoch & 1u) * p.ex.max_nq + qi) * R;   // [parity][query][source]
-  // 1. publish: my list into slot (parity, qi, my rank) of every rank
-  for (int idx = tid; idx < R * k; idx += nthreads) {
-    const int r = idx / k, i = idx - r * k;
-    const KeyId e = s[i];
-    const long long gid = (e.id == kEmptyId) ? -1ll : map_id(p.idmap, e.id);
-    int4 v;
-    v.x = __float_as_int(e.key);
-    v.y = 0;
-    v.z = (int)(gid & 0xffffffffll);
-    v.w = (int)(gid >> 32);
-    *reinterpret_cast<int4*>(p.ex.slots[r] + (cell + p.ex.rank) * CSS_MAX_K + i) = v;
-  }
-  __threadfence_system();
-  __syncthreads();
   if (tid < R) {
-    st_release_sys(p.ex.flags[tid] + cell + p.ex.rank, p.ex.epoch);
-    // 2. wait for the list of source `tid` in my own memory (bounded: a missing peer is an error, not a hang)
     const unsigned* f = p.ex.flags[p.ex.rank] + cell + tid;
     const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(f) != p.ex.epoch) {
       __nanosleep(64);
-      if (global_timer_ns() - t0 > 10000000000ull) {   // 10 s
+      if (global_timer_ns() - t0 > 10000000000ull) {   // 10 s: a missing peer is an error, not a hang
         *p.ex.status = 1;
         break;
       }
     }
   }
   __syncthreads();
-  // 3. merge the R lists
-  KeyId64* m = reinterpret_cast<KeyId64*>(s);
   const ExEntry* mine = p.ex.slots[p.ex.rank] + cell * CSS_MAX_K;
   const int total = R * k;
   int n_sort = 32;
@@ -384,13 +372,40 @@ __device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, Key
   bitonic_sort_desc(m, n_sort, tid, nthreads);
   for (int i = tid; i < k; i += nthreads) {
     const KeyId64 e = m[i];
-    const bool empty = (e.id == LLONG_MAX);
-    float dval;
-    if constexpr (METRIC == CSS_METRIC_INNER_PRODUCT) dval = empty ? -FLT_MAX : e.key;
-    else dval = empty ? FLT_MAX : -e.key;
-    p.D[(int64_t)qi * k + i] = dval;
-    p.I[(int64_t)qi * k + i] = empty ? (int64_t)-1 : (int64_t)e.id;
+    write_result<METRIC>(p, qi, i, e.key, e.id, e.id == LLONG_MAX);
   }
+}
+
+template <int METRIC>
+__device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, KeyId* s, const int tid, const int nthreads) {
+  const int k = p.k_out;
+  if (p.ex.n_ranks <= 1) {
+    for (int i = tid; i < k; i += nthreads) {
+      const KeyId e = s[i];
+      write_result<METRIC>(p, qi, i, e.key, e.id == kEmptyId ? 0ll : map_id(p.idmap, e.id), e.id == kEmptyId);
+    }
+    return;
+  }
+  const int R = p.ex.n_ranks;
+  const size_t cell = ((size_t)(p.ex.epoch & 1u) * p.ex.max_nq + qi) * R;
+  // publish: my list into slot (parity, qi, my rank) of every rank (mine included), then the flags
+  for (int idx = tid; idx < R * k; idx += nthreads) {
+    const int r = idx / k, i = idx - r * k;
+    const KeyId e = s[i];
+    const long long gid = (e.id == kEmptyId) ? -1ll : map_id(p.idmap, e.id);
+    int4 v;
+    v.x = __float_as_int(e.key);
+    v.y = 0;
+    v.z = (int)(gid & 0xffffffffll);
+    v.w = (int)(gid >> 32);
+    *reinterpret_cast<int4*>(p.ex.slots[r] + (cell + p.ex.rank) * CSS_MAX_K + i) = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < R) st_release_sys(p.ex.flags[tid] + cell + p.ex.rank, p.ex.epoch);
+  if (p.ex.deferred) return;   // awaited + merged by the launch that follows (see ExchangeDev)
+  __syncthreads();
+  await_and_merge<METRIC>(p, qi, reinterpret_cast<KeyId64*>(s), tid, nthreads);
 }
 
 // ------------------------------------------------------------------------
@@ -415,6 +430,7 @@ __device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, Key
 constexpr int kRescoreCap = 2048;    // candidates re-scored per query at most (second half of s: rank-sort output)
 constexpr int kTwoPhaseMaxK = 32;    // largest k the two-phase scan serves
 constexpr int kRankSortMax = 1024;   // above this many candidates: bitonic sort instead of rank counting
+constexpr int kTwoPhaseMaxBlocks = 160;  // scan blocks (= SMs) the register-held list entries of two_phase_finish cover
 
 __device__ __forceinline__ KeyId ldcg_keyid(const KeyId* p) {
   const unsigned long long raw = __ldcg(reinterpret_cast<const unsigned long long*>(p));
@@ -424,29 +440,41 @@ __device__ __forceinline__ KeyId ldcg_keyid(const KeyId* p) {
   return e;
 }
 
-__device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid) {
-  __shared__ float s_qn, s_t;
+template <int KPL>
+__device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float qn) {
+  __shared__ float s_t;
   __shared__ int s_cnt, s_unproven;
   const int lane = tid & 31, warp = tid >> 5;
   const int kp = p.k, k = p.k_out, blocks = gridDim.x;
   const KeyId* lists = p.part + (size_t)qi * blocks * kp;
   const float* q = p.q + (size_t)qi * 768;
-  if (warp == 0) {
-    float ss = 0.f;
-    for (int j = lane; j < 768; j += 32) ss = fmaf(q[j], q[j], ss);
-    ss = warp_sum(ss);
-    if (lane == 0) {
-      s_qn = sqrtf(ss);
-      s_t = -INFINITY;
-      s_cnt = 0;
-      s_unproven = 0;
-    }
+  // every list entry is read ONCE, all loads in flight together (one L2 round trip), and kept in registers for the
+  // three selection steps below: thread t holds entries t, t + 512, ...  (kTwoPhaseMaxBlocks bounds the grid)
+  constexpr int kPer = (kTwoPhaseMaxBlocks * 32 * KPL + kScanThreads - 1) / kScanThreads;
+  const int total = blocks * kp;
+  KeyId ent[kPer];
+#pragma unroll
+  for (int c = 0; c < kPer; ++c) {
+    const int i = tid + c * kScanThreads;
+    ent[c].key = -INFINITY;
+    ent[c].id = kEmptyId;
+    if (i < total) ent[c] = ldcg_keyid(lists + i);
+  }
+  if (tid == 0) {
+    s_t = -INFINITY;
+    s_cnt = 0;
+    s_unproven = 0;
   }
   // (A) t0 = k-th best list head (k distinct rows score at least that); with fewer than k lists the
   //     k-th best of their first k entries.
   const int per = blocks >= k ? 1 : k;
   const int nsel = blocks * per;
-  for (int i = tid; i < nsel; i += kScanThreads) s[i] = ldcg_keyid(lists + (i / per) * kp + (i % per));
+#pragma unroll
+  for (int c = 0; c < kPer; ++c) {
+    const int i = tid + c * kScanThreads;
+    const int within = i % kp;
+    if (i < total && within < per) s[(i / kp) * per + within] = ent[c];
+  }
   __syncthreads();
   for (int i = tid; i < nsel; i += kScanThreads) {
     const KeyId e = s[i];
@@ -459,11 +487,11 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   const float t0 = s_t;
   // (B) tighten: the k-th best over all entries >= t0 (there are at least k of them)
   if (t0 > -INFINITY) {
-    for (int i = tid; i < blocks * kp; i += kScanThreads) {
-      const KeyId e = ldcg_keyid(lists + i);
-      if (e.id != kEmptyId && e.key >= t0) {
+#pragma unroll
+    for (int c = 0; c < kPer; ++c) {
+      if (ent[c].id != kEmptyId && ent[c].key >= t0) {
         const int pos = atomicAdd(&s_cnt, 1);
-        if (pos < kRankSortMax) s[pos] = e;
+        if (pos < kRankSortMax) s[pos] = ent[c];
       }
     }
     __syncthreads();
@@ -480,15 +508,16 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (tid == 0) s_cnt = 0;
   }
   __syncthreads();
-  const float eps = s_qn * (1.001f * (*p.max_err) + 4e-6f * (*p.max_norm));
+  const float eps = qn * (1.001f * (*p.max_err) + 4e-6f * (*p.max_norm));
   const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
   // (C) proof + candidates over the full lists
-  for (int i = tid; i < blocks * kp; i += kScanThreads) {
-    const KeyId e = ldcg_keyid(lists + i);
-    if (e.id != kEmptyId && e.key >= thr) {
+#pragma unroll
+  for (int c = 0; c < kPer; ++c) {
+    if (ent[c].id != kEmptyId && ent[c].key >= thr) {
+      const int i = tid + c * kScanThreads;
       if (i % kp == kp - 1) s_unproven = 1;
       const int pos = atomicAdd(&s_cnt, 1);
-      if (pos < kRescoreCap) s[pos] = e;
+      if (pos < kRescoreCap) s[pos] = ent[c];
     }
   }
   __syncthreads();
@@ -586,12 +615,21 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   const float* q = p.q + (int64_t)qi * p.d;
 
   float4 qreg[6];
+  float qn = 0.f;   // ||q|| (two-phase scan: the error bound of two_phase_finish)
   if constexpr (BF16) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       qreg[2 * j] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + lane * 8));
       qreg[2 * j + 1] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + lane * 8) + 1);
     }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      qn = fmaf(qreg[j].x, qreg[j].x, qn);
+      qn = fmaf(qreg[j].y, qreg[j].y, qn);
+      qn = fmaf(qreg[j].z, qreg[j].z, qn);
+      qn = fmaf(qreg[j].w, qreg[j].w, qn);
+    }
+    qn = sqrtf(warp_sum(qn)) * 1.00001f;
   } else if constexpr (D768) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) qreg[j] = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
@@ -766,7 +804,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 
   if constexpr (BF16) {
     // two-phase scan: prove + re-score in fp32 (or queue the query for the fp32 scan)
-    two_phase_finish(p, qi, s_list, tid);
+    two_phase_finish<KPL>(p, qi, s_list, tid, qn);
     return;
   }
 
@@ -804,6 +842,10 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 // slice y walks the listed queries y, y+F, ... (device-side fallback of the batched path).
 template <int KPL, int METRIC, bool D768, bool BF16 = false>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
+  // programmatic dependent launch: the fp32-fallback launch behind a two-phase sweep is set up while the sweep
+  // runs and only waits here (an empty overflow list -- the normal case -- then costs ~1 us instead of a launch gap)
+  if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if constexpr (BF16) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.zero_on_entry != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.zero_on_entry = 0;
   if (p.qlist == nullptr) {
     scan_one_query<KPL, METRIC, D768, BF16>(p, blockIdx.y);
@@ -813,6 +855,15 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p
   for (int slot = blockIdx.y; slot < cnt; slot += gridDim.y) {
     scan_one_query<KPL, METRIC, D768, BF16>(p, p.qlist[slot]);
     __syncthreads();
+  }
+  if (p.ex.n_ranks > 1 && p.ex.deferred && blockIdx.x == 0) {
+    // deferred exchange: every query of the search has been published by now-or-soon (by phase 1, by the scans
+    // above, or by a peer's); no publisher ever waits, so these waits cannot deadlock across ranks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    for (int qi = blockIdx.y; qi < p.ex.nq; qi += gridDim.y) {
+      await_and_merge<METRIC>(p, qi, reinterpret_cast<KeyId64*>(smem_raw), threadIdx.x, kScanThreads);
+      __syncthreads();
+    }
   }
 }
 

@@ -257,13 +257,17 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
   unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
   memcpy(pin, q_host, qbytes);
   std::vector<std::vector<uint32_t>> rms(filter && filter->row_mask ? S : 0);
+  // Pass 1, per shard: scratch, filter evaluation, query upload.  Anything that may free device memory (scratch or
+  // filter buffers growing) happens here: cudaFree waits for ALL work of its device, and once the scans of pass 2
+  // are in flight that includes kernels waiting for the lists of shards that have not been launched yet.
+  std::vector<css_scan_scratch*> scs(S, nullptr);
+  std::vector<const uint32_t*> masks(S, nullptr);
   for (int s = 0; s < S; ++s) {
     css_index* sh = h->shards[s];
     std::lock_guard<std::mutex> lk(sh->mu);
     DeviceGuard g(sh->device);
     cudaStream_t st = sh->stream;
-    css_scan_scratch* sc = nullptr;
-    CSS_CHECK(get_scratch(sh, st, nq, &sc));
+    CSS_CHECK(get_scratch(sh, st, nq, &scs[s]));
     css_filter fs;
     const css_filter* fp = filter;
     if (filter && filter->row_mask) {
@@ -273,11 +277,19 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
       fs.row_mask = rms[s].data();
       fp = &fs;
     }
-    const uint32_t* m = nullptr;
     bool ignore_alive = false;
-    CSS_CHECK(eval_filter(sh, fp, &m, nullptr, false, st, &ignore_alive));
-    if (!m && sh->any_dead && !ignore_alive) m = sh->alive;
-    CSS_CUDA(cudaMemcpyAsync(sc->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
+    CSS_CHECK(eval_filter(sh, fp, &masks[s], nullptr, false, st, &ignore_alive));
+    if (!masks[s] && sh->any_dead && !ignore_alive) masks[s] = sh->alive;
+    CSS_CUDA(cudaMemcpyAsync(scs[s]->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
+  }
+  // Pass 2: the scans (and, on the exchange path, the in-kernel merge)
+  for (int s = 0; s < S; ++s) {
+    css_index* sh = h->shards[s];
+    std::lock_guard<std::mutex> lk(sh->mu);
+    DeviceGuard g(sh->device);
+    cudaStream_t st = sh->stream;
+    css_scan_scratch* sc = scs[s];
+    const uint32_t* m = masks[s];
     int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(sc->D_dev) + i_rel);
     if (exchange) {
       ExchangeDev xd;
@@ -370,8 +382,8 @@ int css_index_create_sharded(int dim, int metric, const int* devices, int n_dev,
   CSS_REQUIRE(dim >= 1 && dim <= 65536, "dim %d out of range", dim);
   CSS_REQUIRE(metric == CSS_METRIC_INNER_PRODUCT || metric == CSS_METRIC_L2, "unknown metric %d", metric);
   CSS_REQUIRE(devices != nullptr && n_dev >= 1 && n_dev <= CSS_MAX_RANKS, "n_dev %d outside [1, %d]", n_dev, CSS_MAX_RANKS);
-  for (int a = 0; a < n_dev; ++a)
-    for (int b = 0; b < a; ++b) CSS_REQUIRE(devices[a] != devices[b], "device %d listed twice", devices[a]);
+  // a device may be listed more than once (several shards on one GPU): of no use in production, but it runs
+  // the whole multi-shard path -- block-cyclic ids, in-kernel exchange -- on a single-GPU box (tests)
   css_index* h = new (std::nothrow) css_index();
   if (!h) {
     set_error("out of host memory");

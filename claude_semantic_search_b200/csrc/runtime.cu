@@ -1,5 +1,6 @@
 // runtime.cu -- error state, device probing and small shared utilities.
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace css {
 
@@ -11,6 +12,24 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(t_error, sizeof(t_error), fmt, ap);
   va_end(ap);
+}
+
+Options& options() {
+  static Options o;
+  static const bool init = [] {
+    auto env = [](const char* n, std::atomic<int>& dst) {
+      const char* v = getenv(n);
+      if (v) dst.store(atoi(v));
+    };
+    env("CSS_SCAN_BF16", o.scan_bf16);
+    env("CSS_SCAN_INTERLEAVE", o.scan_interleave);
+    env("CSS_SCAN_LIST", o.scan_list);
+    env("CSS_SCAN_ADAPTIVE", o.scan_adaptive);
+    env("CSS_SCAN_PDL", o.scan_pdl);
+    return true;
+  }();
+  (void)init;
+  return o;
 }
 
 int ensure_device(int device) {
@@ -156,3 +175,20 @@ int css_device_info(int device, int64_t info_out[5]) {
 int64_t css_kernel_launch_count(void) { return css::g_launches.load(); }
 
 }  // extern "C"
+
+extern "C" int css_set_option(const char* name, int value) {
+  if (!name) return CSS_ERR_INVALID;
+  css::Options& o = css::options();
+  std::atomic<int>* slot = nullptr;
+  if (!strcmp(name, "scan_bf16")) slot = &o.scan_bf16;
+  else if (!strcmp(name, "scan_interleave")) slot = &o.scan_interleave;
+  else if (!strcmp(name, "scan_list")) slot = &o.scan_list;
+  else if (!strcmp(name, "scan_adaptive")) slot = &o.scan_adaptive;
+  else if (!strcmp(name, "scan_pdl")) slot = &o.scan_pdl;
+  if (!slot) {
+    css::set_error("unknown option %s", name);
+    return CSS_ERR_INVALID;
+  }
+  slot->store(value);
+  return CSS_OK;
+}

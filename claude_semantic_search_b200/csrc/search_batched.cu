@@ -145,11 +145,41 @@ struct EpiSearch {
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       if (gm[g] >= t) {
+        // one out-of-line call per 8-column group with a hit: ONE slot reservation for all of its hits.  (A clustered
+        // corpus in session order puts a query's whole cluster -- hundreds of rows above the running threshold -- into
+        // adjacent columns; one call + one atomic per hit made those tiles epilogue-bound: 2.06 vs 1.20 ms per batch.)
+        unsigned hm = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float s = __uint_as_float(v[g * 8 + j]);
-          if (s >= t) offer(m, n0 + g * 8 + j, s);
-        }
+        for (int j = 0; j < 8; ++j) hm |= (__uint_as_float(v[g * 8 + j]) >= t) ? (1u << j) : 0u;
+        append_group(p.count, p.cand, p.ovf_flag, p.mask, p.row0, p.n_rows, m, n0 + g * 8, hm, v[g * 8], v[g * 8 + 1],
+                     v[g * 8 + 2], v[g * 8 + 3], v[g * 8 + 4], v[g * 8 + 5], v[g * 8 + 6], v[g * 8 + 7]);
+      }
+    }
+  }
+  __device__ __noinline__ static void append_group(unsigned* count, Cand* cand, int* ovf_flag, const uint32_t* mask,
+                                                  int row0, int n_rows, int m, int r0, unsigned hm, uint32_t s0,
+                                                  uint32_t s1, uint32_t s2, uint32_t s3, uint32_t s4, uint32_t s5,
+                                                  uint32_t s6, uint32_t s7) {
+    const int left = n_rows - r0;                       // columns of this group inside the pass
+    if (left < 8) hm &= left > 0 ? ((1u << left) - 1u) : 0u;
+    const int g = row0 + r0;                            // multiple of 8
+    if (mask) hm &= (__ldg(mask + (g >> 5)) >> (g & 31)) & 0xffu;
+    if (!hm) return;
+    const unsigned n = __popc(hm);
+    unsigned pos = atomicAdd(count + m, n);
+    if (pos + n > (unsigned)kCap) {
+      ovf_flag[m] = 1;
+      return;
+    }
+    Cand* out = cand + (size_t)m * kCap;
+    const uint32_t sv[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if ((hm >> j) & 1u) {
+        Cand c;
+        c.score = __uint_as_float(sv[j]);
+        c.row = g + j;
+        out[pos++] = c;
       }
     }
   }

@@ -68,14 +68,10 @@ class ShardedSearch:
     def _exchange(self):
         """The in-kernel exchange of this rank, connected to all peers on first use (NCCL groups only)."""
         if self._ex is None:
-            import torch
             ex = _native.Exchange(self.index.device, self.world, self.dist.get_rank(self.group))
-            dev = torch.device("cuda", self.index.device)
-            mine = torch.frombuffer(bytearray(ex.handle), dtype=torch.uint8).to(dev)
-            allh = torch.empty(self.world * _native.IPC_HANDLE_BYTES, dtype=torch.uint8, device=dev)
-            self.dist.all_gather_into_tensor(allh, mine, group=self.group)
-            blob = bytes(allh.cpu().numpy().tobytes())
-            ex.connect([blob[i * _native.IPC_HANDLE_BYTES:(i + 1) * _native.IPC_HANDLE_BYTES] for i in range(self.world)])
+            handles = [None] * self.world
+            self.dist.all_gather_object(handles, ex.handle, group=self.group)   # 64 bytes per rank, any backend
+            ex.connect(handles)
             self.dist.barrier(group=self.group)
             self._ex = ex
         return self._ex

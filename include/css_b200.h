@@ -333,6 +333,13 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
  *              candidate lists), on `stream`, for the roofline measurement of bench.py; no result is produced. */
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream);
 
+/* Process-wide switches (also read from the environment at load: CSS_SCAN_BF16, CSS_SCAN_INTERLEAVE,
+ * CSS_SCAN_LIST, CSS_SCAN_ADAPTIVE): "scan_bf16" 1 = two-phase batch-1 scan, 0 = single fp32 sweep;
+ * "scan_interleave" 1 = block-cyclic 8-row units in the bf16 sweep; "scan_list" 32 | 64 = per-block list length
+ * (0: chosen by k); "scan_adaptive" 1 = bypass phase 1 while most queries cannot be proven.  Results are exact
+ * under every setting; benchmarks use this to time the paths side by side in one process. */
+int css_set_option(const char* name, int value);
+
 /* Timing hook for benchmarks: number of kernels this library has launched in
  * this process (all handles). */
 int64_t css_kernel_launch_count(void);

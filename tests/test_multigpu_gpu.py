@@ -31,8 +31,8 @@ idx = _native.Index(d, device=dev.index)
 idx.add(x[lo:hi])
 ss = ShardedSearch(idx, id_offset=lo)
 qd = torch.from_numpy(q).to(dev)
-D1, I1 = ss.search_device(qd[:3], k)          # streaming scan + gather + merge
-Db, Ib = ss.search_device(qd, k)              # batched path + gather + merge
+D1, I1 = ss.search_device(qd[:3], k)          # streaming scan, in-kernel NVLink exchange + merge
+Db, Ib = ss.search_device(qd, k)              # batched path + NCCL gather + merge kernel
 torch.cuda.synchronize(dev)
 Dh, Ih = ss.search_host(q[:3], k)
 Dr, Ir = so.flat_search_c(x, q, k)
@@ -42,7 +42,22 @@ for name, (D, I, sl) in {"scan": (D1, I1, slice(0, 3)), "batched": (Db, Ib, slic
 ok, why = so.compare_topk(Dr[:3], Ir[:3], Dh, Ih)
 assert ok, f"rank {rank} host: {why}"
 assert I1.cpu().numpy()[0][:2].tolist() == [1, n - 3]
-dist.barrier(); dist.destroy_process_group()
+# NCCL exchange (all-gather + merge kernel) of the same scan: identical result
+ss_nccl = ShardedSearch(idx, id_offset=lo); ss_nccl.use_exchange = False
+Dn, In = ss_nccl.search_device(qd[:3], k)
+torch.cuda.synchronize(dev)
+assert np.array_equal(In.cpu().numpy(), I1.cpu().numpy()) and np.array_equal(Dn.cpu().numpy(), D1.cpu().numpy())
+# filtered search at N > 1 (filter mask sharded, SURVEY 8e row 3)
+col = (np.arange(n) % 10).astype(np.int32)
+idx.set_column(2, col[lo:hi])
+mptr, _ = idx.filter_mask_device(_native.Filter().add_range(2, 3, 5), torch.cuda.current_stream(dev).cuda_stream)
+Df, If = ss.search_device(qd[:4], k, mask_ptr=mptr)
+torch.cuda.synchronize(dev)
+want = (col >= 3) & (col <= 5)
+Drf, Irf = so.flat_search_c(x, q[:4], k, mask_words=so.pack_mask(want))
+ok, why = so.compare_topk(Drf, Irf, Df.cpu().numpy(), If.cpu().numpy())
+assert ok, f"rank {rank} filtered: {why}"
+dist.barrier(); ss.close(); dist.destroy_process_group()
 print(f"rank {rank} ok")
 """
 
