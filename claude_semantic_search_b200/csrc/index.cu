@@ -487,9 +487,42 @@ int search_on_device(css_index* h, css_scan_scratch* sc, const float* q_dev, int
   return scan_search(h, sc, q_dev, nq, k, m, idmap, ex, D_dev, I_dev, st, defer_fallback, two_phase_used);
 }
 
+// Load every kernel a search can launch on the current device now.  CUDA loads kernels lazily, on first launch, and
+// that load waits for the device to go idle: during a multi-device search a scan kernel may be spinning for a
+// peer's list while the host -- which has yet to launch that peer -- sits in the lazy load of the next kernel.
+template <typename K>
+static int preload_kernel(K kern, size_t smem) {
+  cudaFuncAttributes a;
+  CSS_CUDA(cudaFuncGetAttributes(&a, kern));
+  if (smem) CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  return CSS_OK;
+}
+template <int KPL>
+static int preload_scan_kpl(size_t smem, size_t smem_generic) {
+  CSS_CHECK(preload_kernel(scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, true>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<KPL, CSS_METRIC_L2, true>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, false>, smem_generic));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<KPL, CSS_METRIC_L2, false>, smem_generic));
+  return CSS_OK;
+}
+static int preload_index_kernels(int dim) {
+  const size_t smem = sizeof(KeyId) * kMergeCap, smem_generic = smem + (size_t)dim * 4;
+  CSS_CHECK(preload_scan_kpl<1>(smem, smem_generic));
+  CSS_CHECK(preload_scan_kpl<2>(smem, smem_generic));
+  CSS_CHECK(preload_scan_kpl<4>(smem, smem_generic));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, true>, smem));
+  CSS_CHECK(preload_kernel(filter_mask_kernel, 0));
+  CSS_CHECK(preload_kernel(append_rows_kernel, 0));
+  CSS_CHECK(preload_kernel(set_bits_kernel, 0));
+  CSS_CHECK(preload_kernel(fill_i32_kernel, 0));
+  return CSS_OK;
+}
+
 int index_create_single(int dim, int metric, int device, css_index** out) {
   CSS_CHECK(ensure_device(device));
   DeviceGuard g(device);
+  CSS_CHECK(preload_index_kernels(dim));
   css_index* h = new (std::nothrow) css_index();
   if (!h) {
     set_error("out of host memory");
