@@ -20,9 +20,11 @@ def synthetic_batch(n_seq: int, seed: int):
     return np.ascontiguousarray(ids.reshape(-1)), cu
 
 
-def cpu_encoder_baseline(n_seq: int = 16):
+def cpu_encoder_baseline(n_seq: int = 16, device: int = None):
     """The reference's CPU path for this half: transformers MPNetModel fp32 + the restated
-    sentence-transformers pooling (oracle/encoder_oracle.py) on a bounded sample."""
+    sentence-transformers pooling (oracle/encoder_oracle.py) on a bounded sample.  With `device` the same 16
+    chunks (384 tokens, 12 layers, the prescribed random-init weights) also go through the CUDA encoder and the
+    embeddings are compared: the benchmarked configuration is checked against the oracle inside the bench run."""
     import torch
     from oracle import encoder_oracle as eo
     torch.set_num_threads(os.cpu_count() or 1)
@@ -30,10 +32,20 @@ def cpu_encoder_baseline(n_seq: int = 16):
     seqs = eo.synthetic_ids(n_seq, [SEQ_LEN], seed=7)
     eo.st_encode_ids(model, seqs[:2])
     t0 = time.perf_counter()
-    eo.st_encode_ids(model, seqs, batch_size=16)
+    want = eo.st_encode_ids(model, seqs, batch_size=16)
     dt = time.perf_counter() - t0
-    return {"value": n_seq / dt, "unit": "chunks/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n_seq} chunks x {SEQ_LEN} tokens, batch 16, fp32 transformers MPNetModel + ST pooling on the host"}
+    out = {"value": n_seq / dt, "unit": "chunks/s", "cores": os.cpu_count(), "kind": "port",
+           "sample": f"{n_seq} chunks x {SEQ_LEN} tokens, batch 16, fp32 transformers MPNetModel + ST pooling on the host"}
+    if device is not None:
+        from claude_semantic_search_b200.encoder import MPNetEncoder
+        enc = MPNetEncoder.from_hf_model(model, device=device, max_tokens=n_seq * SEQ_LEN)
+        got = enc.encode_ids(seqs)
+        enc.close()
+        cos = eo.cosine_rows(want, got)
+        out["parity"] = {"chunks": n_seq, "min_cosine_vs_fp32_cpu": float(cos.min()), "bar": 0.9999,
+                         "max_abs_component_diff": float(np.abs(want - got).max())}
+        assert cos.min() >= 0.9999, f"encoder parity at the benchmarked shape: min cosine {cos.min():.6f}"
+    return out
 
 
 def bench_text_to_embedding(enc, n_seq: int, reps: int = 3):
@@ -173,5 +185,5 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warm
     if query_leg is not None:
         res["encode"]["single_query"] = query_leg
     if rank == 0 and not getattr(args, "no_cpu", False):
-        res["encode"]["cpu_baseline"] = cpu_encoder_baseline()
+        res["encode"]["cpu_baseline"] = cpu_encoder_baseline(device=dev.index)
     return res
