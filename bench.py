@@ -912,6 +912,15 @@ def bench_sharded_handle(torch, native, dev, dist, world, rank, rows):
     StorageConfig.devices): rank 0 builds ONE index over all `world` GPUs (rows per GPU as in the headline) and
     times css_index_search with host buffers; the other ranks wait.  Checked against brute force."""
     out = None
+    # the other ranks wait on the HOST (a store key), not in an NCCL barrier: a spinning barrier kernel of another
+    # process on a GPU this index uses would time-slice with the index's kernels (2 ms slices)
+    store = None
+    if dist is not None:
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        from torch.distributed.distributed_c10d import _get_default_store
+        store = _get_default_store()
     if rank == 0:
         devs = list(range(world))
         idx = native.Index(D, native.METRIC_INNER_PRODUCT, devices=devs)
@@ -955,6 +964,10 @@ def bench_sharded_handle(torch, native, dev, dist, world, rank, rows):
                "shard_scans_per_s": world * 1e3 / lat["mean_ms"], "batch256_e2e_ms": batch_ms,
                "check": "8 queries == brute force within 1e-4",
                "api": "css_index_create_sharded + css_index_search (one process, host buffers, in-kernel NVLink exchange)"}
+        if store is not None:
+            store.set("css_sharded_handle_done", "1")
+    elif store is not None:
+        store.wait(["css_sharded_handle_done"])
     if dist is not None:
         dist.barrier()
     return out

@@ -97,6 +97,7 @@ struct css_index {
   std::vector<css_index*> shards;
   std::vector<css_exchange*> shard_ex;
   int64_t composite_ntotal = 0;
+  void* workers = nullptr;           // ShardWorkers (index_sharded.cu): one launch thread per shard
 
   // id mapping applied to returned rows (composite shards: block-cyclic)
   int id_shift = 0, id_ndev = 1, id_shard = 0;

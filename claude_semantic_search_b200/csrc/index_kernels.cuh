@@ -351,6 +351,30 @@ __device__ __forceinline__ void await_and_merge(const ScanParams& p, const int q
   __syncthreads();
   const ExEntry* mine = p.ex.slots[p.ex.rank] + cell * CSS_MAX_K;
   const int total = R * k;
+  if (total <= 1024) {
+    // rank counting instead of a sorting network: two barriers, and entry i goes straight to its output slot
+    for (int i = tid; i < total; i += nthreads) {
+      const int r = i / k, j = i - r * k;
+      const int4 v = __ldcg(reinterpret_cast<const int4*>(mine + (size_t)r * CSS_MAX_K + j));
+      KeyId64 e;
+      e.key = __int_as_float(v.x);
+      e.pad = 0;
+      e.id = ((long long)v.w << 32) | (unsigned)v.z;
+      if (e.id < 0) {
+        e.key = -INFINITY;
+        e.id = LLONG_MAX - i;     // holes: distinct ids, after every real entry
+      }
+      m[i] = e;
+    }
+    __syncthreads();
+    for (int i = tid; i < total; i += nthreads) {
+      const KeyId64 e = m[i];
+      int rank = 0;
+      for (int j = 0; j < total; ++j) rank += better(m[j], e) ? 1 : 0;
+      if (rank < k) write_result<METRIC>(p, qi, rank, e.key, e.id, e.key == -INFINITY && e.id > LLONG_MAX - 2048);
+    }
+    return;
+  }
   int n_sort = 32;
   while (n_sort < total) n_sort <<= 1;
   for (int i = tid; i < n_sort; i += nthreads) {

@@ -15,11 +15,96 @@
 #include "index_internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <vector>
 
 using namespace css;
 
 namespace {
+
+// One host thread per shard (shards 1..S-1; the caller's thread serves shard 0), each bound to its shard's device.
+// A search launches ~3 operations per device; issued from one thread the last of 8 devices would start ~80 us after
+// the first -- a third of the 240 us scan.  Workers spin briefly after a job (a burst of queries finds them hot) and
+// then block on a condition variable.
+struct ShardWorkers {
+  std::vector<std::thread> threads;
+  std::function<int(int)> job;          // shard index -> status
+  std::atomic<uint64_t> seq{0};
+  std::atomic<int> pending{0};
+  std::atomic<int> failed{0};
+  std::string error;                    // first failure's message (under mu)
+  std::mutex mu;
+  std::condition_variable cv;
+  bool stop = false;
+
+  void start(css_index* h) {
+    const int S = (int)h->shards.size();
+    for (int s = 1; s < S; ++s) threads.emplace_back([this, h, s] { run(h, s); });
+  }
+  void run(css_index* h, int s) {
+    cudaSetDevice(h->shards[s]->device);
+    uint64_t seen = 0;
+    for (;;) {
+      // spin ~200 us for the next job, then sleep
+      const auto t0 = std::chrono::steady_clock::now();
+      while (seq.load(std::memory_order_acquire) == seen) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(200)) {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return stop || seq.load(std::memory_order_acquire) != seen; });
+          break;
+        }
+      }
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (stop) return;
+      }
+      seen = seq.load(std::memory_order_acquire);
+      const int rc = job(s);
+      if (rc != CSS_OK) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!failed.exchange(rc)) error = css_last_error();
+      }
+      pending.fetch_sub(1, std::memory_order_release);
+    }
+  }
+  // Run fn(s) for every shard: shards 1.. on the workers, shard 0 here.  Returns the first failure.
+  int run_all(int S, std::function<int(int)> fn) {
+    failed.store(0);
+    if (threads.empty()) {
+      for (int s = 0; s < S; ++s) CSS_CHECK(fn(s));
+      return CSS_OK;
+    }
+    job = std::move(fn);
+    pending.store(S - 1, std::memory_order_release);
+    {
+      std::lock_guard<std::mutex> lk(mu);   // pairs with the predicate check of a worker about to sleep
+      seq.fetch_add(1, std::memory_order_release);
+    }
+    cv.notify_all();
+    int rc0 = job(0);
+    while (pending.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+    if (rc0 != CSS_OK) return rc0;
+    const int rc = failed.load();
+    if (rc != CSS_OK) set_error("%s", error.c_str());
+    return rc;
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+      seq.fetch_add(1, std::memory_order_release);
+    }
+    cv.notify_all();
+    for (auto& t : threads) t.join();
+    threads.clear();
+  }
+};
+
+ShardWorkers* workers_of(css_index* h) { return reinterpret_cast<ShardWorkers*>(h->workers); }
 
 inline int64_t words_for(int64_t rows) { return (rows + 31) / 32; }
 
@@ -86,6 +171,11 @@ void spans_of(const css_index* h, int64_t g0, int64_t n, std::vector<RowSpan>* o
 }
 
 int sharded_destroy(css_index* h) {
+  if (h->workers) {
+    workers_of(h)->shutdown();
+    delete workers_of(h);
+    h->workers = nullptr;
+  }
   for (css_exchange* ex : h->shard_ex) css_exchange_destroy(ex);
   for (css_index* s : h->shards) index_destroy_single(s);
   if (h->pinned) cudaFreeHost(h->pinned);
@@ -257,14 +347,20 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
   unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
   memcpy(pin, q_host, qbytes);
   std::vector<std::vector<uint32_t>> rms(filter && filter->row_mask ? S : 0);
-  // Pass 1, per shard: scratch, filter evaluation, query upload.  Anything that may free device memory (scratch or
-  // filter buffers growing) happens here: cudaFree waits for ALL work of its device, and once the scans of pass 2
+  // Pass 1, per shard: scratch, filter evaluation.  Anything that may free device memory (scratch or filter buffers
+  // growing) happens here, sequentially: cudaFree waits for ALL work of its device, and once the scans of pass 2
   // are in flight that includes kernels waiting for the lists of shards that have not been launched yet.
   std::vector<css_scan_scratch*> scs(S, nullptr);
   std::vector<const uint32_t*> masks(S, nullptr);
   for (int s = 0; s < S; ++s) {
     css_index* sh = h->shards[s];
     std::lock_guard<std::mutex> lk(sh->mu);
+    const auto it = sh->scratch.find(sh->stream);
+    const bool ready = it != sh->scratch.end() && it->second.max_nq >= nq;
+    if (ready && !filter && !sh->any_dead) {   // nothing to evaluate, nothing to grow: no CUDA call at all
+      scs[s] = &it->second;
+      continue;
+    }
     DeviceGuard g(sh->device);
     cudaStream_t st = sh->stream;
     CSS_CHECK(get_scratch(sh, st, nq, &scs[s]));
@@ -280,21 +376,24 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
     bool ignore_alive = false;
     CSS_CHECK(eval_filter(sh, fp, &masks[s], nullptr, false, st, &ignore_alive));
     if (!masks[s] && sh->any_dead && !ignore_alive) masks[s] = sh->alive;
-    CSS_CUDA(cudaMemcpyAsync(scs[s]->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
   }
-  // Pass 2: the scans (and, on the exchange path, the in-kernel merge)
-  for (int s = 0; s < S; ++s) {
+  // Pass 2, one host thread per shard: query upload, the scans (and, on the exchange path, the in-kernel merge)
+  std::vector<ExchangeDev> xds(S);
+  if (exchange)
+    for (int s = 0; s < S; ++s) CSS_CHECK(exchange_next(h->shard_ex[s], &xds[s]));
+  auto launch = [&](int s) -> int {
     css_index* sh = h->shards[s];
     std::lock_guard<std::mutex> lk(sh->mu);
-    DeviceGuard g(sh->device);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != sh->device) CSS_CUDA(cudaSetDevice(sh->device));   // workers are bound already; the caller's thread is restored below
     cudaStream_t st = sh->stream;
     css_scan_scratch* sc = scs[s];
     const uint32_t* m = masks[s];
+    CSS_CUDA(cudaMemcpyAsync(sc->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
     int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(sc->D_dev) + i_rel);
     if (exchange) {
-      ExchangeDev xd;
-      CSS_CHECK(exchange_next(h->shard_ex[s], &xd));
-      CSS_CHECK(scan_search(sh, sc, sc->q_dev, nq, k, m, index_idmap(sh, 0), &xd, sc->D_dev, I_dev, st,
+      CSS_CHECK(scan_search(sh, sc, sc->q_dev, nq, k, m, index_idmap(sh, 0), &xds[s], sc->D_dev, I_dev, st,
                             /*defer_fallback=*/false, nullptr));
       if (s == 0) CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, i_rel + ibytes, cudaMemcpyDeviceToHost, st));
     } else {
@@ -302,6 +401,17 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
                                  /*defer_fallback=*/false, nullptr));
       CSS_CUDA(cudaMemcpyAsync(pin + d_off + res_stride * s, sc->D_dev, i_rel + ibytes, cudaMemcpyDeviceToHost, st));
     }
+    return CSS_OK;
+  };
+  // the tensor-core path may grow its own state (allocations): keep it on the caller's thread, one shard after the other
+  if (!exchange || !h->workers) {
+    for (int s = 0; s < S; ++s) {
+      DeviceGuard g(h->shards[s]->device);
+      CSS_CHECK(launch(s));
+    }
+  } else {
+    CSS_CHECK(workers_of(h)->run_all(S, launch));
+    cudaSetDevice(h->device);
   }
   if (exchange) {
     // every device merged the same lists; device 0's copy is the answer.  Its completion implies that
@@ -412,6 +522,19 @@ int css_index_create_sharded(int dim, int metric, const int* devices, int n_dev,
     return rc;
   }
   h->n_sm = h->shards[0]->n_sm;
+  // host threads for the per-device launches: only worth it (and only safe against oversubscription in tests that
+  // put many shards on one GPU) with distinct devices; CSS_SHARD_THREADS=0 keeps everything on the caller's thread
+  bool distinct = n_dev >= 2;
+  for (int a = 0; a < n_dev; ++a)
+    for (int b = 0; b < a; ++b) distinct = distinct && devices[a] != devices[b];
+  const char* tv = getenv("CSS_SHARD_THREADS");
+  if (distinct && !(tv && atoi(tv) == 0)) {
+    ShardWorkers* w = new (std::nothrow) ShardWorkers();
+    if (w) {
+      w->start(h);
+      h->workers = w;
+    }
+  }
   *out = h;
   return CSS_OK;
 }
