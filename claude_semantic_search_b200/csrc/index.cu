@@ -167,7 +167,7 @@ int launch_scan_m(css_index* h, const ScanParams& p, int nq, cudaStream_t st) {
 }
 
 // Compile a host css_filter into device FilterParams (uploads bitsets / row mask).
-int build_filter_params(css_index* h, const css_filter* f, FilterParams* fp, cudaStream_t st) {
+int build_filter_params(css_index* h, const css_filter* f, FilterParams* fp, cudaStream_t st, size_t pinned_front) {
   memset(fp, 0, sizeof(*fp));
   fp->n = h->ntotal;
   fp->out = h->mask;
@@ -197,8 +197,9 @@ int build_filter_params(css_index* h, const css_filter* f, FilterParams* fp, cud
   }
   // stage all bitsets contiguously in pinned memory, one H2D copy
   if (words) {
-    CSS_CHECK(ensure_pinned(h, words * 4));
-    uint32_t* stage = reinterpret_cast<uint32_t*>(h->pinned);
+    // behind the caller's own staging area (query / results of css_index_search): no wait between the two uses
+    CSS_CHECK(ensure_pinned(h, pinned_front + words * 4));
+    uint32_t* stage = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(h->pinned) + pinned_front);
     size_t off = 0;
     for (int i = 0; i < f->n_clauses; ++i) {
       const css_clause& c = f->clauses[i];
@@ -234,9 +235,7 @@ int build_filter_params(css_index* h, const css_filter* f, FilterParams* fp, cud
       CSS_CHECK(dev_alloc(&h->rowmask_scratch, (size_t)words_for(h->capacity)));
       h->rowmask_words = words_for(h->capacity);
     }
-    // the staging buffer for set bits was already consumed by an async copy on the same
-    // stream; pageable source is fine here (synchronous w.r.t. host)
-    CSS_CUDA(cudaStreamSynchronize(st));
+    // pageable source: the driver has staged the bytes when the call returns
     CSS_CUDA(cudaMemcpyAsync(h->rowmask_scratch, f->row_mask, (size_t)w * 4, cudaMemcpyHostToDevice, st));
     fp->row_mask = h->rowmask_scratch;
   }
@@ -250,8 +249,28 @@ namespace css {
 // Evaluate `f` into h->mask.  *mask_out = nullptr when every row passes trivially; *ignore_alive_out
 // tells the caller that the alive bits must NOT be substituted for a null mask (css_filter.ignore_alive:
 // HybridStorage's reference mode wants the orphans in its global top-100 window).
+// Serialised form of a filter (clauses + set bits) for the "same filter as last time?" test.
+static bool filter_key(const css_filter* f, std::vector<uint32_t>* key) {
+  key->clear();
+  if (f && f->row_mask) return false;   // an explicit row mask is not compared (ntotal / 8 bytes): always evaluated
+  key->push_back(f ? (uint32_t)f->n_clauses : 0u);
+  key->push_back(f ? (uint32_t)f->ignore_alive : 0u);
+  if (!f) return true;
+  for (int i = 0; i < f->n_clauses; ++i) {
+    const css_clause& c = f->clauses[i];
+    key->push_back((uint32_t)c.column);
+    key->push_back((uint32_t)c.kind);
+    key->push_back((uint32_t)c.lo);
+    key->push_back((uint32_t)c.hi);
+    key->push_back((uint32_t)c.set_nbits);
+    if (c.kind == CSS_CLAUSE_SET && c.set_bits)
+      key->insert(key->end(), c.set_bits, c.set_bits + (size_t)(c.set_nbits + 31) / 32);
+  }
+  return true;
+}
+
 int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, int64_t* n_pass,
-                bool need_count, cudaStream_t st, bool* ignore_alive_out) {
+                bool need_count, cudaStream_t st, bool* ignore_alive_out, size_t pinned_front) {
   const bool ignore_alive = f && f->ignore_alive;
   if (ignore_alive_out) *ignore_alive_out = ignore_alive;
   const bool trivial = (!f || (f->n_clauses == 0 && !f->row_mask)) && (!h->any_dead || ignore_alive);
@@ -265,9 +284,20 @@ int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, in
     if (n_pass) *n_pass = 0;
     return CSS_OK;
   }
+  // the mask of an unchanged filter over an unchanged index is still in h->mask (evaluated on the handle's own
+  // stream order; a different stream would have to wait for that evaluation, so the shortcut is for st == h->stream)
+  std::vector<uint32_t> key;
+  const bool cacheable = filter_key(f, &key) && st == h->stream && f != nullptr && f->n_clauses > 0;
+  if (cacheable && h->mask_version == h->version && key == h->mask_key && (!n_pass || h->mask_n_pass >= 0)) {
+    *mask_out = h->mask;
+    if (n_pass) *n_pass = h->mask_n_pass;
+    return CSS_OK;
+  }
+  h->mask_version = ~0ull;
   FilterParams fp;
-  CSS_CHECK(build_filter_params(h, f, &fp, st));
-  CSS_CUDA(cudaMemsetAsync(h->n_pass_dev, 0, sizeof(unsigned long long), st));
+  CSS_CHECK(build_filter_params(h, f, &fp, st, pinned_front));
+  if (n_pass) CSS_CUDA(cudaMemsetAsync(h->n_pass_dev, 0, sizeof(unsigned long long), st));
+  else fp.n_pass = nullptr;
   int64_t blocks = (h->ntotal + 255) / 256;
   filter_mask_kernel<<<(unsigned)blocks, 256, 0, st>>>(fp);
   CSS_LAUNCHED();
@@ -277,6 +307,11 @@ int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, in
     CSS_CUDA(cudaMemcpyAsync(&c, h->n_pass_dev, sizeof(c), cudaMemcpyDeviceToHost, st));
     CSS_CUDA(cudaStreamSynchronize(st));
     *n_pass = (int64_t)c;
+  }
+  if (cacheable) {
+    h->mask_key.swap(key);
+    h->mask_version = h->version;
+    h->mask_n_pass = n_pass ? *n_pass : -1;
   }
   return CSS_OK;
 }
@@ -594,6 +629,7 @@ void index_destroy_single(css_index* h) {
 // copied straight into x and finished in place (normalisation, bf16 shadow, maxima).  Asynchronous
 // on the handle's stream; the caller synchronises.  Rows beyond ntotal must fit the capacity.
 int put_rows_host_async(css_index* h, const float* x_host, int64_t row0, int64_t n, int normalize) {
+  h->version++;
   float* dst = h->x + (size_t)row0 * h->dim;
   CSS_CUDA(cudaMemcpyAsync(dst, x_host, (size_t)n * h->dim * 4, cudaMemcpyHostToDevice, h->stream));
   return finish_rows(h, dst, row0, n, normalize, h->stream);
@@ -605,11 +641,13 @@ int single_add(css_index* h, const float* x_host, int64_t n, int normalize, bool
   CSS_CHECK(put_rows_host_async(h, x_host, h->ntotal, n, normalize));
   CSS_CHECK(mark_alive(h, h->ntotal, n, h->stream));
   h->ntotal += n;
+  h->version++;
   if (sync) CSS_CUDA(cudaStreamSynchronize(h->stream));
   return CSS_OK;
 }
 
 int single_reset(css_index* h) {
+  h->version++;
   h->ntotal = 0;
   h->any_dead = false;
   CSS_CUDA(cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream));
@@ -628,6 +666,7 @@ int single_reset(css_index* h) {
 }
 
 int single_set_column(css_index* h, int column, const int32_t* values_host, int64_t start, int64_t n, bool sync) {
+  h->version++;
   CSS_CHECK(ensure_column(h, column));
   CSS_CUDA(cudaMemcpyAsync(h->cols[column] + start, values_host, (size_t)n * 4, cudaMemcpyHostToDevice, h->stream));
   if (sync) CSS_CUDA(cudaStreamSynchronize(h->stream));
@@ -636,6 +675,7 @@ int single_set_column(css_index* h, int column, const int32_t* values_host, int6
 
 int single_set_alive_ids(css_index* h, const int64_t* ids_host, int64_t n, int alive) {
   if (n == 0) return CSS_OK;
+  h->version++;
   if (n > h->ids_scratch_n) {
     cudaFree(h->ids_scratch);
     h->ids_scratch_n = 0;
@@ -654,7 +694,10 @@ int single_set_alive_ids(css_index* h, const int64_t* ids_host, int64_t n, int a
 
 int single_grow(css_index* h, int64_t cap) { return grow(h, cap); }
 int single_ensure_room(css_index* h, int64_t extra) { return ensure_room(h, extra); }
-int single_mark_alive(css_index* h, int64_t row0, int64_t n) { return mark_alive(h, row0, n, h->stream); }
+int single_mark_alive(css_index* h, int64_t row0, int64_t n) {
+  h->version++;
+  return mark_alive(h, row0, n, h->stream);
+}
 
 }  // namespace css
 
@@ -792,6 +835,7 @@ int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep
   }
   CSS_CUDA(cudaStreamSynchronize(st));
   h->ntotal = n_keep;
+  h->version++;
   h->any_dead = true;   // conservative: the scan keeps honouring the alive bits
   return CSS_OK;
 }
@@ -830,6 +874,7 @@ int css_index_add_device(css_index* h, const float* x_dev, int64_t n, int normal
   }
   CSS_CHECK(append_from_device(h, x_dev, n, normalize, st));
   h->ntotal += n;
+  h->version++;
   return CSS_OK;
 }
 
@@ -873,6 +918,7 @@ int css_index_set_alive(css_index* h, const uint8_t* alive_host, int64_t start, 
   DeviceGuard g(h->device);
   uint8_t* tmp = nullptr;
   CSS_CHECK(dev_alloc(&tmp, (size_t)n));
+  h->version++;
   int rc = CSS_OK;
   cudaError_t e = cudaMemcpyAsync(tmp, alive_host, (size_t)n, cudaMemcpyHostToDevice, h->stream);
   if (e == cudaSuccess) {
@@ -914,7 +960,7 @@ int css_index_filter_mask(css_index* h, const css_filter* f, uint32_t* mask_out_
   // force evaluation even for the trivial filter so the mask is materialised
   css_filter empty;
   memset(&empty, 0, sizeof(empty));
-  CSS_CHECK(eval_filter(h, f ? f : &empty, &m, &n_pass, /*need_count=*/true, h->stream, nullptr));
+  CSS_CHECK(eval_filter(h, f ? f : &empty, &m, &n_pass, /*need_count=*/true, h->stream, nullptr, 0));
   if (h->ntotal > 0) {
     CSS_CUDA(cudaMemcpyAsync(mask_out_host, h->mask, (size_t)words_for(h->ntotal) * 4,
                              cudaMemcpyDeviceToHost, h->stream));
@@ -933,7 +979,7 @@ int css_index_filter_mask_device(css_index* h, const css_filter* f, const uint32
   std::lock_guard<std::mutex> lk(h->mu);
   DeviceGuard g(h->device);
   cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-  return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st, nullptr);
+  return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st, nullptr, 0);
 }
 
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream) {
@@ -1019,15 +1065,14 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   }
   css_scan_scratch* sc = nullptr;
   CSS_CHECK(get_scratch(h, st, nq, &sc));
+  // pinned staging: [q | D | I | overflow count | clause bitsets of the filter]
+  const size_t front = (qbytes + dbytes + ibytes + 128 + 63) / 64 * 64;
+  CSS_CHECK(ensure_pinned(h, front));
   const uint32_t* m = nullptr;
   bool ignore_alive = false;
-  CSS_CHECK(eval_filter(h, filter, &m, nullptr, false, st, &ignore_alive));
+  CSS_CHECK(eval_filter(h, filter, &m, nullptr, false, st, &ignore_alive, front));
   if (!m && h->any_dead && !ignore_alive) m = h->alive;
-  // pinned staging: [q | D | I | overflow count]
-  CSS_CHECK(ensure_pinned(h, qbytes + dbytes + ibytes + 128));
   unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
-  // set bitsets staged in the same pinned block were consumed by an async copy: wait for it
-  if (filter && filter->n_clauses) CSS_CUDA(cudaStreamSynchronize(st));
   memcpy(pin, q_host, qbytes);
   size_t d_off = (qbytes + 15) / 16 * 16;
   size_t i_off = (d_off + dbytes + 15) / 16 * 16;

@@ -79,6 +79,11 @@ struct css_index {
   uint32_t* rowmask_scratch = nullptr;  // uploaded explicit row mask
   int64_t rowmask_words = 0;
   unsigned long long* n_pass_dev = nullptr;
+  // the filter evaluated into `mask` last: an unchanged filter over an unchanged index is not evaluated again
+  uint64_t version = 0;              // bumped by everything that changes rows, columns or alive bits
+  uint64_t mask_version = ~0ull;
+  std::vector<uint32_t> mask_key;
+  int64_t mask_n_pass = -1;
   int64_t* ids_scratch = nullptr;    // css_index_set_alive_ids
   int64_t ids_scratch_n = 0;
   // scratch (pinned host)
@@ -125,7 +130,7 @@ int get_scratch(css_index* h, cudaStream_t st, int nq, css_scan_scratch** out);
 int ensure_pinned(css_index* h, size_t bytes);
 IdMap index_idmap(const css_index* h, int64_t id_offset);
 int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, int64_t* n_pass, bool need_count,
-                cudaStream_t st, bool* ignore_alive_out);
+                cudaStream_t st, bool* ignore_alive_out, size_t pinned_front);
 int search_on_device(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* m,
                      const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, cudaStream_t st,
                      bool defer_fallback, bool* two_phase_used);

@@ -233,6 +233,7 @@ int css_index_load(css_index* h, const char* path) {
         if (rc == CSS_OK) rc = io.mark(h, b, sp.shard);
         if (rc != CSS_OK) break;
         sh->ntotal = sp.local + sp.n;
+        sh->version++;
       }
     }
     if (rc == CSS_OK) rc = io.wait(h, 0);

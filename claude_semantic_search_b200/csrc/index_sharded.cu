@@ -374,7 +374,7 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
       fp = &fs;
     }
     bool ignore_alive = false;
-    CSS_CHECK(eval_filter(sh, fp, &masks[s], nullptr, false, st, &ignore_alive));
+    CSS_CHECK(eval_filter(sh, fp, &masks[s], nullptr, false, st, &ignore_alive, 0));
     if (!masks[s] && sh->any_dead && !ignore_alive) masks[s] = sh->alive;
   }
   // Pass 2, one host thread per shard: query upload, the scans (and, on the exchange path, the in-kernel merge)
@@ -476,6 +476,7 @@ int sharded_compact(css_index* h, const int64_t* keep, int64_t n_keep) {
     }
     CSS_CUDA(cudaStreamSynchronize(sh->stream));
     sh->ntotal = nl;
+    sh->version++;
     sh->any_dead = false;
   }
   h->composite_ntotal = n_keep;

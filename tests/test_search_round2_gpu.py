@@ -437,3 +437,57 @@ def test_in_kernel_exchange_between_processes(native, tmp_path, world):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     for rk in range(world):
         assert f"rank {rk} ok" in r.stdout
+
+
+def test_repeated_filter_reuses_mask_until_the_index_changes(native):
+    """An unchanged filter over an unchanged index is not evaluated again (its mask is still on the device); any
+    change of rows, columns or alive bits invalidates it."""
+    rng = np.random.default_rng(41)
+    n, d = 50_000, 768
+    x = so.normalize_rows(rng.standard_normal((n, d), dtype=np.float32))
+    q = so.normalize_rows(rng.standard_normal((3, d), dtype=np.float32))
+    col = rng.integers(0, 20, size=n).astype(np.int32)
+    idx = native.Index(d)
+    idx.add(x)
+    idx.set_column(1, col)
+    launches = native.kernel_launch_count
+
+    def filt(lo, hi, allowed):
+        return native.Filter().add_range(1, lo, hi).add_set(1, allowed, 20)
+
+    def expect(lo, hi, allowed, alive=None):
+        m = (col >= lo) & (col <= hi) & np.isin(col, allowed)
+        return m if alive is None else (m & alive)
+
+    f1 = filt(3, 12, [3, 4, 5, 9, 12, 15])
+    l0 = launches()
+    D1, I1 = idx.search(q[:1], 10, f1)
+    first = launches() - l0
+    l0 = launches()
+    D2, I2 = idx.search(q[:1], 10, filt(3, 12, [3, 4, 5, 9, 12, 15]))     # an equal filter, rebuilt
+    again = launches() - l0
+    assert again == first - 1, (first, again)                               # the filter kernel was skipped
+    np.testing.assert_array_equal(I1, I2)
+    Dr, Ir = so.flat_search_c(x, q[:1], 10, mask_words=so.pack_mask(expect(3, 12, [3, 4, 5, 9, 12, 15])))
+    _check(Dr, Ir, D2, I2)
+    D3, I3 = idx.search(q[:1], 10, filt(3, 12, [3, 4, 5, 9, 12]))          # one bit of the set differs: evaluated
+    Dr, Ir = so.flat_search_c(x, q[:1], 10, mask_words=so.pack_mask(expect(3, 12, [3, 4, 5, 9, 12])))
+    _check(Dr, Ir, D3, I3)
+    # index changes: column rewrite, kill, append -- each invalidates the cached mask
+    col[:] = (col + 7) % 20
+    idx.set_column(1, col)
+    D4, I4 = idx.search(q[:1], 10, filt(3, 12, [3, 4, 5, 9, 12]))
+    Dr, Ir = so.flat_search_c(x, q[:1], 10, mask_words=so.pack_mask(expect(3, 12, [3, 4, 5, 9, 12])))
+    _check(Dr, Ir, D4, I4)
+    alive = np.ones(n, bool)
+    alive[I4[0][:5]] = False
+    idx.set_alive_ids(I4[0][:5], False)
+    D5, I5 = idx.search(q[:1], 10, filt(3, 12, [3, 4, 5, 9, 12]))
+    Dr, Ir = so.flat_search_c(x, q[:1], 10, mask_words=so.pack_mask(expect(3, 12, [3, 4, 5, 9, 12], alive)))
+    _check(Dr, Ir, D5, I5)
+    extra = so.normalize_rows(q[:1] + 0.01 * rng.standard_normal((4, d), dtype=np.float32))
+    idx.add(extra)
+    idx.set_column(1, np.full(4, 4, np.int32), start=n)
+    D6, I6 = idx.search(q[:1], 10, filt(3, 12, [3, 4, 5, 9, 12]))
+    assert set(I6[0][:4].tolist()) == {n, n + 1, n + 2, n + 3}
+    idx.close()
