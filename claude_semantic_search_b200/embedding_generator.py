@@ -54,6 +54,12 @@ class EmbeddingStats:
     model_info: Dict[str, Any] = field(default_factory=dict)
 
 
+def _has_embedding(c: Chunk) -> bool:
+    """`if c.embedding` of the reference (src/embeddings.py:249,274), also for ndarray-view embeddings
+    (EmbeddingConfig.embedding_as_ndarray), whose truth value is ambiguous."""
+    return c.embedding is not None and len(c.embedding) > 0
+
+
 class EmbeddingGenerator:
     def __init__(self, config: Optional[EmbeddingConfig] = None):
         self.config = config or EmbeddingConfig()
@@ -169,7 +175,7 @@ class EmbeddingGenerator:
 
     def save_embeddings(self, chunks: List[Chunk], file_path: str) -> None:
         data = [{"chunk_id": c.id, "embedding": c.embedding, "text": c.text, "metadata": c.metadata}
-                for c in chunks if c.embedding]
+                for c in chunks if _has_embedding(c)]
         np.savez_compressed(file_path, embeddings=data)
         self.logger.info("Saved %d embeddings to %s", len(data), file_path)
 
@@ -185,7 +191,7 @@ class EmbeddingGenerator:
                                "embedding_stats": {}, "issues": []}
         embs = []
         for c in chunks:
-            if c.embedding:
+            if _has_embedding(c):
                 res["chunks_with_embeddings"] += 1
                 embs.append(np.array(c.embedding))
                 if res["embedding_dimension"] is None:

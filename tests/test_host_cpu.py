@@ -310,3 +310,20 @@ def test_missing_checkpoint_is_an_error_not_a_download(tmp_path, monkeypatch):
     d.mkdir()
     (d / "model.safetensors").write_bytes(b"")
     assert _find_model_dir("sentence-transformers/all-mpnet-base-v2", str(tmp_path)) == d
+
+
+def test_embedding_helpers_accept_ndarray_views(tmp_path):
+    """save / validate follow `if c.embedding` of the reference (src/embeddings.py:249,274) and must not trip
+    over the ndarray-view embeddings of EmbeddingConfig.embedding_as_ndarray."""
+    from claude_semantic_search_b200 import Chunk, EmbeddingGenerator
+    g = EmbeddingGenerator()
+    v = np.ones(768, dtype=np.float32) / np.sqrt(768.0)
+    chunks = [Chunk(id="a", text="x", metadata={}, embedding=v),
+              Chunk(id="b", text="y", metadata={}, embedding=v.tolist()),
+              Chunk(id="c", text="z", metadata={}, embedding=None)]
+    res = g.validate_embeddings(chunks)
+    assert res["chunks_with_embeddings"] == 2 and res["embedding_dimension"] == 768
+    assert any("Missing embedding for chunk c" in s for s in res["issues"])
+    path = str(tmp_path / "e.npz")
+    g.save_embeddings(chunks, path)
+    assert [c.id for c in g.load_embeddings(path)] == ["a", "b"]
