@@ -72,11 +72,13 @@ struct AttnTcParams {
   int rel_half;
   int n_seq;
   __nv_bfloat16* ctx;       // [T, 768]
-  long long* trace;         // optional [5 roles][128 items][8 tags] clock64 stamps of CTA 0 (profiling aid)
+  int trace_cta;            // the CTA whose timeline is recorded (CSS_ATTN_TRACE_CTA)
+  long long* trace;         // optional [6 roles][128 items][8 tags] clock64 stamps of one CTA + every CTA's start / end time (profiling aid)
 };
 
+// Timeline stamps of ONE CTA (AttnTcParams::trace_cta): every other CTA carries a null pointer.
 __device__ __forceinline__ void attn_trace(long long* trace, int role, uint32_t item, int tag) {
-  if (trace != nullptr && blockIdx.x == 0 && item < 128u) trace[(role * 128 + item) * 8 + tag] = clock64();
+  if (trace != nullptr && item < 128u) trace[(role * 128 + item) * 8 + tag] = clock64();
 }
 
 // Every role walks the same item sequence: units u = blockIdx.x, +gridDim.x, ...; unit = (sequence,
@@ -279,6 +281,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 
   AttnWalk w;
   w.init(cu, p.n_seq * kHeads);
+  long long* const trace = (p.trace != nullptr && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
+  if (p.trace != nullptr && threadIdx.x == 0) {   // start: wall clock (ns) of every CTA, SM clock of the traced CTA
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    if (blockIdx.x < 200) p.trace[5 * 1024 + 600 + 2 * blockIdx.x] = (long long)ns;
+    if (trace != nullptr) {
+      trace[127 * 8 + 6] = clock64();
+      trace[127 * 8 + 7] = (long long)ns;
+    }
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -315,7 +327,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       m.o_full = o_full; m.o_free = o_free; m.p_full = p_full; m.p_empty = p_empty;
       m.sQ = tc::smem_u32(sQ); m.sK = tc::smem_u32(sK); m.sV = tc::smem_u32(sV); m.sP = tc::smem_u32(sP);
       m.tmem_base = tmem_base;
-      m.trace = p.trace;
+      m.trace = trace;
       m.run(w);
     }
   } else if (warp < 6) {
@@ -327,14 +339,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     while (w.advance()) {
       const uint32_t par = e & 1, ph = (e >> 1) & 1;
       const bool tr = lane == 0 && quarter == 0;
-      if (tr) attn_trace(p.trace, 4, e, 0);
+      if (tr) attn_trace(trace, 4, e, 0);
       tc::mbar_wait_sleep(st_full + par, ph, 300);
       const float* st = sStat + par * 4 * 128;
       const float inv = 1.f / ((st[r] + st[128 + r]) + (st[256 + r] + st[384 + r]));
-      if (tr) attn_trace(p.trace, 4, e, 1);
+      if (tr) attn_trace(trace, 4, e, 1);
       tc::mbar_wait_sleep(o_full + par, ph, 100);
       tc::tc_fence_after();
-      if (tr) attn_trace(p.trace, 4, e, 2);
+      if (tr) attn_trace(trace, 4, e, 2);
       uint32_t a[32], b[32];
       tc::tmem_ld_32x32(lane_addr + par * kHeadDim, a);
       tc::tmem_ld_32x32(lane_addr + par * kHeadDim + 32, b);
@@ -386,7 +398,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
           *reinterpret_cast<uint4*>(p.ctx + (size_t)(w.t0 + q0 + rr) * kHidden + w.h * kHeadDim + c * 8) = o;
         }
       }
-      if (tr) attn_trace(p.trace, 4, e, 3);
+      if (tr) attn_trace(trace, 4, e, 3);
       ++e;
     }
     if (threadIdx.x == 64) tc::tma_store_wait_all();   // the last tile has left shared memory
@@ -422,14 +434,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const float* rel_i = relbuf + (kAttnTcMaxLen - 1) - i;   // rel_i[j] = bias(j - i) * log2e
       const uint32_t par = n & 1;
       const bool tr = lane == 0 && ch == 0 && quarter == 0 && g == 0;
-      if (tr) attn_trace(p.trace, 2 + g, n, 0);
+      if (tr) attn_trace(trace, 2 + g, n, 0);
       uint32_t v[kAtHf][32];
       // ---- pass 1: maximum of the raw scores over this thread's real keys ----
       float mx = -INFINITY;
       if (nb > 0) {
         tc::mbar_wait(s_full + g, ng & 1);
         tc::tc_fence_after();
-        if (tr) attn_trace(p.trace, 2 + g, n, 1);
+        if (tr) attn_trace(trace, 2 + g, n, 1);
         // blocks in descending order: block 0's scores are still in registers when pass 2 starts
         for (int lb = nb - 1; lb >= 0; --lb) {
           const int c0 = key0 + lb * 64;
@@ -458,9 +470,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       float* xm = sXmax + par * 4 * 128;
       xm[slot * 128 + r] = mx;
       if (kAtHf == 2) xm[(slot + 1) * 128 + r] = mx;
-      if (tr) attn_trace(p.trace, 2 + g, n, 2);
+      if (tr) attn_trace(trace, 2 + g, n, 2);
       asm volatile("bar.sync 1, %0;" ::"n"(2 * kAtGW * 32) : "memory");
-      if (tr) attn_trace(p.trace, 2 + g, n, 3);
+      if (tr) attn_trace(trace, 2 + g, n, 3);
       mx = fmaxf(fmaxf(xm[r], xm[128 + r]), fmaxf(xm[256 + r], xm[384 + r]));
       // upper bound of the row maximum of (s/8 + bias) in the log2 domain
       const float m_hat = fmaf(mx, kScale, sRelMax[w.h]);
@@ -536,7 +548,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(p_full + g * 2 + buf);
-        if (tr) attn_trace(p.trace, 2 + g, n, 4 + lb);
+        if (tr) attn_trace(trace, 2 + g, n, 4 + lb);
       }
       float sum_lo, sum_hi;
       f32x2_unpack(sum2, sum_lo, sum_hi);
@@ -556,6 +568,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 1) tc::tmem_dealloc(tmem_base, 512);
+  if (p.trace != nullptr && threadIdx.x == 0) {   // end
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    if (blockIdx.x < 200) p.trace[5 * 1024 + 600 + 2 * blockIdx.x + 1] = (long long)ns;
+    if (trace != nullptr) {
+      trace[(128 + 127) * 8 + 6] = clock64();
+      trace[(128 + 127) * 8 + 7] = (long long)ns;
+    }
+  }
 }
 
 // Host launcher.  qkv: [T, 2304] bf16 packed (q | k | v).
@@ -582,6 +603,8 @@ static int attention_tc_launch(const __nv_bfloat16* qkv, int T, const int32_t* c
   p.n_seq = n_seq;
   p.ctx = ctx;
   p.trace = trace;
+  const char* cta_env = trace ? getenv("CSS_ATTN_TRACE_CTA") : nullptr;
+  p.trace_cta = cta_env ? atoi(cta_env) : 0;
   const int units = n_seq * kHeads;
   const int grid = units < n_sm ? units : n_sm;
   attention_tc_kernel<<<grid, kAttnTcThreads, kAtSmem, st>>>(tq, tkv, to, p);

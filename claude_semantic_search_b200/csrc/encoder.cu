@@ -867,10 +867,10 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
     DevBuf maxd;
     CSS_CHECK(maxd.alloc(kHeads * 4));
     CSS_CUDA(cudaMemcpy(maxd.p, tmax.data(), kHeads * 4, cudaMemcpyHostToDevice));
-    // CSS_ATTN_TRACE=<file>: dump CTA 0's clock64 stamps [5 roles][128 items][8 tags] (profiling aid)
+    // CSS_ATTN_TRACE=<file>: dump CTA 0's clock64 stamps [6 roles][128 items][8 tags] (profiling aid)
     const char* trace_path = getenv("CSS_ATTN_TRACE");
     DevBuf traced;
-    const size_t trace_n = 5 * 128 * 8;
+    const size_t trace_n = 6 * 128 * 8;
     if (trace_path) {
       CSS_CHECK(traced.alloc(trace_n * 8));
       CSS_CUDA(cudaMemset(traced.p, 0, trace_n * 8));
@@ -880,6 +880,45 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
                                     (const float*)reld.p, (const float*)maxd.p, rel_half, (__nv_bfloat16*)c16.p,
                                     sm_count(device), st, (long long*)traced.p));
     CSS_CUDA(cudaStreamSynchronize(st));
+    // CSS_ATTN_TIME=<reps>: CUDA-event time of the kernel alone (profiling aid, printed to stderr)
+    if (const char* reps_env = getenv("CSS_ATTN_TIME")) {
+      const int reps = std::max(1, atoi(reps_env));
+      cudaEvent_t e0, e1;
+      CSS_CUDA(cudaEventCreate(&e0));
+      CSS_CUDA(cudaEventCreate(&e1));
+      CSS_CUDA(cudaEventRecord(e0, st));
+      for (int rep = 0; rep < reps; ++rep)
+        CSS_CHECK(attention_tc_launch((const __nv_bfloat16*)q16.p, T, (const int32_t*)cud.p, n_seq, max_len,
+                                      (const float*)reld.p, (const float*)maxd.p, rel_half, (__nv_bfloat16*)c16.p,
+                                      sm_count(device), st, (long long*)traced.p));
+      CSS_CUDA(cudaEventRecord(e1, st));
+      CSS_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CSS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      fprintf(stderr, "css_debug_attention: %d sequences, %d tokens, %.2f us per launch (%d launches)\n", n_seq, T,
+              1e3f * ms / reps, reps);
+      if (trace_path) {   // CTA 0 of the last launch: cycles and nanoseconds from its first to its last instruction
+        long long t[4];
+        CSS_CUDA(cudaMemcpy(t, (long long*)traced.p + 127 * 8 + 6, 16, cudaMemcpyDeviceToHost));
+        CSS_CUDA(cudaMemcpy(t + 2, (long long*)traced.p + (128 + 127) * 8 + 6, 16, cudaMemcpyDeviceToHost));
+        fprintf(stderr, "css_debug_attention: CTA 0 of the last launch: %lld cycles in %.2f us (%.0f MHz)\n", t[2] - t[0],
+                1e-3 * (double)(t[3] - t[1]), 1e3 * (double)(t[2] - t[0]) / (double)(t[3] - t[1]));
+        std::vector<long long> se(2 * 148);
+        CSS_CUDA(cudaMemcpy(se.data(), (long long*)traced.p + 5 * 1024 + 600, se.size() * 8, cudaMemcpyDeviceToHost));
+        long long s0 = se[0], s1 = se[0], e0 = se[1], e1 = se[1], dmin = se[1] - se[0], dmax = dmin;
+        for (int b = 0; b < 148; ++b) {
+          s0 = std::min(s0, se[2 * b]); s1 = std::max(s1, se[2 * b]);
+          e0 = std::min(e0, se[2 * b + 1]); e1 = std::max(e1, se[2 * b + 1]);
+          dmin = std::min(dmin, se[2 * b + 1] - se[2 * b]); dmax = std::max(dmax, se[2 * b + 1] - se[2 * b]);
+        }
+        for (int b = 0; b < 148; ++b) fprintf(stderr, "%d%c", (int)((se[2 * b + 1] - se[2 * b]) / 1000), b % 37 == 36 ? '\n' : ' ');
+        fprintf(stderr, "css_debug_attention: CTA starts spread %.1f us, ends spread %.1f us, CTA lifetime %.1f .. %.1f us, "
+                "first start to last end %.1f us\n", 1e-3 * (s1 - s0), 1e-3 * (e1 - e0), 1e-3 * dmin, 1e-3 * dmax,
+                1e-3 * (e1 - s0));
+      }
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+    }
     if (trace_path) {
       std::vector<long long> host(trace_n);
       CSS_CUDA(cudaMemcpy(host.data(), traced.p, trace_n * 8, cudaMemcpyDeviceToHost));
