@@ -27,6 +27,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&t);
 }
 
+// Streaming stores of the GEMM epilogues: the activations (hundreds of MB per launch) must not allocate in L1.  With
+// 227 KB of shared memory the L1 is ~28 KB and has to keep what the epilogue re-reads for every tile -- the bias /
+// gamma / beta vectors and the few spilled registers; with default stores their hit rate was 25 % / 16 % (ncu), i.e.
+// every such load paid the L2 latency and the K = 768 projection ran at 42 % tensor-pipe activity.
+__device__ __forceinline__ void st_global_stream(void* ptr, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st_global_stream(void* ptr, const float2& v) {
+  asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(ptr), "f"(v.x), "f"(v.y) : "memory");
+}
+
 // Packed fp32x2 arithmetic of sm_100 (two independent fp32 lanes in one 64-bit register).
 __device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
   uint64_t r;
@@ -453,14 +465,16 @@ struct EpiBiasBf16 {
   };
   const Params& p;
   uint8_t* stage;
-  float2 mr_cur = make_float2(0.f, 1.f), mr_next = make_float2(0.f, 1.f);
+  float2 mr_cur = make_float2(0.f, 1.f);
   __device__ EpiBiasBf16(const Params& p_, int, uint8_t* stage_) : p(p_), stage(stage_) {}
+  // Called before the wait for the tile's accumulator: the row statistics arrive while the tensor core still works
+  // on the tile.  (Requested a tile ahead they were spilled by ptxas -- a store that waits for the load on the spot.)
+  __device__ __forceinline__ void tile_begin(int m_warp, int lane, int M) {
+    if constexpr (kFold) mr_cur = __ldg(p.mr + min(m_warp + lane, M - 1));
+  }
   __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
     uint4* srow = reinterpret_cast<uint4*>(stage + lane * kRowBytes);
-    if constexpr (kFold) {
-      if (slot == 0) mr_cur = mr_next;   // this tile's row statistics, requested a tile ahead
-    }
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       const float4 ba = __ldg(b4 + g * 2), bb = __ldg(b4 + g * 2 + 1);
@@ -502,16 +516,12 @@ struct EpiBiasBf16 {
       const int m = m_warp + r;
       if (m < M) {
         const uint4 o = *reinterpret_cast<const uint4*>(stage + r * kRowBytes + piece * 16);
-        *reinterpret_cast<uint4*>(p.out + (size_t)m * p.ldo + n0 + piece * 8) = o;
+        st_global_stream(p.out + (size_t)m * p.ldo + n0 + piece * 8, o);
       }
     }
     __syncwarp();
   }
-  __device__ __forceinline__ void prefetch(int slot, int m_warp, int lane, int M, int) {
-    if constexpr (kFold) {
-      if (slot == 0) mr_next = __ldg(p.mr + min(m_warp + lane, M - 1));
-    }
-  }
+  __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
   __device__ __forceinline__ void prefetch_none() {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
@@ -616,9 +626,12 @@ struct EpiResidLN {
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + slot_off(r, piece)), "l"(src) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
+    // (mean, rstd) of the next tile's residual rows, a tile ahead (requested at the start of the tile instead, before
+    // the wait for the accumulator, the K = 768 projection was 7 % slower: 230k against 214k cycles)
     if (p.rmr != nullptr && slot == 0) mr_next = __ldg(p.rmr + min(m_warp + lane, M - 1));
   }
   __device__ __forceinline__ void prefetch_none() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void tile_begin(int, int, int) {}
   __device__ __forceinline__ void chunk(int slot, int m_warp, int lane, int M, int n0, const uint32_t (&v)[32]) {
     uint8_t* blk = stage + slot * kSlotBytes;
     // the copy into this slot was committed one tile ago; the only younger group is the other chunk's
@@ -672,7 +685,7 @@ struct EpiResidLN {
       const int m = m_warp + r;
       if (m < M) {
         const uint4 o = *reinterpret_cast<const uint4*>(blk + slot_off(r, piece));
-        *reinterpret_cast<uint4*>(p.out + (size_t)m * kHidden + n0 + piece * 8) = o;
+        st_global_stream(p.out + (size_t)m * kHidden + n0 + piece * 8, o);
       }
     }
     __syncwarp();
@@ -683,7 +696,7 @@ struct EpiResidLN {
       float s0, s1, q0, q1;
       f32x2_unpack(sum2, s0, s1);
       f32x2_unpack(sq2, q0, q1);
-      if (my_row < M) p.stats[((size_t)my_row * num_n + nb) * kSplit + colq] = make_float2(s0 + s1, q0 + q1);
+      if (my_row < M) st_global_stream(p.stats + ((size_t)my_row * num_n + nb) * kSplit + colq, make_float2(s0 + s1, q0 + q1));
       sum2 = 0ull;
       sq2 = 0ull;
     } else {

@@ -205,6 +205,7 @@ struct EpiSearch {
   }
   __device__ __forceinline__ void prefetch(int, int, int, int, int) {}
   __device__ __forceinline__ void prefetch_none() {}
+  __device__ __forceinline__ void tile_begin(int, int, int) {}
   __device__ __forceinline__ void tile_end(int, int, int, int) {}
   __device__ __forceinline__ void finish() {}
 };
