@@ -112,6 +112,29 @@ def bench_single_query(enc, reps: int = 300):
     return out
 
 
+def bench_multi_device_handle(n_dev: int, n_seq: int, ids, cu, emb_one, reps: int = 5):
+    """north_star: embedding batches split data-parallel over the GPUs of one box behind the unchanged API.  One
+    process, one MultiDeviceEncoder (EmbeddingConfig.devices) over `n_dev` GPUs, host ids in -> host embeddings out for
+    n_dev x n_seq chunks per call; the rows must equal the single-device result bit for bit."""
+    from claude_semantic_search_b200.encoder import MPNetEncoder, MultiDeviceEncoder, random_state_dict
+    sd = random_state_dict(0)
+    enc = MultiDeviceEncoder.create(lambda d: MPNetEncoder(sd, device=d, max_tokens=n_seq * SEQ_LEN), list(range(n_dev)))
+    big_ids = np.tile(ids, n_dev)
+    big_cu = (np.arange(n_dev * n_seq + 1, dtype=np.int64) * SEQ_LEN).astype(np.int32)
+    got = enc.encode_packed(big_ids, big_cu)           # sizes the staging buffers of every device
+    same = all(np.array_equal(got[r * n_seq:(r + 1) * n_seq], emb_one) for r in range(n_dev))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        enc.encode_packed(big_ids, big_cu)
+    dt = (time.perf_counter() - t0) / reps
+    enc.close()
+    assert same, "multi-device encode differs from the single-device result"
+    return {"n_devices": n_dev, "chunks_per_call": n_dev * n_seq, "e2e_chunks_per_s": n_dev * n_seq / dt,
+            "check": "every device's rows == the single-device embeddings bit for bit",
+            "api": "MultiDeviceEncoder.encode_packed behind EmbeddingConfig.devices (one process, host ids -> host embeddings, "
+                   "one css_encoder per GPU, one host thread per GPU, no collective)"}
+
+
 def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warmup: int = 3):
     from claude_semantic_search_b200 import _native as native
     from claude_semantic_search_b200.encoder import MPNetEncoder, random_state_dict
@@ -173,6 +196,31 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warm
         except Exception as e:  # report, never hide
             query_leg = {"error": repr(e)}
     enc.close()
+    multi_leg = None
+    if world > 1:
+        # the single-process multi-device handle (EmbeddingConfig.devices): rank 0 drives all GPUs of the job while the
+        # other ranks sleep on a flag file (an NCCL barrier would park a spinning kernel on the GPUs under test)
+        import tempfile
+        from pathlib import Path
+        flag = Path(tempfile.gettempdir()) / f"css_b200_multi_encoder_{os.environ.get('MASTER_PORT', '0')}.done"
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        if rank == 0:
+            try:
+                multi_leg = bench_multi_device_handle(world, n_seq, ids, cu, emb)
+            except Exception as e:  # report, never hide
+                multi_leg = {"error": repr(e)}
+            flag.write_text("done")
+        else:
+            t_wait = time.time()
+            while not flag.exists() and time.time() - t_wait < 600:
+                time.sleep(0.05)
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            flag.unlink(missing_ok=True)
     res = {"encode": {"chunks_per_s": chunks_s, "ms_per_step": ms / steps, "chunks_per_step_per_gpu": n_seq,
                       "seq_len": SEQ_LEN, "achieved_tflops_per_gpu": tf,
                       "frac_of_bf16_peak": tf / pk["bf16_tflops_sustained"], "peak": pk["bf16_tflops_sustained"],
@@ -184,6 +232,8 @@ def bench_encoder(torch, dev, pk, world, rank, dist, args, steps: int = 20, warm
         res["encode"]["e2e_from_text"] = text_leg
     if query_leg is not None:
         res["encode"]["single_query"] = query_leg
+    if multi_leg is not None:
+        res["encode"]["multi_device_handle"] = multi_leg
     if rank == 0 and not getattr(args, "no_cpu", False):
         res["encode"]["cpu_baseline"] = cpu_encoder_baseline(device=dev.index)
     return res

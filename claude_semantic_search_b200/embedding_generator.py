@@ -40,6 +40,10 @@ class EmbeddingConfig:
     # 768 Python floats per chunk cost 0.76 s per 10 k chunks (tolist + the asarray in add_chunks) against
     # 0.83 s of GPU time: the list round trip halves the indexing rate.  HybridStorage.add_chunks takes both.
     embedding_as_ndarray: bool = False
+    # Extension (north_star: embedding batches split data-parallel over the GPUs of one box, same API): the GPUs to
+    # use, e.g. [0, 1, ..., 7].  The weights are replicated, every generate_embeddings call is split into contiguous
+    # ranges of equal token count, one per device, no collective; None = the one device of `device`.
+    devices: Optional[List[int]] = None
 
 
 @dataclass
@@ -80,8 +84,11 @@ class EmbeddingGenerator:
             self._gpu_capability = assess_gpu_capability()
             if not self._gpu_capability.can_use_gpu:
                 raise _native.NoDeviceError(_native.CSS_ERR_NO_DEVICE, self._gpu_capability.status_message)
-            self.model = SentenceTransformer(self.config.model_name, cache_folder=cache_dir)
-            self.model.to(self._determine_target_device())
+            target = self._determine_target_device()
+            # the shim loads the weights where they will live (the reference constructs on the CPU and moves)
+            self.model = SentenceTransformer(self.config.model_name, cache_folder=cache_dir, device=target,
+                                             devices=self.config.devices)
+            self.model.to(target)
             self.model.max_seq_length = self.config.max_seq_length
             if self.config.use_gpu and self.config.auto_batch_size and self._gpu_capability.gpu_memory_free:
                 self.config.batch_size = calculate_optimal_batch_size(self._gpu_capability.gpu_memory_free / 1024 ** 3)

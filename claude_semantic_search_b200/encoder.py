@@ -195,6 +195,89 @@ class MPNetEncoder:
             pass
 
 
+def split_by_tokens(cu_seqlens: np.ndarray, parts: int) -> List[Tuple[int, int]]:
+    """Contiguous sequence ranges [a, b) with (nearly) equal token counts, one per device; the order of the
+    sequences is kept, a range may be empty.  SURVEY.md 8(e): "static contiguous split ... weights replicated;
+    each rank writes rows [start_r, end_r)"."""
+    cu = np.asarray(cu_seqlens, dtype=np.int64)
+    n = cu.shape[0] - 1
+    total = int(cu[-1]) if n > 0 else 0
+    cuts = [0]
+    for r in range(1, parts):
+        # first sequence boundary at or after r / parts of the tokens, never before the previous cut
+        target = total * r / parts
+        cuts.append(max(cuts[-1], int(np.searchsorted(cu, target, side="left"))))
+    cuts.append(n)
+    return [(min(cuts[r], n), min(cuts[r + 1], n)) for r in range(parts)]
+
+
+class MultiDeviceEncoder:
+    """One encoder over several GPUs of this box, inside one process: the weights are replicated (one
+    css_encoder per device), a batch of sequences is split into contiguous ranges of equal token count and every
+    range is encoded on its own device from its own host thread (ctypes releases the GIL; no collective -- SURVEY.md
+    8(e)).  Results are bit-identical to a single device: a sequence's embedding does not depend on what else is
+    in the pass.  Small calls (a query, a handful of chunks) stay on the first device."""
+
+    def __init__(self, encoders: List[MPNetEncoder], min_seqs_per_device: int = 8):
+        if not encoders:
+            raise ValueError("MultiDeviceEncoder needs at least one encoder")
+        self._encoders = list(encoders)
+        self.devices = [e.device for e in encoders]
+        self.device = self.devices[0]
+        self.dim = encoders[0].dim
+        self.max_tokens = encoders[0].max_tokens
+        self.max_seq_len = encoders[0].max_seq_len
+        self.config = encoders[0].config
+        self.min_seqs_per_device = min_seqs_per_device
+        self._pool = None
+
+    @classmethod
+    def create(cls, make_one, devices: Sequence[int]) -> "MultiDeviceEncoder":
+        """`make_one(device) -> MPNetEncoder`; the per-device loads run concurrently."""
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(devices)) as pool:
+            return cls(list(pool.map(make_one, devices)))
+
+    pack = staticmethod(MPNetEncoder.pack)
+
+    def encode_ids(self, seqs: Iterable[Sequence[int]], normalize: bool = True) -> np.ndarray:
+        ids, cu = self.pack(seqs)
+        return self.encode_packed(ids, cu, normalize)
+
+    def encode_packed(self, ids: np.ndarray, cu_seqlens: np.ndarray, normalize: bool = True) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        cu = np.ascontiguousarray(cu_seqlens, dtype=np.int32)
+        n = cu.shape[0] - 1
+        parts = min(len(self._encoders), max(1, n // self.min_seqs_per_device))
+        if parts <= 1:
+            return self._encoders[0].encode_packed(ids, cu, normalize)
+        out = np.empty((n, self.dim), np.float32)
+        ranges = [(e, a, b) for e, (a, b) in zip(self._encoders, split_by_tokens(cu, parts)) if b > a]
+
+        def run(job):
+            enc, a, b = job
+            out[a:b] = enc.encode_packed(ids[cu[a]:cu[b]], cu[a:b + 1] - cu[a], normalize)
+
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=len(self._encoders))
+        list(self._pool.map(run, ranges))   # re-raises the first failure
+        return out
+
+    def close(self) -> None:
+        if self._pool is not None:
+            self._pool.shutdown(wait=True)
+            self._pool = None
+        for e in self._encoders:
+            e.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def relative_bucket(rel: int, num_buckets: int = 32, max_distance: int = 128) -> int:
     return int(_native.load().css_mpnet_relative_bucket(int(rel), num_buckets, max_distance))
 

@@ -20,7 +20,7 @@ from typing import Dict, List, Optional, Sequence, Union
 
 import numpy as np
 
-from .encoder import DEFAULT_CONFIG, MPNetEncoder, random_state_dict
+from .encoder import DEFAULT_CONFIG, MPNetEncoder, MultiDeviceEncoder, random_state_dict
 
 BOS, PAD, EOS, UNK = 0, 1, 2, 3
 
@@ -262,6 +262,17 @@ def _find_model_dir(name: str, cache_folder: Optional[str]) -> Optional[Path]:
 
 
 # ---------------------------------------------------------------------- SentenceTransformer
+def _device_index_of(device) -> int:
+    """'cuda:3' -> 3; 'cuda', 'auto', None, 'cpu' -> 0 (torch's current-device convention)."""
+    s = str(device) if device is not None else ""
+    if s.startswith("cuda:"):
+        try:
+            return int(s.split(":", 1)[1])
+        except ValueError:
+            return 0
+    return 0
+
+
 def encode_texts_pipelined(tokenizer, encoder, texts: Sequence[str], max_len: int, normalize: bool,
                            slab: int = 1024) -> np.ndarray:
     """Text in, embeddings out with the host tokenizer one slab ahead of the GPU: a worker thread
@@ -291,15 +302,24 @@ def encode_texts_pipelined(tokenizer, encoder, texts: Sequence[str], max_len: in
 
 class SentenceTransformer:
     def __init__(self, model_name_or_path: str = "all-mpnet-base-v2", cache_folder: Optional[str] = None,
-                 device: Optional[str] = None, **_unused):
+                 device: Optional[str] = None, devices: Optional[Sequence[int]] = None, **_unused):
+        """`devices` (extension, EmbeddingConfig.devices): several GPUs of this box -- the weights are replicated and
+        every encode() call is split data-parallel over them (MultiDeviceEncoder).  The encoder is built on first
+        use, so that `.to("cuda:N")` (src/embeddings.py:94) decides where without loading the weights twice."""
         self.model_name = model_name_or_path
         self.max_seq_length = 384
         self.tokenize_slab = 1024   # texts per tokeniser slab when tokenising overlaps encoding
-        self._device_index = 0
+        self._device_index = _device_index_of(device)
+        self._devices = [int(d) for d in devices] if devices else None
+        if self._devices:
+            self.tokenize_slab *= len(self._devices)   # every device still gets a full pass per slab
+        self._enc = None
         synthetic = model_name_or_path == "synthetic-mpnet" or os.environ.get("CSS_B200_SYNTHETIC_MODEL") == "1"
         model_dir = None if model_name_or_path == "synthetic-mpnet" else _find_model_dir(model_name_or_path, cache_folder)
+        self._model_dir = model_dir
         if model_dir is not None:
-            self._encoder = MPNetEncoder.from_pretrained(model_dir, device=self._device_index)
+            if not ((model_dir / "model.safetensors").exists() or (model_dir / "pytorch_model.bin").exists()):
+                raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {model_dir}")
             self.tokenizer = self._load_tokenizer(model_dir)
             if self.tokenizer is None and (model_dir / "tokenizer.json").exists():
                 self.tokenizer = FastTokenizer(model_dir / "tokenizer.json")   # a pipeline the native one does not implement
@@ -307,7 +327,6 @@ class SentenceTransformer:
                 raise FileNotFoundError(f"{model_dir}: neither tokenizer.json nor vocab.txt")
             self.synthetic = False
         elif synthetic:
-            self._encoder = MPNetEncoder(random_state_dict(0), device=self._device_index)
             # benchmarks of the text path: random-init weights with a real WordPiece vocabulary file
             vocab = os.environ.get("CSS_B200_SYNTHETIC_VOCAB")
             self.tokenizer = NativeWordPieceTokenizer(vocab) if vocab else StandInTokenizer(DEFAULT_CONFIG["vocab_size"])
@@ -317,6 +336,21 @@ class SentenceTransformer:
                 f"model '{model_name_or_path}' not found locally (cache_folder={cache_folder!r}); this build does "
                 "not download.  Point cache_folder at a directory holding the checkpoint, or set "
                 "CSS_B200_SYNTHETIC_MODEL=1 for random-init weights + stand-in tokenizer (benchmarks only).")
+        self._encoder   # fail now, not at the first encode(), when the device or the checkpoint is unusable
+
+    def _make_encoder(self, device: int) -> MPNetEncoder:
+        if self._model_dir is not None:
+            return MPNetEncoder.from_pretrained(self._model_dir, device=device)
+        return MPNetEncoder(random_state_dict(0), device=device)
+
+    @property
+    def _encoder(self):
+        if self._enc is None:
+            if self._devices and len(self._devices) > 1:
+                self._enc = MultiDeviceEncoder.create(self._make_encoder, self._devices)
+            else:
+                self._enc = self._make_encoder(self._devices[0] if self._devices else self._device_index)
+        return self._enc
 
     @staticmethod
     def _load_tokenizer(model_dir: Path):
@@ -347,11 +381,18 @@ class SentenceTransformer:
         if s.startswith("cpu"):
             # the reference moves to "cpu" when use_gpu is False; this path has no CPU encoder
             return self
+        idx = _device_index_of(s)
+        if not self._devices and idx != self._device_index:
+            self._device_index = idx
+            if self._enc is not None:   # already resident elsewhere: move = reload there
+                self._enc.close()
+                self._enc = None
+            self._encoder
         return self
 
     @property
     def device(self) -> str:
-        return f"cuda:{self._device_index}"
+        return f"cuda:{self._devices[0] if self._devices else self._device_index}"
 
     def get_sentence_embedding_dimension(self) -> int:
         return self._encoder.dim
@@ -377,4 +418,6 @@ class SentenceTransformer:
         return emb[0] if single else emb
 
     def close(self) -> None:
-        self._encoder.close()
+        if self._enc is not None:
+            self._enc.close()
+            self._enc = None

@@ -197,3 +197,34 @@ def test_local_checkpoint_text_to_embedding_vs_hf(tmp_path):
         st.tokenize_slab = slab
         np.testing.assert_array_equal(st.encode(texts, normalize_embeddings=True), got, err_msg=f"slab={slab}")
     st.close()
+
+
+def test_embedding_generator_over_several_devices_matches_one_device():
+    """EmbeddingConfig.devices (north_star: embedding batches split data-parallel over the GPUs of one box behind
+    the unchanged generate_embeddings API): replicated weights, contiguous ranges of equal token count,
+    no collective.  A sequence's embedding does not depend on which pass it travels in, so the result must equal the
+    single-device one bit for bit.  On a one-GPU box the two handles share the device (the split / thread / reassembly
+    logic is what is under test); `device="cuda:N"` must be honoured as well."""
+    from claude_semantic_search_b200 import EmbeddingConfig, EmbeddingGenerator, _native
+
+    n_dev = min(_native.device_count(), 4)
+    devices = list(range(n_dev)) if n_dev > 1 else [0, 0]
+    chunks = _make_chunks(333, seed=77)
+    one = EmbeddingGenerator(EmbeddingConfig(model_name="synthetic-mpnet", use_gpu=True, show_progress=False))
+    ref = np.array(one.generate_embeddings(chunks))
+    many = EmbeddingGenerator(EmbeddingConfig(model_name="synthetic-mpnet", use_gpu=True, show_progress=False,
+                                              devices=devices, embedding_as_ndarray=True))
+    got = many.generate_embeddings(chunks)
+    assert got.shape == ref.shape and got.dtype == np.float32
+    assert np.array_equal(got, ref)
+    assert all(isinstance(c.embedding, np.ndarray) for c in chunks)
+    q1 = one.generate_single_embedding("where is the vector index kept")
+    qn = many.generate_single_embedding("where is the vector index kept")
+    assert np.array_equal(q1, qn)                       # a single query stays on the first device
+    assert many.model.device == f"cuda:{devices[0]}" and many.is_using_gpu
+    last = _native.device_count() - 1
+    pinned = EmbeddingGenerator(EmbeddingConfig(model_name="synthetic-mpnet", use_gpu=True, show_progress=False,
+                                                device=f"cuda:{last}"))
+    pinned.load_model()
+    assert pinned.model.device == f"cuda:{last}"
+    assert np.array_equal(np.array(pinned.generate_embeddings(chunks[:40])), ref[:40])

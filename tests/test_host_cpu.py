@@ -327,3 +327,57 @@ def test_embedding_helpers_accept_ndarray_views(tmp_path):
     path = str(tmp_path / "e.npz")
     g.save_embeddings(chunks, path)
     assert [c.id for c in g.load_embeddings(path)] == ["a", "b"]
+
+
+def test_split_by_tokens_is_contiguous_ordered_and_balanced():
+    """static contiguous split of the sequences over the devices, by token count."""
+    from claude_semantic_search_b200.encoder import split_by_tokens
+    rng = np.random.default_rng(5)
+    for n, parts in [(0, 4), (1, 4), (3, 8), (100, 1), (100, 2), (257, 8), (4096, 8)]:
+        lens = rng.integers(1, 385, size=n)
+        cu = np.zeros(n + 1, np.int64)
+        cu[1:] = np.cumsum(lens)
+        ranges = split_by_tokens(cu, parts)
+        assert len(ranges) == parts and ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a <= b for a, b in ranges) and all(ranges[i][1] == ranges[i + 1][0] for i in range(parts - 1))
+        if n >= 64 * parts:   # balanced to within one sequence
+            tok = [int(cu[b] - cu[a]) for a, b in ranges]
+            assert max(tok) - min(tok) <= 2 * 384
+
+
+def test_multi_device_encoder_splits_and_reassembles_in_order():
+    """MultiDeviceEncoder over stand-in per-device encoders: every sequence is encoded exactly once, on the device
+    that owns its range, the result rows come back in input order, and small calls stay on the first device."""
+    from claude_semantic_search_b200.encoder import MultiDeviceEncoder
+
+    class Fake:
+        dim, max_tokens, max_seq_len, config = 4, 1 << 20, 384, {}
+
+        def __init__(self, device):
+            self.device, self.calls = device, []
+
+        def encode_packed(self, ids, cu, normalize=True):
+            assert cu[0] == 0 and cu[-1] == ids.shape[0]
+            self.calls.append(cu.shape[0] - 1)
+            out = np.empty((cu.shape[0] - 1, 4), np.float32)
+            for i in range(cu.shape[0] - 1):
+                seg = ids[cu[i]:cu[i + 1]]
+                out[i] = (seg.sum(), seg.shape[0], seg[0], self.device)
+            return out
+
+        def close(self):
+            pass
+
+    fakes = [Fake(d) for d in range(4)]
+    enc = MultiDeviceEncoder(fakes, min_seqs_per_device=8)
+    rng = np.random.default_rng(0)
+    seqs = [rng.integers(4, 30000, size=int(l)).astype(np.int32) for l in rng.integers(2, 385, size=203)]
+    got = enc.encode_ids(seqs)
+    assert got.shape == (203, 4)
+    for i, s in enumerate(seqs):
+        assert got[i, 0] == np.float32(s.sum()) and got[i, 1] == len(s) and got[i, 2] == s[0]
+    assert (np.diff(got[:, 3]) >= 0).all() and set(got[:, 3]) == {0.0, 1.0, 2.0, 3.0}   # contiguous ranges, all devices
+    assert sum(sum(f.calls) for f in fakes) == 203
+    few = enc.encode_ids(seqs[:5])                       # a handful of sequences: first device only
+    assert (few[:, 3] == 0).all()
+    enc.close()
