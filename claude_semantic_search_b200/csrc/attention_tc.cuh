@@ -439,7 +439,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       // ---- pass 1: maximum of the raw scores over this thread's real keys ----
       float mx = -INFINITY;
       if (nb > 0) {
-        tc::mbar_wait(s_full + g, ng & 1);
+        tc::mbar_wait_spin(s_full + g, ng & 1);
         tc::tc_fence_after();
         if (tr) attn_trace(trace, 2 + g, n, 1);
         // blocks in descending order: block 0's scores are still in registers when pass 2 starts
@@ -486,7 +486,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       for (int lb = 0; lb < nb; ++lb, ++np) {
         const uint32_t buf = np & 1;
         const int c0 = key0 + lb * 64;
-        tc::mbar_wait(p_empty + g * 2 + buf, ((np >> 1) & 1) ^ 1);
+        tc::mbar_wait_spin(p_empty + g * 2 + buf, ((np >> 1) & 1) ^ 1);
         uint8_t* prow = sP + (g * 2 + buf) * kAtP + r * 128;
         tc::tmem_ld_wait();
 #pragma unroll
@@ -554,7 +554,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       f32x2_unpack(sum2, sum_lo, sum_hi);
       // row sums for the epilogue warps (a half without keys contributes 0); the slot was last used
       // by item n - 2, which the epilogue has finished once it has released that item's O buffer
-      tc::mbar_wait(o_free + par, ((n >> 1) & 1) ^ 1);
+      tc::mbar_wait_spin(o_free + par, ((n >> 1) & 1) ^ 1);
       sStat[(par * 4 + slot) * 128 + r] = sum_lo + sum_hi;
       if (kAtHf == 2) sStat[(par * 4 + slot + 1) * 128 + r] = 0.f;
       __syncwarp();

@@ -75,6 +75,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Unbounded wait for the hot loops of kernels whose other roles keep the bounded one: a hang still traps there (every
+// pipeline of such a kernel is a cycle of roles), and the waiting code stays a three-instruction loop instead of
+// dragging the watchdog (clock read, printf, trap) into every wait site of the instruction cache's hottest warps.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  while (!mbar_try_wait_suspend(bar, parity, 4000u)) {
+  }
+}
+
 // Wait for roles with slack (TMA producer, epilogue warps): sleep between polls so the polling
 // costs (almost) no issue slots of the SM sub-partition it shares with compute warps.
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, uint32_t ns) {
