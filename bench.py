@@ -52,6 +52,8 @@ def unit_for(rows: int) -> str:
 # DRAM traffic per launch from the committed ncu --set full captures, keyed by rows per GPU
 NCU_SCAN_TRAFFIC = {1_000_000: 3_072_071_000 + 4_015_872}       # fp32 sweep (profiles/r1_ncu_kernels_summary.txt)
 NCU_SCAN_TRAFFIC_BF16 = {1_000_000: 1_536_171_000 + 7_699_456}  # bf16 sweep incl. its last-CTA finish (profiles/r2_scan_two_phase_ncu_summary.txt)
+NCU_SCAN_TRAFFIC_INT8 = {}                                       # int8 sweep incl. its last-CTA finish (profiles/r2_scan_int8_ncu_summary.txt)
+INT8_ROW_BYTES = D + 4                                           # 768 codes + the row's fp32 scale
 
 
 def shared_config(rows: int, world: int) -> dict:
@@ -417,6 +419,7 @@ def main():
     id_offset = rank * rows
     sharded = ShardedSearch(idx, id_offset)
     two_phase = os.environ.get("CSS_SCAN_BF16", "1") != "0"
+    int8_tier = two_phase and os.environ.get("CSS_SCAN_INT8", "1") != "0"
 
     # ---- in-run correctness, before any timing: merged top-k vs brute force, one filtered ----
     check = verify_headline(torch, native, dev, dist, world, rank, rows, idx, sharded, qs)
@@ -451,17 +454,20 @@ def main():
     n_k = max(args.steps, 100)
     ms_scan, _ = time_region(torch, dev, scan_only, n_k, dist)
     ms_scan /= n_k
-    # The default path is the two-phase exact scan: the dominant kernel sweeps the bf16 shadow rows (1536 B per row,
-    # half of SURVEY 8(d)'s 3072 B fp32 row), the fp32 rows are touched only for the few re-scored candidates.
-    # Its roofline is quoted on the bytes it has to read, timed alone through css_debug_scan_bf16.
+    # The default path is the two-phase exact scan: the dominant kernel sweeps the int8 shadow rows (768 + 4 B per row,
+    # a quarter of SURVEY 8(d)'s 3072 B fp32 row; CSS_SCAN_INT8=0: the bf16 shadow rows, 1536 B), the fp32 rows are
+    # touched only for the few re-scored candidates.  Its roofline is quoted on the bytes it has to read, timed alone
+    # through css_debug_scan_int8 / css_debug_scan_bf16.
     if two_phase:
         def phase1_only(i):
-            idx.debug_scan_bf16(qs[i % nq_pool].data_ptr(), 1, sp)
+            (idx.debug_scan_int8 if int8_tier else idx.debug_scan_bf16)(qs[i % nq_pool].data_ptr(), 1, sp)
+        for i in range(5):
+            phase1_only(i)
         ms_kernel, _ = time_region(torch, dev, phase1_only, n_k, dist)
         ms_kernel /= n_k
-        kernel_bytes = rows * D * 2
-        kernel_name = ("scan_topk_kernel<bf16 shadow> (sweep of the two-phase exact scan, timed alone without its last-CTA "
-                       "proof + fp32 re-score; the step adds that and one idle fp32-fallback launch)")
+        kernel_bytes = rows * (INT8_ROW_BYTES if int8_tier else D * 2)
+        kernel_name = (f"scan_topk_kernel<{'int8' if int8_tier else 'bf16'} shadow> (sweep of the two-phase exact scan, timed alone "
+                       "without its last-CTA proof + fp32 re-score; the step adds that and one idle fp32-fallback launch)")
     else:
         ms_kernel, kernel_bytes, kernel_name = ms_scan, rows * BYTES_PER_ROW, "scan_topk_kernel (fp32 sweep)"
     achieved = kernel_bytes / (ms_kernel * 1e-3) / 1e9
@@ -486,6 +492,8 @@ def main():
     if not args.no_extra and args.only == "":
         if "fp32_sweep" not in skip and two_phase:
             extra["fp32_sweep"] = bench_fp32_sweep(torch, native, dev, idx, qs, pk, rows, id_offset, sp, dist, D_loc, I_loc)
+        if "bf16_tier" not in skip and int8_tier:
+            extra["bf16_two_phase"] = bench_bf16_tier(torch, native, dev, idx, qs, pk, rows, id_offset, sp, dist, D_loc, I_loc)
         if "batched" not in skip:
             try:
                 extra.update(bench_batched(torch, native, dev, idx, qs, pk, world, rank, rows, dist))
@@ -534,15 +542,17 @@ def main():
             "config": shared_config(rows, world),
             "qps": qps,
             "latency_ms": {"device": lat_dev, "e2e": lat_wall},
-            "path": {"scan": "two-phase exact scan (bf16 shadow sweep; proof + fp32 re-score in the sweep's last CTA)" if two_phase
-                     else "single fp32 sweep",
+            "path": {"scan": (f"two-phase exact scan ({'int8' if int8_tier else 'bf16'} shadow sweep; proof + fp32 re-score in the "
+                              "sweep's last CTA; unproven queries re-run by the fp32 sweep)") if two_phase else "single fp32 sweep",
                      "exchange": "none" if world == 1 else "in-kernel: k x 16 B stored into every peer over NVLink (CUDA IPC), "
                                                           "flags awaited and lists merged by the last CTA of the scan; no NCCL, no merge launch",
                      "two_phase_queries": stats["two_phase_queries"], "unproven_queries": stats["unproven_queries"],
-                     "max_bf16_error_norm": stats["max_bf16_error_norm"]},
+                     "max_bf16_error_norm": stats["max_bf16_error_norm"],
+                     "max_int8_error_norm": stats["max_int8_error_norm"], "last_tier": stats["last_tier"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / pk["hbm_gbs"],
-                         "traffic": (NCU_SCAN_TRAFFIC_BF16 if two_phase else NCU_SCAN_TRAFFIC).get(rows),
+                         "traffic": (NCU_SCAN_TRAFFIC_INT8 if int8_tier else NCU_SCAN_TRAFFIC_BF16 if two_phase
+                                     else NCU_SCAN_TRAFFIC).get(rows),
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture under profiles/",
                          "peak_source": pk["source"],
                          "kernel": kernel_name, "kernel_ms": ms_kernel, "step_ms_device": ms_scan,
@@ -551,7 +561,8 @@ def main():
                          "fp32_row_definition": {"bytes_per_row": BYTES_PER_ROW,
                                                  "step_gbs": rows * BYTES_PER_ROW / (ms_scan * 1e-3) / 1e9,
                                                  "note": "SURVEY 8(d) counts 3072 B per row; the two-phase scan answers the same exact "
-                                                         "query from 1536 B per row, see extra.fp32_sweep for the kernel that streams the fp32 rows"}},
+                                                         "query from 772 B per row (int8 shadow; extra.bf16_two_phase: 1536 B per row), "
+                                                         "see extra.fp32_sweep for the kernel that streams the fp32 rows"}},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_qps * world, "unit": UNIT, "h2d_bytes_per_step": D * 4, "d2h_bytes_per_step": K * 12,
                     "qps": e2e_qps,
@@ -632,6 +643,34 @@ def bench_fp32_sweep(torch, native, dev, idx, qs, pk, rows, id_offset, sp, dist,
             "qps": 1e3 / ms}
 
 
+def bench_bf16_tier(torch, native, dev, idx, qs, pk, rows, id_offset, sp, dist, D_loc, I_loc):
+    """The two-phase scan with the bf16 shadow rows as its sweep (the second tier: CSS_SCAN_INT8=0, and what the
+    adaptive switch falls back to when the int8 tier cannot prove most queries), timed in the same run."""
+    native.set_option("scan_int8", 0)
+    try:
+        def f(i):
+            idx.search_device(qs[i % 1024].data_ptr(), 1, K, D_loc.data_ptr(), I_loc.data_ptr(), 0, id_offset, sp)
+        for i in range(5):
+            f(i)
+        ms, _ = time_region(torch, dev, f, 200, dist)
+        ms /= 200
+
+        def g(i):
+            idx.debug_scan_bf16(qs[i % 1024].data_ptr(), 1, sp)
+        for i in range(5):
+            g(i)
+        msk, _ = time_region(torch, dev, g, 200, dist)
+        msk /= 200
+    finally:
+        native.set_option("scan_int8", 1)
+    gbs = rows * D * 2 / (msk * 1e-3) / 1e9
+    return {"roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "traffic": NCU_SCAN_TRAFFIC_BF16.get(rows), "kernel": "scan_topk_kernel<bf16 shadow> (sweep timed alone)",
+                         "kernel_ms": msk, "algorithmic_bytes_per_launch": rows * D * 2,
+                         "step_ms_device": ms, "step_frac_of_peak": rows * D * 2 / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+            "qps": 1e3 / ms}
+
+
 def bench_clustered(torch, native, dev, pk, rows):
     """The headline search on a clustered corpus (2000 caps, intra-cluster cosine 0.6-0.95, members adjacent in
     row order): QPS, share of queries the two-phase proof could not close (they take the fp32 sweep), and an
@@ -699,6 +738,8 @@ def bench_clustered(torch, native, dev, pk, rows):
         out[order] = {"qps": 1e3 / ms, "ms_per_query": ms, "e2e_qps": 1e3 / e2e_ms,
                       "two_phase_queries": asked, "unproven_queries": unproven,
                       "fallback_rate": (unproven / asked) if asked else None,
+                      "last_tier": s1["last_tier"],
+                      "step_frac_of_hbm_peak_on_int8_bytes": rows * INT8_ROW_BYTES / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                       "step_frac_of_hbm_peak_on_bf16_bytes": rows * D * 2 / (ms * 1e-3) / 1e9 / pk["hbm_gbs"],
                       "batch1024_ms": msb, "batch1024_tflops": 2.0 * 1024 * rows * D / (msb * 1e-3) / 1e12,
                       "check": "8 queries == brute force within 1e-4; batched == batch-1 bit for bit"}
@@ -788,6 +829,7 @@ def bench_filtered(torch, native, dev, pk, rows=10_000_000, n_queries=300):
     dense = rows * BYTES_PER_ROW + rows / 8
     selective = sel * rows * BYTES_PER_ROW + rows / 8 + 3 * 4 * rows   # + the 3 int32 columns the predicate reads
     selective_bf16 = sel * rows * D * 2 + rows / 8 + 3 * 4 * rows
+    selective_int8 = sel * rows * INT8_ROW_BYTES + rows / 8 + 3 * 4 * rows
     return {"filtered_10M": {"rows": rows, "selectivity": sel, "p50_ms": p50, "p99_ms": float(np.percentile(lat, 99)),
                              "repeated_filter_p50_ms": float(np.median(lat_same)), "repeated_filter_p99_ms": float(np.percentile(lat_same, 99)),
                              "unfiltered_p50_ms": float(np.median(lat_u)), "device_scan_ms_mask_cached": ms_scan,
@@ -796,6 +838,9 @@ def bench_filtered(torch, native, dev, pk, rows=10_000_000, n_queries=300):
                              "dense_roofline_ms": dense / (pk["hbm_gbs"] * 1e9) * 1e3,
                              "selective_roofline_ms": selective / (pk["hbm_gbs"] * 1e9) * 1e3,
                              "selective_bf16_roofline_ms": selective_bf16 / (pk["hbm_gbs"] * 1e9) * 1e3,
+                             "selective_int8_roofline_ms": selective_int8 / (pk["hbm_gbs"] * 1e9) * 1e3,
+                             "device_scan_frac_of_hbm_peak_selective_int8_denominator":
+                                 (sel * rows * INT8_ROW_BYTES + rows / 8) / (ms_scan * 1e-3) / 1e9 / pk["hbm_gbs"],
                              "achieved_gbs_dense_denominator": dense / (p50 * 1e-3) / 1e9,
                              "achieved_gbs_selective_denominator": selective / (p50 * 1e-3) / 1e9,
                              "frac_of_hbm_peak_selective_bf16_denominator": selective_bf16 / (p50 * 1e-3) / 1e9 / pk["hbm_gbs"],
@@ -885,6 +930,19 @@ def bench_config4(torch, native, dev, pk, world, rank, dist, rows):
         ms_f = timed(lambda i: ss.search_device(q[i % 1024:i % 1024 + 1], K), 60)
     finally:
         native.set_option("scan_bf16", 1)
+    # second tier: bf16 shadow sweep (needles again, then timing)
+    int8_tier = os.environ.get("CSS_SCAN_BF16", "1") != "0" and os.environ.get("CSS_SCAN_INT8", "1") != "0"
+    ok_bf16, ms_b16 = None, None
+    if int8_tier:
+        native.set_option("scan_int8", 0)
+        try:
+            ok_bf16 = bool((batch1_ids(0, n_needle_q) == needle_ids).all())
+            for i in range(3):
+                ss.search_device(q[i:i + 1], K)
+            ms_b16 = timed(lambda i: ss.search_device(q[i % 1024:i % 1024 + 1], K), 100)
+        finally:
+            native.set_option("scan_int8", 1)
+    row_bytes = INT8_ROW_BYTES if int8_tier else D * 2
     for i in range(5):
         ss.search_device(q[i:i + 1], K)
     ms1 = timed(lambda i: ss.search_device(q[i % 1024:i % 1024 + 1], K), 200)
@@ -902,12 +960,16 @@ def bench_config4(torch, native, dev, pk, world, rank, dist, rows):
         "workload": f"exact top-10 over {N} x {D} fp32 rows, row-sharded over {world} GPU(s) ({rows} rows per GPU)",
         "rows_per_gpu": rows, "n_gpus": world, "build_s": build_s,
         "batch1": {"ms_per_query": ms1, "qps": 1e3 / ms1, "p50_ms": lat["p50_ms"], "p99_ms": lat["p99_ms"], "e2e_ms_per_query": e2e_ms,
-                   "path": "two-phase exact scan + in-kernel exchange",
-                   "per_gpu_gbs_on_bytes_read": rows * D * 2 / (ms1 * 1e-3) / 1e9,
-                   "frac_of_hbm_peak_on_bytes_read": rows * D * 2 / (ms1 * 1e-3) / 1e9 / hbm,
-                   "aggregate_gbs_on_bytes_read": world * rows * D * 2 / (ms1 * 1e-3) / 1e9,
+                   "path": f"two-phase exact scan ({'int8' if int8_tier else 'bf16'} shadow sweep, {row_bytes} B per row) + in-kernel exchange",
+                   "per_gpu_gbs_on_bytes_read": rows * row_bytes / (ms1 * 1e-3) / 1e9,
+                   "frac_of_hbm_peak_on_bytes_read": rows * row_bytes / (ms1 * 1e-3) / 1e9 / hbm,
+                   "aggregate_gbs_on_bytes_read": world * rows * row_bytes / (ms1 * 1e-3) / 1e9,
+                   "last_tier": stats["last_tier"],
                    "per_gpu_gbs_fp32_row_definition": rows * BYTES_PER_ROW / (ms1 * 1e-3) / 1e9,
                    "unproven_queries": stats["unproven_queries"], "two_phase_queries": stats["two_phase_queries"]},
+        "batch1_bf16_tier": None if ms_b16 is None else {
+            "ms_per_query": ms_b16, "qps": 1e3 / ms_b16, "per_gpu_gbs_on_bytes_read": rows * D * 2 / (ms_b16 * 1e-3) / 1e9,
+            "frac_of_hbm_peak_on_bytes_read": rows * D * 2 / (ms_b16 * 1e-3) / 1e9 / hbm, "needles_exact": ok_bf16},
         "batch1_fp32_sweep": {"ms_per_query": ms_f, "qps": 1e3 / ms_f, "per_gpu_gbs": rows * BYTES_PER_ROW / (ms_f * 1e-3) / 1e9,
                               "frac_of_hbm_peak": rows * BYTES_PER_ROW / (ms_f * 1e-3) / 1e9 / hbm,
                               "aggregate_gbs": world * rows * BYTES_PER_ROW / (ms_f * 1e-3) / 1e9},

@@ -137,6 +137,7 @@ SIGNATURES = {
     "css_encoder_max_seq_len": (c_int, [c_void_p]),
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
     "css_debug_scan_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "css_debug_scan_int8": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "css_tokenizer_create": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
     "css_tokenizer_destroy": (c_int, [c_void_p]),
     "css_tokenizer_vocab_size": (c_int, [c_void_p]),
@@ -209,7 +210,7 @@ def device_info(device: int = 0) -> dict:
 
 
 def set_option(name: str, value: int) -> None:
-    """Process-wide switch of libcss_b200 (css_set_option): scan_bf16, scan_interleave, scan_list, scan_adaptive."""
+    """Process-wide switch of libcss_b200 (css_set_option): scan_bf16, scan_int8, scan_interleave, scan_list, scan_adaptive."""
     check(load().css_set_option(name.encode(), int(value)))
 
 
@@ -394,10 +395,12 @@ class Index:
         check(self._lib.css_index_set_alive_ids(self._h, a.ctypes.data, a.shape[0], 1 if alive else 0))
 
     def scan_stats(self) -> dict:
-        out = (c_int64 * 4)()
+        out = (c_int64 * 6)()
         check(self._lib.css_index_scan_stats(self._h, out))
         return {"two_phase_queries": int(out[0]), "unproven_queries": int(out[1]), "bypassed": bool(out[2]),
-                "max_bf16_error_norm": out[3] * 1e-9}
+                "max_bf16_error_norm": out[3] * 1e-9,
+                "max_int8_error_norm": float("inf") if out[4] == 2 ** 63 - 1 else out[4] * 1e-9,
+                "last_tier": int(out[5])}
 
     # -- filter / search ----------------------------------------------------
     def filter_mask(self, flt: Optional[Filter]) -> tuple:
@@ -479,6 +482,10 @@ class Index:
     def debug_scan_bf16(self, q_ptr: int, nq: int, stream: int = 0) -> None:
         """Phase 1 alone of the two-phase scan (benchmark hook, css_debug_scan_bf16)."""
         check(self._lib.css_debug_scan_bf16(self._h, c_void_p(q_ptr), nq, c_void_p(stream)))
+
+    def debug_scan_int8(self, q_ptr: int, nq: int, stream: int = 0) -> None:
+        """The int8 shadow sweep alone (first tier of the two-phase scan; benchmark hook, css_debug_scan_int8)."""
+        check(self._lib.css_debug_scan_int8(self._h, c_void_p(q_ptr), nq, c_void_p(stream)))
 
     # -- persistence --------------------------------------------------------
     def save(self, path) -> None:

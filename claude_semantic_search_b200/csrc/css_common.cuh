@@ -73,6 +73,7 @@ struct DeviceGuard {
 // CSS_SCAN_ADAPTIVE) and changeable at run time through css_set_option (benchmarks compare the paths in one run).
 struct Options {
   std::atomic<int> scan_bf16{1};        // two-phase batch-1 scan (0: single fp32 sweep)
+  std::atomic<int> scan_int8{1};        // int8 shadow rows as the first tier of the two-phase scan (0: bf16 shadow only)
   std::atomic<int> scan_interleave{1};  // dense bf16 sweep deals 8-row units block-cyclically
   std::atomic<int> scan_list{0};        // per-block list length 32 | 64 (0: by k)
   std::atomic<int> scan_adaptive{1};    // bypass phase 1 while most queries cannot be proven

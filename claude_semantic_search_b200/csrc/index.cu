@@ -25,6 +25,9 @@ int dev_alloc(T** p, size_t count) {
 
 inline int64_t words_for(int64_t rows) { return (rows + 31) / 32; }
 
+// The int8 shadow copy (first tier of the two-phase scan) exists where the kernel that reads it does.
+inline bool has_int8_shadow(const css_index* h) { return h->dim == 768 && h->metric == CSS_METRIC_INNER_PRODUCT; }
+
 int vmm_status(int rc) { return rc == 0 ? CSS_OK : (rc == -4 ? CSS_ERR_OOM : CSS_ERR_CUDA); }
 
 // Largest row count the virtual ranges are sized for: what fits the device's HBM as fp32 rows.
@@ -42,6 +45,12 @@ int reserve_ranges(css_index* h) {
   const size_t d = (size_t)h->dim;
   CSS_CHECK(vmm_status(vmm_reserve(&h->vx, h->device, (size_t)mr * d * 4)));
   CSS_CHECK(vmm_status(vmm_reserve(&h->vxb, h->device, (size_t)mr * d * 2)));
+  if (has_int8_shadow(h)) {
+    CSS_CHECK(vmm_status(vmm_reserve(&h->vxq, h->device, (size_t)mr * d)));
+    CSS_CHECK(vmm_status(vmm_reserve(&h->vxs, h->device, (size_t)mr * 4)));
+    h->xq = reinterpret_cast<int8_t*>(h->vxq.ptr());
+    h->xs = reinterpret_cast<float*>(h->vxs.ptr());
+  }
   CSS_CHECK(vmm_status(vmm_reserve(&h->valive, h->device, (size_t)words_for(mr) * 4)));
   CSS_CHECK(vmm_status(vmm_reserve(&h->vmask, h->device, (size_t)words_for(mr) * 4)));
   h->x = reinterpret_cast<float*>(h->vx.ptr());
@@ -61,6 +70,10 @@ int grow(css_index* h, int64_t new_cap) {
   const int64_t old_cap = h->capacity;
   CSS_CHECK(vmm_status(vmm_grow(&h->vx, (size_t)new_cap * d * 4)));
   CSS_CHECK(vmm_status(vmm_grow(&h->vxb, (size_t)new_cap * d * 2)));
+  if (h->xq) {
+    CSS_CHECK(vmm_status(vmm_grow(&h->vxq, (size_t)new_cap * d)));
+    CSS_CHECK(vmm_status(vmm_grow(&h->vxs, (size_t)new_cap * 4)));
+  }
   CSS_CHECK(vmm_status(vmm_grow(&h->valive, (size_t)words_for(new_cap) * 4)));
   CSS_CHECK(vmm_status(vmm_grow(&h->vmask, (size_t)words_for(new_cap) * 4)));
   cudaStream_t st = h->stream;
@@ -108,7 +121,8 @@ int finish_rows(css_index* h, const float* src_dev, int64_t row0, int64_t n, int
   int64_t blocks = (n + warps_per_block - 1) / warps_per_block;
   const size_t off = (size_t)row0 * h->dim;
   append_rows_kernel<<<(unsigned)blocks, warps_per_block * 32, 0, st>>>(
-      src_dev, n, h->dim, normalize, h->x + off, h->xb + off, h->max_norm_dev, h->max_err_dev);
+      src_dev, n, h->dim, normalize, h->x + off, h->xb + off, h->max_norm_dev, h->max_err_dev,
+      h->xq ? h->xq + off : nullptr, h->xs ? h->xs + row0 : nullptr, h->max_err8_dev);
   CSS_LAUNCHED();
   return CSS_OK;
 }
@@ -393,6 +407,7 @@ static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const
   p->I = I_dev;
   p->max_norm = h->max_norm_dev;
   p->max_err = h->max_err_dev;
+  p->max_err8 = h->max_err8_dev;
   p->ovf_list = sc->ovf_list;
   p->ovf_count = sc->ovf_count;
   p->stats_dev = h->stats_dev;
@@ -408,15 +423,27 @@ static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const
 // the exact one.  CSS_SCAN_BF16=0 disables it; CSS_SCAN_LIST=32|64 fixes the per-block list length (default 32
 // for k <= 16, 64 above); CSS_SCAN_INTERLEAVE=0 walks contiguous row ranges per warp instead of dealing 8-row
 // units block-cyclically.
+template <int KPL, int SH>
+static int launch_phase1_as(const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kern = scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, true, SH>;
+  CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, kScanThreads, smem, st>>>(p);
+  CSS_LAUNCHED();
+  return CSS_OK;
+}
+
+// tier: 1 = bf16 shadow rows (1536 B per row), 2 = int8 shadow rows (768 + 4 B per row)
 static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
                          const IdMap& idmap, const ExchangeDev* ex, float* D_dev, int64_t* I_dev, int no_merge,
-                         cudaStream_t st) {
+                         cudaStream_t st, int tier) {
   const int list_env = options().scan_list.load();
   const int interleave = options().scan_interleave.load();
   const int kp = list_env == 32 || list_env == 64 ? list_env : (k <= 16 ? 32 : 64);
   ScanParams p;
   fill_common(h, sc, &p, q_dev, mask_dev, idmap, ex, D_dev, I_dev);
   p.xb = h->xb;
+  p.xq = h->xq;
+  p.xs = h->xs;
   p.k = kp;
   p.k_out = k;
   p.no_merge = no_merge;
@@ -424,17 +451,12 @@ static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev,
   p.zero_on_entry = sc->ovf_count;
   const size_t smem = sizeof(KeyId) * kMergeCap;
   const dim3 grid((unsigned)h->scan_blocks, (unsigned)nq);
-  if (kp == 32) {
-    auto kern = scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>;
-    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kScanThreads, smem, st>>>(p);
-  } else {
-    auto kern = scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, true>;
-    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kScanThreads, smem, st>>>(p);
+  if (tier == 2) {
+    CSS_REQUIRE(h->xq != nullptr, "this index has no int8 shadow copy");
+    const size_t smem8 = std::max(smem, (size_t)kI8SmemBytes);   // the sweep's ring of bulk copies; the lists alias it
+    return kp == 32 ? launch_phase1_as<1, 2>(p, grid, smem8, st) : launch_phase1_as<2, 2>(p, grid, smem8, st);
   }
-  CSS_LAUNCHED();
-  return CSS_OK;
+  return kp == 32 ? launch_phase1_as<1, 1>(p, grid, smem, st) : launch_phase1_as<2, 1>(p, grid, smem, st);
 }
 
 int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
@@ -450,27 +472,31 @@ int scan_fallback(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq
   return launch_scan_m<CSS_METRIC_INNER_PRODUCT>(h, f, std::min(nq, 8), st);
 }
 
-// Should this call try the two-phase scan?  The kernels mirror {queries, unproven} into mapped host memory;
-// when more than half of the recent queries could not be proven (a corpus whose rows sit within the bf16
-// rounding error of each other), phase 1 is wasted work and the next calls go straight to the fp32 sweep,
-// with a new probe every 4096 queries.  Exactness never depends on this choice.
-static bool two_phase_wanted(css_index* h, int nq) {
-  if (!options().scan_adaptive.load() || !h->stats_host) return true;
-  if (h->skip_two_phase > 0) {
-    h->skip_two_phase -= nq;
-    return false;
-  }
+// Which tier answers this call: 2 = int8 shadow sweep, 1 = bf16 shadow sweep, 0 = plain fp32 sweep.  The kernels
+// mirror {queries, unproven} into mapped host memory; when more than half of the recent queries of a tier could not
+// be proven (a corpus whose rows sit within that tier's error bound of each other), its phase 1 is wasted work and
+// the next 4096 scan queries skip the tier, after which it is probed again.  Exactness never depends on this choice.
+static int scan_tier(css_index* h, int nq) {
+  if (!options().scan_bf16.load()) return h->last_tier = 0;
+  const int top = (options().scan_int8.load() && h->xq) ? 2 : 1;
+  if (!options().scan_adaptive.load() || !h->stats_host) return h->last_tier = top;
   const unsigned q = h->stats_host[0], u = h->stats_host[1];
-  if (q - h->seen_q >= 64u) {
+  if (h->last_tier > 0 && q - h->seen_q >= 64u) {
     const bool bad = (u - h->seen_u) * 2u > (q - h->seen_q);
     h->seen_q = q;
     h->seen_u = u;
-    if (bad) {
-      h->skip_two_phase = 4096;
-      return false;
-    }
+    if (bad) h->tier_ban[h->last_tier] = 4096;
   }
-  return true;
+  int t = top;
+  while (t > 0 && h->tier_ban[t] > 0) --t;
+  for (int i = 1; i <= 2; ++i)
+    if (h->tier_ban[i] > 0) h->tier_ban[i] -= nq;
+  if (t != h->last_tier) {   // a tier is judged on its own queries only
+    h->seen_q = q;
+    h->seen_u = u;
+    h->last_tier = t;
+  }
+  return t;
 }
 
 int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
@@ -478,9 +504,11 @@ int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, 
                 bool defer_fallback, bool* two_phase_used) {
   CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
   if (two_phase_used) *two_phase_used = false;
-  const bool bf16_phase = options().scan_bf16.load() != 0;
-  if (bf16_phase && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK && nq <= 64 &&
-      h->ntotal > 0 && h->scan_blocks <= kTwoPhaseMaxBlocks && two_phase_wanted(h, nq)) {
+  int tier = 0;
+  if (h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && k <= kTwoPhaseMaxK && nq <= 64 && h->ntotal > 0 &&
+      h->scan_blocks <= kTwoPhaseMaxBlocks)
+    tier = scan_tier(h, nq);
+  if (tier > 0) {
     // Exchange + several queries in one launch: a CTA that waited for its peers inside phase 1 would hold up the
     // fallback launch behind it, which a peer's phase 1 may in turn be waiting for (query u unproven here, query v
     // unproven there).  So with nq > 1 the producers only publish and the fallback launch awaits + merges.
@@ -491,7 +519,7 @@ int scan_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int nq, 
       xd.nq = nq;
       ex = &xd;
     }
-    CSS_CHECK(launch_phase1(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, 0, st));
+    CSS_CHECK(launch_phase1(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, 0, st, tier));
     if (two_phase_used) *two_phase_used = true;
     if (defer_fallback) return CSS_OK;   // the caller reads the overflow count with the result
     return scan_fallback(h, sc, q_dev, nq, k, mask_dev, idmap, ex, D_dev, I_dev, st, /*pdl_ok=*/!(ex && ex->no_pdl));
@@ -545,8 +573,10 @@ static int preload_index_kernels(int dim) {
   CSS_CHECK(preload_scan_kpl<1>(smem, smem_generic));
   CSS_CHECK(preload_scan_kpl<2>(smem, smem_generic));
   CSS_CHECK(preload_scan_kpl<4>(smem, smem_generic));
-  CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, true>, smem));
-  CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, true>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, 1>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, 1>, smem));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, 2>, std::max(smem, (size_t)kI8SmemBytes)));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, 2>, std::max(smem, (size_t)kI8SmemBytes)));
   CSS_CHECK(preload_kernel(filter_mask_kernel, 0));
   CSS_CHECK(preload_kernel(append_rows_kernel, 0));
   CSS_CHECK(preload_kernel(set_bits_kernel, 0));
@@ -577,6 +607,7 @@ int index_create_single(int dim, int metric, int device, css_index** out) {
   void* sh = nullptr;
   if (dev_alloc(&h->n_pass_dev, 1) != CSS_OK || dev_alloc(&h->max_norm_dev, 1) != CSS_OK ||
       dev_alloc(&h->max_err_dev, 1) != CSS_OK || dev_alloc(&h->stats_dev, 2) != CSS_OK ||
+      dev_alloc(&h->max_err8_dev, 1) != CSS_OK || cudaMemset(h->max_err8_dev, 0, sizeof(float)) != cudaSuccess ||
       cudaMemset(h->max_norm_dev, 0, sizeof(float)) != cudaSuccess ||
       cudaMemset(h->max_err_dev, 0, sizeof(float)) != cudaSuccess ||
       cudaMemset(h->stats_dev, 0, 2 * sizeof(unsigned)) != cudaSuccess ||
@@ -586,6 +617,7 @@ int index_create_single(int dim, int metric, int device, css_index** out) {
     cudaFree(h->n_pass_dev);
     cudaFree(h->max_norm_dev);
     cudaFree(h->max_err_dev);
+    cudaFree(h->max_err8_dev);
     cudaFree(h->stats_dev);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -609,6 +641,8 @@ void index_destroy_single(css_index* h) {
   h->scratch.clear();
   vmm_release(&h->vx);
   vmm_release(&h->vxb);
+  vmm_release(&h->vxq);
+  vmm_release(&h->vxs);
   vmm_release(&h->valive);
   vmm_release(&h->vmask);
   for (int c = 0; c < CSS_MAX_COLUMNS; ++c) vmm_release(&h->vcols[c]);
@@ -617,6 +651,7 @@ void index_destroy_single(css_index* h) {
   cudaFree(h->n_pass_dev);
   cudaFree(h->max_norm_dev);
   cudaFree(h->max_err_dev);
+  cudaFree(h->max_err8_dev);
   cudaFree(h->stats_dev);
   cudaFree(h->ids_scratch);
   if (h->stats_host) cudaFreeHost(const_cast<unsigned*>(h->stats_host));
@@ -652,6 +687,7 @@ int single_reset(css_index* h) {
   h->any_dead = false;
   CSS_CUDA(cudaMemsetAsync(h->max_norm_dev, 0, sizeof(float), h->stream));
   CSS_CUDA(cudaMemsetAsync(h->max_err_dev, 0, sizeof(float), h->stream));
+  CSS_CUDA(cudaMemsetAsync(h->max_err8_dev, 0, sizeof(float), h->stream));
   if (h->capacity > 0) {
     CSS_CUDA(cudaMemsetAsync(h->alive, 0, (size_t)words_for(h->capacity) * 4, h->stream));
     for (int c = 0; c < CSS_MAX_COLUMNS; ++c) {
@@ -779,15 +815,18 @@ int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep
   int64_t* ids_dev = nullptr;
   float* sx = nullptr;
   __nv_bfloat16* sb = nullptr;
+  int8_t* sq = nullptr;
+  float* ss = nullptr;
   int32_t* sc = nullptr;
   uint32_t* sw = nullptr;
   auto cleanup = [&]() {
-    cudaFree(ids_dev); cudaFree(sx); cudaFree(sb); cudaFree(sc); cudaFree(sw);
+    cudaFree(ids_dev); cudaFree(sx); cudaFree(sb); cudaFree(sq); cudaFree(ss); cudaFree(sc); cudaFree(sw);
   };
   if (n_keep > 0) {
     const int64_t w = std::min(win, n_keep);
     if (cudaMalloc(&ids_dev, (size_t)n_keep * 8) != cudaSuccess || cudaMalloc(&sx, (size_t)w * d * 4) != cudaSuccess ||
         cudaMalloc(&sb, (size_t)w * d * 2) != cudaSuccess || cudaMalloc(&sc, (size_t)w * 4) != cudaSuccess ||
+        (h->xq && (cudaMalloc(&sq, (size_t)w * d) != cudaSuccess || cudaMalloc(&ss, (size_t)w * 4) != cudaSuccess)) ||
         cudaMalloc(&sw, (size_t)words_for(n_keep) * 4) != cudaSuccess) {
       (void)cudaGetLastError();
       cleanup();
@@ -802,10 +841,13 @@ int css_index_compact(css_index* h, const int64_t* keep_ids_host, int64_t n_keep
     }
     for (int64_t i0 = 0; i0 < n_keep && ce == cudaSuccess; i0 += win) {
       const int64_t n = std::min(win, n_keep - i0);
-      gather_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h->x, h->xb, ids_dev + i0, n, d, sx, sb);
+      gather_rows_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(h->x, h->xb, ids_dev + i0, n, d, sx, sb, h->xq, h->xs, sq,
+                                                                  ss);
       css::g_launches.fetch_add(1, std::memory_order_relaxed);
       ce = cudaMemcpyAsync(h->x + i0 * d, sx, (size_t)n * d * 4, cudaMemcpyDeviceToDevice, st);
       if (ce == cudaSuccess) ce = cudaMemcpyAsync(h->xb + i0 * d, sb, (size_t)n * d * 2, cudaMemcpyDeviceToDevice, st);
+      if (ce == cudaSuccess && h->xq) ce = cudaMemcpyAsync(h->xq + i0 * d, sq, (size_t)n * d, cudaMemcpyDeviceToDevice, st);
+      if (ce == cudaSuccess && h->xq) ce = cudaMemcpyAsync(h->xs + i0, ss, (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
       for (int c = 0; c < CSS_MAX_COLUMNS && ce == cudaSuccess; ++c) {
         if (!h->cols[c]) continue;
         gather_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->cols[c], ids_dev + i0, n, sc);
@@ -982,7 +1024,16 @@ int css_index_filter_mask_device(css_index* h, const css_filter* f, const uint32
   return eval_filter(h, f, mask_dev_out, n_pass_out, n_pass_out != nullptr, st, nullptr, 0);
 }
 
+static int debug_scan_tier(css_index* h, const float* q_dev, int nq, void* stream, int tier);
+
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream) {
+  return debug_scan_tier(h, q_dev, nq, stream, 1);
+}
+int css_debug_scan_int8(css_index* h, const float* q_dev, int nq, void* stream) {
+  return debug_scan_tier(h, q_dev, nq, stream, 2);
+}
+
+static int debug_scan_tier(css_index* h, const float* q_dev, int nq, void* stream, int tier) {
   CSS_REQUIRE(h != nullptr && q_dev != nullptr, "NULL argument");
   CSS_REQUIRE(nq >= 1 && nq <= 64, "nq=%d outside [1, 64]", nq);
   CSS_REQUIRE(!CSS_IS_COMPOSITE(h) && h->metric == CSS_METRIC_INNER_PRODUCT && h->dim == 768 && h->ntotal > 0,
@@ -993,7 +1044,7 @@ int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream) 
   css_scan_scratch* sc = nullptr;
   CSS_CHECK(get_scratch(h, st, nq, &sc));
   return launch_phase1(h, sc, q_dev, nq, 10, h->any_dead ? h->alive : nullptr, index_idmap(h, 0), nullptr, nullptr,
-                       nullptr, /*no_merge=*/1, st);
+                       nullptr, /*no_merge=*/1, st, tier);
 }
 
 int css_index_search_device(css_index* h, const float* q_dev, int nq, int k, const uint32_t* mask_dev,
@@ -1097,20 +1148,24 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   return CSS_OK;
 }
 
-int css_index_scan_stats(css_index* h, int64_t out[4]) {
+int css_index_scan_stats(css_index* h, int64_t out[6]) {
   CSS_REQUIRE(h != nullptr && out != nullptr, "NULL argument");
   std::lock_guard<std::mutex> lk(h->mu);
-  out[0] = out[1] = out[2] = out[3] = 0;
+  out[0] = out[1] = out[2] = out[3] = out[4] = 0;
+  out[5] = -1;
   auto one = [&](css_index* s) -> int {
     DeviceGuard g(s->device);
     unsigned v[2] = {0, 0};
     CSS_CUDA(cudaMemcpy(v, s->stats_dev, sizeof(v), cudaMemcpyDeviceToHost));
     out[0] += v[0];
     out[1] += v[1];
-    out[2] += s->skip_two_phase > 0 ? 1 : 0;
+    out[2] += (s->tier_ban[1] > 0 || s->tier_ban[2] > 0) ? 1 : 0;
     float e = 0.f;
     CSS_CUDA(cudaMemcpy(&e, s->max_err_dev, sizeof(e), cudaMemcpyDeviceToHost));
     out[3] = std::max<int64_t>(out[3], (int64_t)(e * 1e9f));
+    CSS_CUDA(cudaMemcpy(&e, s->max_err8_dev, sizeof(e), cudaMemcpyDeviceToHost));
+    out[4] = std::max<int64_t>(out[4], e < 1e9f ? (int64_t)(e * 1e9f) : (int64_t)INT64_MAX);
+    out[5] = std::max<int64_t>(out[5], s->last_tier);
     return CSS_OK;
   };
   if (CSS_IS_COMPOSITE(h)) {

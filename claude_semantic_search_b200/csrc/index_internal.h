@@ -4,8 +4,11 @@
 //   x      float32 [capacity, dim] row-major  -- the source of truth, what faiss
 //                                               IndexFlat stores (3072 B/row at d=768)
 //   xb     bf16    [capacity, dim] row-major  -- shadow copy: stream of phase 1 of the two-phase
-//                                               batch-1 scan and K-major B operand of the tcgen05
-//                                               batched score GEMM
+//                                               batch-1 scan (second tier) and K-major B operand of the
+//                                               tcgen05 batched score GEMM
+//   xq     int8    [capacity, 768] row-major  -- shadow copy, first tier of the two-phase scan (768 B/row),
+//   xs     float32 [capacity]                    with one scale per row: x ~= xs[row] * xq[row]
+//                                               (768-d inner-product indexes only)
 //   cols   int32   [CSS_MAX_COLUMNS][capacity] SoA metadata columns (lazily allocated)
 //   alive  uint32  [capacity/32]              -- 1 bit per row
 //   mask   uint32  [capacity/32]              -- last evaluated filter
@@ -63,13 +66,16 @@ struct css_index {
   int64_t capacity = 0;
   float* x = nullptr;
   __nv_bfloat16* xb = nullptr;
+  int8_t* xq = nullptr;              // int8 shadow rows + per-row scales (768-d inner-product indexes only)
+  float* xs = nullptr;
   int32_t* cols[CSS_MAX_COLUMNS] = {};
   uint32_t* alive = nullptr;
   uint32_t* mask = nullptr;
-  css::VmmArray vx, vxb, valive, vmask, vcols[CSS_MAX_COLUMNS];
+  css::VmmArray vx, vxb, vxq, vxs, valive, vmask, vcols[CSS_MAX_COLUMNS];
   bool any_dead = false;
   float* max_norm_dev = nullptr;     // largest row norm stored (upper bound), 1 float
   float* max_err_dev = nullptr;      // largest ||x - bf16(x)|| stored (upper bound), 1 float
+  float* max_err8_dev = nullptr;     // largest ||x - xs * xq|| stored (upper bound; +inf after a non-finite row), 1 float
 
   // scratch (device)
   int scan_blocks = 148;
@@ -96,7 +102,8 @@ struct css_index {
   volatile unsigned* stats_host = nullptr;   // mapped pinned
   unsigned* stats_host_devptr = nullptr;
   unsigned seen_q = 0, seen_u = 0;   // counters at the last decision
-  int64_t skip_two_phase = 0;        // > 0: next that many scan queries go straight to the fp32 sweep
+  int64_t tier_ban[3] = {0, 0, 0};   // [t] > 0: the next that many scan queries skip tier t (1 = bf16, 2 = int8 shadow)
+  int last_tier = -1;                // tier of the previous scan call (-1: none yet)
 
   // multi-device composite
   std::vector<css_index*> shards;

@@ -178,6 +178,8 @@ struct ExchangeDev {
 struct ScanParams {
   const float* x;        // [n, d]
   const __nv_bfloat16* xb;  // [n, d] bf16 shadow rows (two-phase scan only)
+  const int8_t* xq;      // [n, 768] int8 shadow rows (two-phase scan, first tier; nullable)
+  const float* xs;       // [n] scale of each int8 row: x ~= xs[row] * xq[row]
   int64_t n;
   int d;
   const float* q;        // [nq, d]
@@ -198,6 +200,7 @@ struct ScanParams {
   // two-phase scan
   const float* max_norm; // largest stored row norm
   const float* max_err;  // largest ||x - bf16(x)|| over the stored rows
+  const float* max_err8; // largest ||x - xs * xq|| over the stored rows (+inf once a non-finite row was stored)
   int* ovf_list;         // queries handed to the fp32 scan
   int* ovf_count;
   unsigned* stats_dev;   // [2] two-phase queries, unproven queries (device counters)
@@ -297,6 +300,171 @@ __device__ __forceinline__ void score_rows_bf16(const ScanParams& p, const float
   }
 #pragma unroll
   for (int i = 0; i < kRowsPerUnit; ++i) acc[i] = warp_sum(acc[i]);
+}
+
+// ------------------------------------------------------------------------
+// Two-phase scan, first tier: the rows are read from the int8 shadow copy (768 B per 768-d row + a 4-byte
+// scale: x ~= xs[row] * xq[row], codes in [-127, 127], scale = max|x| / 127 per row), a QUARTER of the fp32
+// bytes.  The query is split into two int8 vectors, q ~= a1 q1 + a2 q2 with a2 = a1 / 254 (q2 quantises the
+// residual of q1), so its own quantisation error is ~2^-15 |q|_inf per element and the integer dot products
+// I1 = q1.xq, I2 = q2.xq (dp4a, exact) give   x^.q^ = xs a1 (I1 + I2 / 254).
+//   |x.q - x^.q^| <= ||x - x^|| ||q|| + ||x^|| ||q - q^||  <=  max_err8 ||q|| + (max_norm + max_err8) ||q - q^||
+// (max_err8: largest quantisation-error norm of any stored row, tracked exactly at add time; ||q - q^|| is
+// computed exactly below), plus a few float roundings covered by the 4e-6 ||q|| max_norm of two_phase_finish.
+// Layout: a HALF-warp owns a row -- lane (hl = lane & 15) holds elements 256 j + 16 hl .. + 16, j = 0..2, of
+// the row of its half (3 x 16 B loads per lane and row), the query codes live in registers in the same layout.
+// ------------------------------------------------------------------------
+constexpr float kInv254 = 1.f / 254.f;
+constexpr int kI8UnitBytes = kRowsPerUnit * 768;            // one 8-row unit of int8 rows: 6 KB, contiguous
+constexpr int kI8Stages = 2;                                // per warp: two units in flight (TMA bulk copies)
+constexpr int kI8RingBytes = kScanWarps * kI8Stages * kI8UnitBytes;                  // 192 KB per CTA
+constexpr int kI8SmemBytes = kI8RingBytes + kScanWarps * kI8Stages * 8;              // + one mbarrier per stage
+
+// ---- mbarrier / bulk-copy primitives of the int8 sweep (one producer lane and 32 consumers per warp) ----
+__device__ __forceinline__ uint32_t sb_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void sb_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sb_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sb_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool sb_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(sb_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded: a pipeline bug must surface as a trapped kernel, never as a GPU that spins for ever.
+__device__ __forceinline__ void sb_mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (sb_mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!sb_mbar_try_wait(bar, parity)) {
+    if ((++spins & 4095u) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > 4000000000ll) {   // ~2 s
+        printf("css: int8 sweep: bulk copy did not arrive (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+// 1-D bulk copy global -> shared through the TMA unit; completion (bytes) is signalled on `bar`.
+__device__ __forceinline__ void sb_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(sb_smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(sb_smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ int pack_i8x4(float c0, float c1, float c2, float c3) {
+  return (__float2int_rn(c0) & 0xff) | ((__float2int_rn(c1) & 0xff) << 8) | ((__float2int_rn(c2) & 0xff) << 16) |
+         ((__float2int_rn(c3) & 0xff) << 24);
+}
+
+// Quantise the query (every warp for itself).  Out: codes, a1, qn >= ||q||, dq >= ||q - (a1 q1 + a2 q2)||.
+__device__ __forceinline__ void quantize_query_i8(const float* q, const int lane, int (&q1)[12], int (&q2)[12], float& a1,
+                                                  float& qn, float& dq) {
+  const int hl = lane & 15;
+  float4 f[12];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int w = 0; w < 4; ++w) f[j * 4 + w] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + hl * 16) + w);
+  float amax = 0.f, ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(f[i].x), fabsf(f[i].y)), fmaxf(fabsf(f[i].z), fabsf(f[i].w))));
+    ss = fmaf(f[i].x, f[i].x, ss);
+    ss = fmaf(f[i].y, f[i].y, ss);
+    ss = fmaf(f[i].z, f[i].z, ss);
+    ss = fmaf(f[i].w, f[i].w, ss);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {   // both halves of the warp hold the same values
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  qn = sqrtf(ss) * 1.00001f;
+  a1 = amax / 127.f;
+  const float a2 = a1 * kInv254;
+  const float inv1 = amax > 0.f ? 127.f / amax : 0.f;
+  const float inv2 = a2 > 0.f ? 1.f / a2 : 0.f;
+  float d2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; ++i) {
+    const float v[4] = {f[i].x, f[i].y, f[i].z, f[i].w};
+    float c1[4], c2[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      c1[e] = fminf(fmaxf(rintf(v[e] * inv1), -127.f), 127.f);
+      const float r = fmaf(-a1, c1[e], v[e]);
+      c2[e] = fminf(fmaxf(rintf(r * inv2), -127.f), 127.f);
+      const float r2 = fmaf(-a2, c2[e], r);
+      d2 = fmaf(r2, r2, d2);
+    }
+    q1[i] = pack_i8x4(c1[0], c1[1], c1[2], c1[3]);
+    q2[i] = pack_i8x4(c2[0], c2[1], c2[2], c2[3]);
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+  dq = sqrtf(d2) * 1.001f;
+}
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// This lane's share of x^.q^ for one row (48 elements), already multiplied by the row's scale and a1.
+__device__ __forceinline__ float dot_i8(const uint4 (&v)[3], const int (&q1)[12], const int (&q2)[12], const float scale) {
+  int i1 = 0, i2 = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    i1 = __dp4a((int)v[j].x, q1[j * 4 + 0], i1);
+    i2 = __dp4a((int)v[j].x, q2[j * 4 + 0], i2);
+    i1 = __dp4a((int)v[j].y, q1[j * 4 + 1], i1);
+    i2 = __dp4a((int)v[j].y, q2[j * 4 + 1], i2);
+    i1 = __dp4a((int)v[j].z, q1[j * 4 + 2], i1);
+    i2 = __dp4a((int)v[j].z, q2[j * 4 + 2], i2);
+    i1 = __dp4a((int)v[j].w, q1[j * 4 + 3], i1);
+    i2 = __dp4a((int)v[j].w, q2[j * 4 + 3], i2);
+  }
+  return fmaf((float)i2, kInv254, (float)i1) * scale;
+}
+
+// Sum over the 16 lanes of each half; acc0 = the first half's row, acc1 = the second half's (warp-uniform).
+__device__ __forceinline__ void half_sums(float f, float& acc0, float& acc1) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+  acc0 = __shfl_sync(0xffffffffu, f, 0);
+  acc1 = __shfl_sync(0xffffffffu, f, 16);
+}
+
+// Scores of 8 listed rows (filtered scan; the dense sweep keeps its loads rolling, see scan_one_query).
+__device__ __forceinline__ void score_rows_i8(const ScanParams& p, const int (&q1)[12], const int (&q2)[12], const float a1,
+                                              const int64_t (&r)[kRowsPerUnit], const int lane, float (&acc)[kRowsPerUnit]) {
+  const int hl = lane & 15, half = lane >> 4;
+  uint4 v[4][3];
+  float sc[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const int64_t row = half ? r[2 * s + 1] : r[2 * s];
+    const uint4* src = reinterpret_cast<const uint4*>(p.xq + row * 768) + hl;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[s][j] = ld_stream_u4(src + j * 16);
+    sc[s] = __ldg(p.xs + row);
+  }
+#pragma unroll
+  for (int s = 0; s < 4; ++s) half_sums(dot_i8(v[s], q1, q2, sc[s] * a1), acc[2 * s], acc[2 * s + 1]);
 }
 
 // ------------------------------------------------------------------------
@@ -465,7 +633,7 @@ __device__ __forceinline__ KeyId ldcg_keyid(const KeyId* p) {
 }
 
 template <int KPL>
-__device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float qn) {
+__device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float eps) {
   __shared__ float s_t;
   __shared__ int s_cnt, s_unproven;
   const int lane = tid & 31, warp = tid >> 5;
@@ -532,8 +700,10 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (tid == 0) s_cnt = 0;
   }
   __syncthreads();
-  const float eps = qn * (1.001f * (*p.max_err) + 4e-6f * (*p.max_norm));
+  // eps: the tier's bound on |approximate score - exact score| (see scan_one_query); a bound that is not finite
+  // (non-finite query or stored row) proves nothing
   const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
+  if (tid == 0 && !(eps < INFINITY)) s_unproven = 1;
   // (C) proof + candidates over the full lists
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
@@ -623,10 +793,12 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
 // grid = (blocks, nq).  Each warp owns a contiguous range of 8-row units, keeps
 // a register top-k, the block merges its 16 warps in shared memory, and the last
 // block to finish (atomic ticket) merges the per-block lists into D/I.
-// BF16 (inner product, d = 768, no mask): phase 1 of the two-phase scan -- scores from the bf16 shadow rows.
-template <int KPL, int METRIC, bool D768, bool BF16 = false>
+// SH = 1 / 2 (inner product, d = 768): phase 1 of the two-phase scan -- scores from the bf16 / int8 shadow rows.
+template <int KPL, int METRIC, bool D768, int SH = 0>
 __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi) {
-  static_assert(!BF16 || (D768 && METRIC == CSS_METRIC_INNER_PRODUCT), "bf16 phase: inner product, d = 768");
+  static_assert(SH == 0 || (D768 && METRIC == CSS_METRIC_INNER_PRODUCT), "shadow phase: inner product, d = 768");
+  constexpr bool BF16 = SH == 1;
+  constexpr bool I8 = SH == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
   float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
@@ -640,7 +812,15 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 
   float4 qreg[6];
   float qn = 0.f;   // ||q|| (two-phase scan: the error bound of two_phase_finish)
-  if constexpr (BF16) {
+  float eps = 0.f;  // two-phase scan: bound on |shadow score - exact score| of any stored row
+  int q1c[12], q2c[12];   // int8 tier: the query's two code vectors
+  float a1 = 0.f;
+  if constexpr (I8) {
+    float dq;
+    quantize_query_i8(q, lane, q1c, q2c, a1, qn, dq);
+    const float e8 = *p.max_err8, mn = *p.max_norm;
+    eps = 1.001f * (qn * e8 + dq * (mn + e8)) + 4e-6f * qn * mn;
+  } else if constexpr (BF16) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       qreg[2 * j] = __ldg(reinterpret_cast<const float4*>(q + j * 256 + lane * 8));
@@ -654,6 +834,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       qn = fmaf(qreg[j].w, qreg[j].w, qn);
     }
     qn = sqrtf(warp_sum(qn)) * 1.00001f;
+    eps = qn * (1.001f * (*p.max_err) + 4e-6f * (*p.max_norm));
   } else if constexpr (D768) {
 #pragma unroll
     for (int j = 0; j < 6; ++j) qreg[j] = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
@@ -673,6 +854,74 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   const unsigned char* mask8 = reinterpret_cast<const unsigned char*>(p.mask);
 
   bool swept = false;
+  if constexpr (I8) {
+    if (mask8 == nullptr) {
+      // Dense sweep, 8-row units dealt block-cyclically (see the bf16 sweep below).  A unit is 6 KB of contiguous
+      // int8 rows: one lane per warp fetches it with a TMA bulk copy into the warp's two-stage ring in shared
+      // memory (192 KB per CTA in flight, no registers held by data in flight); the warp copies an arrived unit
+      // into registers, re-arms the stage with the unit after next at once and only then does the arithmetic, so
+      // both stages stay in flight during the dot products.  A unit is four row pairs, one row per half-warp.
+      const int hl = lane & 15, half = lane >> 4;
+      const int64_t stride = (int64_t)gridDim.x * kScanWarps;
+      const int64_t last = p.n - 1;
+      unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
+      int64_t u = blockIdx.x + (int64_t)gridDim.x * warp;
+      if (lane == 0) {
+#pragma unroll
+        for (int st = 0; st < kI8Stages; ++st) sb_mbar_init(bars + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < kI8Stages; ++st) {
+          const int64_t us = u + st * stride;
+          if (us < units) {
+            sb_mbar_expect_tx(bars + st, kI8UnitBytes);
+            sb_bulk_load(ring + st * kI8UnitBytes, p.xq + us * kI8UnitBytes, kI8UnitBytes, bars + st);
+          }
+        }
+      }
+      // scales of the rows in flight: lane i < 8 holds row i's of the current (sc_a) and the next unit (sc_b)
+      float sc_a = 0.f, sc_b = 0.f;
+      if (lane < kRowsPerUnit) {
+        if (u < units) sc_a = __ldg(p.xs + min(u * kRowsPerUnit + lane, last));
+        if (u + stride < units) sc_b = __ldg(p.xs + min((u + stride) * kRowsPerUnit + lane, last));
+      }
+      __syncwarp();
+      for (uint32_t it = 0; u < units; ++it, u += stride) {
+        const uint32_t st = it & 1u;
+        sb_mbar_wait(bars + st, (it >> 1) & 1u);
+        const unsigned char* src = ring + st * kI8UnitBytes + half * 768 + hl * 16;
+        uint4 v[4][3];
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) v[s][j] = *reinterpret_cast<const uint4*>(src + s * 1536 + j * 256);
+        const float sc_cur = sc_a * a1;
+        sc_a = sc_b;
+        __syncwarp();   // every lane has read the stage: it may be overwritten
+        const int64_t u2 = u + 2 * stride;
+        if (u2 < units) {
+          if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            sb_mbar_expect_tx(bars + st, kI8UnitBytes);
+            sb_bulk_load(ring + st * kI8UnitBytes, p.xq + u2 * kI8UnitBytes, kI8UnitBytes, bars + st);
+          }
+          if (lane < kRowsPerUnit) sc_b = __ldg(p.xs + min(u2 * kRowsPerUnit + lane, last));
+        }
+        const int64_t row0 = u * kRowsPerUnit;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+          const float f = dot_i8(v[s], q1c, q2c, __shfl_sync(0xffffffffu, sc_cur, 2 * s + half));
+          float a_lo, a_hi;
+          half_sums(f, a_lo, a_hi);
+          if (row0 + 2 * s <= last) top.consider(a_lo, (int)(row0 + 2 * s), lane);
+          if (row0 + 2 * s + 1 <= last) top.consider(a_hi, (int)(row0 + 2 * s + 1), lane);
+        }
+      }
+      swept = true;
+    }
+  }
   if constexpr (BF16) {
     if (mask8 == nullptr && p.interleave) {
       // Dense sweep, 8-row units dealt block-cyclically: unit u belongs to block u % gridDim.x, warp
@@ -745,6 +994,20 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       }
       __syncwarp();
       const int64_t base = ub * kRowsPerUnit;
+      if constexpr (I8) {
+        for (int g0 = 0; g0 < total; g0 += kRowsPerUnit) {
+          int64_t r[kRowsPerUnit];
+#pragma unroll
+          for (int i = 0; i < kRowsPerUnit; ++i) r[i] = base + s_rows[warp][min(g0 + i, total - 1)];
+          float acc[kRowsPerUnit];
+          score_rows_i8(p, q1c, q2c, a1, r, lane, acc);
+#pragma unroll
+          for (int i = 0; i < kRowsPerUnit; ++i)
+            if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
+        }
+        __syncwarp();
+        continue;
+      }
       if constexpr (BF16) {
         for (int g0 = 0; g0 < total; g0 += kRowsPerUnit) {
           int64_t r[kRowsPerUnit];
@@ -826,9 +1089,9 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   __threadfence();
   if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
 
-  if constexpr (BF16) {
+  if constexpr (SH != 0) {
     // two-phase scan: prove + re-score in fp32 (or queue the query for the fp32 scan)
-    two_phase_finish<KPL>(p, qi, s_list, tid, qn);
+    two_phase_finish<KPL>(p, qi, s_list, tid, eps);
     return;
   }
 
@@ -864,20 +1127,20 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 
 // grid = (blocks, nq) scans query blockIdx.y; with p.qlist set, grid = (blocks, F) and
 // slice y walks the listed queries y, y+F, ... (device-side fallback of the batched path).
-template <int KPL, int METRIC, bool D768, bool BF16 = false>
+template <int KPL, int METRIC, bool D768, int SH = 0>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p) {
   // programmatic dependent launch: the fp32-fallback launch behind a two-phase sweep is set up while the sweep
   // runs and only waits here (an empty overflow list -- the normal case -- then costs ~1 us instead of a launch gap)
   if (p.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if constexpr (BF16) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if constexpr (SH != 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (p.zero_on_entry != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *p.zero_on_entry = 0;
   if (p.qlist == nullptr) {
-    scan_one_query<KPL, METRIC, D768, BF16>(p, blockIdx.y);
+    scan_one_query<KPL, METRIC, D768, SH>(p, blockIdx.y);
     return;
   }
   const int cnt = *p.qcount;
   for (int slot = blockIdx.y; slot < cnt; slot += gridDim.y) {
-    scan_one_query<KPL, METRIC, D768, BF16>(p, p.qlist[slot]);
+    scan_one_query<KPL, METRIC, D768, SH>(p, p.qlist[slot]);
     __syncthreads();
   }
   if (p.ex.n_ranks > 1 && p.ex.deferred && blockIdx.x == 0) {
@@ -893,28 +1156,41 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(ScanParams p
 
 // ------------------------------------------------------------------------
 // S1: append rows.  One warp per row: optional L2 normalisation with the
-// reference's epsilon (x / (||x|| + 1e-8)), fp32 store + bf16 shadow store.
+// reference's epsilon (x / (||x|| + 1e-8)), fp32 store + bf16 shadow store + (dst_q8 != nullptr) int8 shadow
+// store: codes rint(v / scale) with scale = max|v| / 127 per row, the scale, and the exact quantisation-error
+// norm ||v - scale * code|| folded into max_err8.
 // ------------------------------------------------------------------------
 static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t n, int d, int normalize,
                                    float* __restrict__ dst, __nv_bfloat16* __restrict__ dst_bf16,
-                                   float* __restrict__ max_norm, float* __restrict__ max_err) {
+                                   float* __restrict__ max_norm, float* __restrict__ max_err,
+                                   int8_t* __restrict__ dst_q8, float* __restrict__ dst_scale,
+                                   float* __restrict__ max_err8) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const float* s = src + row * d;
   float denom = 1.f;
-  float ss = 0.f;
+  float ss = 0.f, amax = 0.f;
   for (int j = lane; j < d; j += 32) {
     float v = s[j];
     ss = fmaf(v, v, ss);
+    amax = fmaxf(amax, fabsf(v));
   }
   ss = warp_sum(ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
   float nrm = sqrtf(ss);
   if (normalize) {
     denom = nrm + 1e-8f;
     nrm = nrm / denom;
+    amax = amax / denom;   // division is monotone: the largest |stored value|
   }
+  // a row with a non-finite element gets zero codes and makes max_err8 infinite: the int8 tier then proves nothing
+  const bool finite = ss < INFINITY;   // false for NaN too
+  const float scale = finite ? amax / 127.f : 0.f;
+  const float inv_scale = (finite && amax > 0.f) ? 127.f / amax : 0.f;
   float es = 0.f;   // ||v - bf16(v)||^2 of the stored row
+  float e8 = 0.f;   // ||v - scale * code||^2
   for (int j = lane; j < d; j += 32) {
     // numpy computes x / (norm + 1e-8); a true division keeps the last bit identical
     float v = normalize ? s[j] / denom : s[j];
@@ -925,8 +1201,22 @@ static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t
       const float e = v - __bfloat162float(b);   // exact in fp32
       es = fmaf(e, e, es);
     }
+    if (dst_q8) {
+      const float c = finite ? fminf(fmaxf(rintf(v * inv_scale), -127.f), 127.f) : 0.f;
+      dst_q8[row * d + j] = (int8_t)__float2int_rn(c);
+      const float e = fmaf(-scale, c, v);
+      e8 = fmaf(e, e, e8);
+    }
   }
   es = warp_sum(es);
+  if (dst_q8) {
+    e8 = warp_sum(e8);
+    if (lane == 0) {
+      dst_scale[row] = scale;
+      const float bound = (finite && e8 < INFINITY) ? sqrtf(e8) * 1.001f : INFINITY;
+      atomicMax(reinterpret_cast<int*>(max_err8), __float_as_int(bound));
+    }
+  }
   // largest stored row norm and largest bf16 rounding-error norm: the error bounds of the two-phase scan
   // and of the batched search derive from them (non-negative floats order like their bit patterns;
   // the 1.0001 covers the rounding of the fp32 sums, non-finite rows poison neither)
@@ -943,7 +1233,9 @@ static __global__ void append_rows_kernel(const float* __restrict__ src, int64_t
 // ------------------------------------------------------------------------
 static __global__ void gather_rows_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ xb,
                                           const int64_t* __restrict__ ids, int64_t n, int d,
-                                          float* __restrict__ out, __nv_bfloat16* __restrict__ outb) {
+                                          float* __restrict__ out, __nv_bfloat16* __restrict__ outb,
+                                          const int8_t* __restrict__ xq, const float* __restrict__ xs,
+                                          int8_t* __restrict__ outq, float* __restrict__ outs) {
   const int lane = threadIdx.x & 31;
   const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
@@ -951,7 +1243,9 @@ static __global__ void gather_rows_kernel(const float* __restrict__ x, const __n
   for (int j = lane; j < d; j += 32) {
     out[i * d + j] = x[src * d + j];
     outb[i * d + j] = xb[src * d + j];
+    if (xq) outq[i * d + j] = xq[src * d + j];
   }
+  if (xq && lane == 0) outs[i] = xs[src];
 }
 static __global__ void gather_i32_kernel(const int32_t* __restrict__ col, const int64_t* __restrict__ ids, int64_t n,
                                          int32_t* __restrict__ out) {

@@ -22,6 +22,7 @@ Options& options() {
       if (v) dst.store(atoi(v));
     };
     env("CSS_SCAN_BF16", o.scan_bf16);
+    env("CSS_SCAN_INT8", o.scan_int8);
     env("CSS_SCAN_INTERLEAVE", o.scan_interleave);
     env("CSS_SCAN_LIST", o.scan_list);
     env("CSS_SCAN_ADAPTIVE", o.scan_adaptive);
@@ -181,6 +182,7 @@ extern "C" int css_set_option(const char* name, int value) {
   css::Options& o = css::options();
   std::atomic<int>* slot = nullptr;
   if (!strcmp(name, "scan_bf16")) slot = &o.scan_bf16;
+  else if (!strcmp(name, "scan_int8")) slot = &o.scan_int8;
   else if (!strcmp(name, "scan_interleave")) slot = &o.scan_interleave;
   else if (!strcmp(name, "scan_list")) slot = &o.scan_list;
   else if (!strcmp(name, "scan_adaptive")) slot = &o.scan_adaptive;

@@ -195,9 +195,11 @@ int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float
                                      int64_t* I_dev, void* stream);
 
 /* Counters of the two-phase batch-1 scan since the index was created: out = {queries answered by it,
- * queries it could not prove from the bf16 lists (re-run by the fp32 sweep), 1 if the adaptive switch
- * currently bypasses it, largest ||x - bf16(x)|| of a stored row x 1e9}. */
-int css_index_scan_stats(css_index* h, int64_t out[4]);
+ * queries it could not prove from the shadow-row lists (re-run by the fp32 sweep), 1 if the adaptive switch
+ * currently bypasses a tier, largest ||x - bf16(x)|| of a stored row x 1e9, largest ||x - scale * int8(x)||
+ * of a stored row x 1e9 (INT64_MAX once a non-finite row was stored), tier of the last scan call (2 = int8
+ * shadow sweep, 1 = bf16 shadow sweep, 0 = fp32 sweep, -1 = none yet)}. */
+int css_index_scan_stats(css_index* h, int64_t out[6]);
 
 /* Evaluate a filter into the index's internal device mask and return its
  * device address (valid until the next call that changes the index/mask). */
@@ -332,9 +334,12 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
 /*   scan_bf16: phase 1 alone of the two-phase batch-1 scan (the bf16 shadow sweep that leaves the per-block
  *              candidate lists), on `stream`, for the roofline measurement of bench.py; no result is produced. */
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream);
+/*   scan_int8: the same for the first tier, the int8 shadow sweep (768 + 4 bytes per 768-d row). */
+int css_debug_scan_int8(css_index* h, const float* q_dev, int nq, void* stream);
 
-/* Process-wide switches (also read from the environment at load: CSS_SCAN_BF16, CSS_SCAN_INTERLEAVE,
+/* Process-wide switches (also read from the environment at load: CSS_SCAN_BF16, CSS_SCAN_INT8, CSS_SCAN_INTERLEAVE,
  * CSS_SCAN_LIST, CSS_SCAN_ADAPTIVE): "scan_bf16" 1 = two-phase batch-1 scan, 0 = single fp32 sweep;
+ * "scan_int8" 1 = the two-phase scan sweeps the int8 shadow rows first (0: the bf16 shadow rows);
  * "scan_interleave" 1 = block-cyclic 8-row units in the bf16 sweep; "scan_list" 32 | 64 = per-block list length
  * (0: chosen by k); "scan_adaptive" 1 = bypass phase 1 while most queries cannot be proven.  Results are exact
  * under every setting; benchmarks use this to time the paths side by side in one process. */

@@ -101,23 +101,23 @@ def test_clustered_corpus_exact_and_mostly_proven(native, order):
 
 def test_near_duplicate_corpus_switches_to_fp32_sweep(native):
     """A corpus whose rows all sit within the bf16 bound of each other (random-init encoder outputs: pairwise cosine
-    ~0.99) cannot be proven from bf16 scores; results stay exact and after 64 such queries the index stops paying
-    for phase 1 (adaptive bypass)."""
+    ~0.99) cannot be proven from int8 or bf16 scores; results stay exact and after 64 such queries per tier the index
+    stops paying for phase 1 (adaptive bypass: int8 tier off after 64 queries, bf16 tier after the next 64)."""
     rng = np.random.default_rng(9)
     n, d = 80_000, 768
     base = so.normalize_rows(rng.standard_normal((1, d), dtype=np.float32))
     x = so.normalize_rows(base + 0.02 * rng.standard_normal((n, d), dtype=np.float32) / np.sqrt(d) * 3)
-    q = so.normalize_rows(base + 0.02 * rng.standard_normal((96, d), dtype=np.float32) / np.sqrt(d) * 3)
+    q = so.normalize_rows(base + 0.02 * rng.standard_normal((192, d), dtype=np.float32) / np.sqrt(d) * 3)
     idx = native.Index(d)
     idx.add(x, normalize=False)
     Dr, Ir = so.flat_search_c(x, q, 10)
-    for i in range(96):
+    for i in range(192):
         D, I = idx.search(q[i:i + 1], 10)
         _check(Dr[i:i + 1], Ir[i:i + 1], D, I, tol=1e-5)
     st = idx.scan_stats()
     if os.environ.get("CSS_SCAN_BF16", "1") != "0" and os.environ.get("CSS_SCAN_ADAPTIVE", "1") != "0":
         assert st["unproven_queries"] >= 60 and st["bypassed"], st
-        assert st["two_phase_queries"] < 96, st                 # the tail of the loop skipped phase 1
+        assert st["two_phase_queries"] < 192 and st["last_tier"] == 0, st   # the tail of the loop skipped phase 1
     idx.close()
 
 
