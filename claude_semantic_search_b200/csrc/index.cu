@@ -353,6 +353,7 @@ static void free_scratch(css_scan_scratch* sc) {
   batched_release(sc);
   cudaFree(sc->q_dev);
   cudaFree(sc->part);
+  cudaFree(sc->part_exact);
   cudaFree(sc->ticket);
   cudaFree(sc->D_dev);
   cudaFree(sc->ovf_list);
@@ -372,6 +373,7 @@ int get_scratch(css_index* h, cudaStream_t st, int nq, css_scan_scratch** out) {
   sc.batched = keep_batched;
   CSS_CHECK(dev_alloc(&sc.q_dev, (size_t)want * h->dim));
   CSS_CHECK(dev_alloc(&sc.part, (size_t)want * h->scan_blocks * CSS_MAX_K));
+  CSS_CHECK(dev_alloc(&sc.part_exact, (size_t)want * h->scan_blocks * CSS_MAX_K));
   CSS_CHECK(dev_alloc(&sc.ticket, (size_t)want));
   // scores, then the ids of the same call, then the overflow count: one D2H returns all three
   CSS_CHECK(dev_alloc(&sc.D_dev, (size_t)want * CSS_MAX_K * 3 + 16));
@@ -401,6 +403,7 @@ static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const
   p->q = q_dev;
   p->mask = mask_dev;
   p->part = sc->part;
+  p->part_exact = sc->part_exact;
   p->ticket = sc->ticket;
   p->idmap = idmap;
   p->D = D_dev;
@@ -557,7 +560,9 @@ template <typename K>
 static int preload_kernel(K kern, size_t smem) {
   cudaFuncAttributes a;
   CSS_CUDA(cudaFuncGetAttributes(&a, kern));
-  if (smem) CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (smem) {
+    CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
   return CSS_OK;
 }
 template <int KPL>

@@ -32,6 +32,7 @@ struct css_scan_scratch {
   int max_nq = 0;
   float* q_dev = nullptr;            // [max_nq, dim]
   css::KeyId* part = nullptr;        // [max_nq][scan_blocks][CSS_MAX_K]
+  float* part_exact = nullptr;       // [max_nq][scan_blocks][CSS_MAX_K] two-phase scan: fp32 scores of the list entries
   unsigned int* ticket = nullptr;    // [max_nq]
   float* D_dev = nullptr;            // [max_nq, CSS_MAX_K] scores + ids of one host call (12 B per slot) + overflow count
   int* ovf_list = nullptr;           // two-phase scan: [max_nq] queries handed to the fp32 scan

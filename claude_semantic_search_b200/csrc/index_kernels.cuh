@@ -9,6 +9,8 @@
 // row exactly once with 128-bit streaming loads and keeps the top-k in
 // registers, so nothing but k results per block is ever written.
 #pragma once
+#include <type_traits>
+
 #include "css_common.cuh"
 
 namespace css {
@@ -112,6 +114,7 @@ struct WarpTopK {
     thr_id = wi;
   }
 
+  __device__ __forceinline__ void maybe_compact(int) {}
   // Warp-uniform call: (k_, i_) identical in all lanes.
   __device__ __forceinline__ void consider(float k_, int i_, int lane) {
     if (!better(k_, i_, thr_key, thr_id)) return;
@@ -127,6 +130,85 @@ struct WarpTopK {
       }
     }
     recompute();
+  }
+};
+
+// ------------------------------------------------------------------------
+// Per-warp top-32 of the shadow sweeps (two-phase scan, 32-entry block lists): a sorted list, one entry per
+// lane, plus a 32-entry buffer of pending candidates, one per lane.  A row that beats the 32nd key so far costs a
+// predicated register write; every 32 such rows the buffer is sorted and merged into the list across the lanes.
+// WarpTopK::consider pays a ballot and a 10-shuffle re-scan of the list per accepted row -- a quarter of all rows
+// while a warp has seen only a few hundred (1 M rows over 2368 warps), 130 instructions per 8-row unit.  Ties at
+// the 32nd key are dropped: the proof of two_phase_finish only needs every row outside a list to score no higher
+// than the list's last entry.  Same members as WarpTopK<1> for the block merge (after flush()).
+// ------------------------------------------------------------------------
+struct WarpBufTop32 {
+  float key[1];
+  int id[1];
+  float bkey;
+  int bid;
+  int nb;       // pending entries: lanes [0, nb)
+  float thr;    // 32nd best key so far (-inf until 32 rows were kept)
+
+  __device__ __forceinline__ void init(int, int) {
+    key[0] = -INFINITY;
+    id[0] = kEmptyId;
+    bkey = -INFINITY;
+    bid = kEmptyId;
+    nb = 0;
+    thr = -INFINITY;
+  }
+  __device__ __forceinline__ static void exchange(float& k, int& i, const int lane, const int o, const bool keep_better) {
+    const float ok = __shfl_xor_sync(0xffffffffu, k, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    const bool other_better = better(ok, oi, k, i);
+    if (other_better == keep_better) {
+      k = ok;
+      i = oi;
+    }
+  }
+  __device__ __forceinline__ void compact(const int lane) {
+    if (lane >= nb) {
+      bkey = -INFINITY;
+      bid = kEmptyId;
+    }
+    // bitonic sort of the buffer, best entry in lane 0
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+      for (int o = size >> 1; o > 0; o >>= 1) {
+        const bool desc = (lane & size) == 0 || size == 32;
+        const bool lower = (lane & o) == 0;
+        exchange(bkey, bid, lane, o, lower == desc);
+      }
+    }
+    // list[i] = better(list[i], buffer[31 - i]): the 32 best of both, as a bitonic sequence; then a bitonic merge
+    const float rk = __shfl_sync(0xffffffffu, bkey, 31 - lane);
+    const int ri = __shfl_sync(0xffffffffu, bid, 31 - lane);
+    if (better(rk, ri, key[0], id[0])) {
+      key[0] = rk;
+      id[0] = ri;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) exchange(key[0], id[0], lane, o, (lane & o) == 0);
+    thr = __shfl_sync(0xffffffffu, key[0], 31);
+    nb = 0;
+  }
+  // Warp-uniform (k_, i_).  The caller runs maybe_compact() at least once per 8 calls (the buffer keeps 8 free slots).
+  __device__ __forceinline__ void consider(const float k_, const int i_, const int lane) {
+    if (k_ > thr) {
+      if (lane == nb) {
+        bkey = k_;
+        bid = i_;
+      }
+      ++nb;
+    }
+  }
+  __device__ __forceinline__ void maybe_compact(const int lane) {
+    if (nb > 24) compact(lane);
+  }
+  __device__ __forceinline__ void flush(const int lane) {
+    if (nb > 0) compact(lane);
   }
 };
 
@@ -187,6 +269,7 @@ struct ScanParams {
   int k;                 // entries kept per warp / per block list
   int k_out;             // entries of the result (== k except in the two-phase scan, where k is the list length)
   KeyId* part;           // [nq][gridDim.x][k]
+  float* part_exact;     // [nq][gridDim.x][k] two-phase scan: fp32 scores of the list entries (written by the block that owns the list)
   unsigned int* ticket;  // [nq], zero on entry, zero on exit
   IdMap idmap;
   float* D;              // [nq, k_out]
@@ -426,19 +509,19 @@ __device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
 
 // This lane's share of x^.q^ for one row (48 elements), already multiplied by the row's scale and a1.
 __device__ __forceinline__ float dot_i8(const uint4 (&v)[3], const int (&q1)[12], const int (&q2)[12], const float scale) {
-  int i1 = 0, i2 = 0;
+  int i1 = 0, i2 = 0, j1 = 0, j2 = 0;   // two chains per code vector: six dependent dp4a instead of twelve
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     i1 = __dp4a((int)v[j].x, q1[j * 4 + 0], i1);
     i2 = __dp4a((int)v[j].x, q2[j * 4 + 0], i2);
-    i1 = __dp4a((int)v[j].y, q1[j * 4 + 1], i1);
-    i2 = __dp4a((int)v[j].y, q2[j * 4 + 1], i2);
+    j1 = __dp4a((int)v[j].y, q1[j * 4 + 1], j1);
+    j2 = __dp4a((int)v[j].y, q2[j * 4 + 1], j2);
     i1 = __dp4a((int)v[j].z, q1[j * 4 + 2], i1);
     i2 = __dp4a((int)v[j].z, q2[j * 4 + 2], i2);
-    i1 = __dp4a((int)v[j].w, q1[j * 4 + 3], i1);
-    i2 = __dp4a((int)v[j].w, q2[j * 4 + 3], i2);
+    j1 = __dp4a((int)v[j].w, q1[j * 4 + 3], j1);
+    j2 = __dp4a((int)v[j].w, q2[j * 4 + 3], j2);
   }
-  return fmaf((float)i2, kInv254, (float)i1) * scale;
+  return fmaf((float)(i2 + j2), kInv254, (float)(i1 + j1)) * scale;
 }
 
 // Sum over the 16 lanes of each half; acc0 = the first half's row, acc1 = the second half's (warp-uniform).
@@ -619,7 +702,31 @@ __device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, Key
 // Selection is by rank counting (no sorting network: one barrier per step); s: kMergeCap entries.
 // Returns true when the result was emitted.
 // ------------------------------------------------------------------------
-constexpr int kRescoreCap = 2048;    // candidates re-scored per query at most (second half of s: rank-sort output)
+// Exact fp32 scores of two rows with the arithmetic of the fp32 scan (score_rows: lane l holds float4 32 j + l,
+// FMAs in element order, butterfly sum) -- bit-identical scores.  Whole warp; q: the query in global memory.
+__device__ __forceinline__ void exact_score_pair(const float* __restrict__ x, const float* __restrict__ q, const int id0,
+                                                 const int id1, const int lane, float& a0, float& a1) {
+  const float4* r0 = reinterpret_cast<const float4*>(x + (size_t)id0 * 768);
+  const float4* r1 = reinterpret_cast<const float4*>(x + (size_t)id1 * 768);
+  float4 v0[6], v1[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    v0[j] = ld_stream_f4(r0 + j * 32 + lane);
+    v1[j] = ld_stream_f4(r1 + j * 32 + lane);
+  }
+  a0 = 0.f;
+  a1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
+    a0 = fmaf(v0[j].x, qv.x, a0); a0 = fmaf(v0[j].y, qv.y, a0); a0 = fmaf(v0[j].z, qv.z, a0); a0 = fmaf(v0[j].w, qv.w, a0);
+    a1 = fmaf(v1[j].x, qv.x, a1); a1 = fmaf(v1[j].y, qv.y, a1); a1 = fmaf(v1[j].z, qv.z, a1); a1 = fmaf(v1[j].w, qv.w, a1);
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+}
+
+constexpr int kRescoreCap = 2048;    // candidates kept per query at most (second half of s: rank-sort output)
 constexpr int kTwoPhaseMaxK = 32;    // largest k the two-phase scan serves
 constexpr int kRankSortMax = 1024;   // above this many candidates: bitonic sort instead of rank counting
 constexpr int kTwoPhaseMaxBlocks = 160;  // scan blocks (= SMs) the register-held list entries of two_phase_finish cover
@@ -636,21 +743,25 @@ template <int KPL>
 __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float eps) {
   __shared__ float s_t;
   __shared__ int s_cnt, s_unproven;
-  const int lane = tid & 31, warp = tid >> 5;
   const int kp = p.k, k = p.k_out, blocks = gridDim.x;
   const KeyId* lists = p.part + (size_t)qi * blocks * kp;
-  const float* q = p.q + (size_t)qi * 768;
   // every list entry is read ONCE, all loads in flight together (one L2 round trip), and kept in registers for the
   // three selection steps below: thread t holds entries t, t + 512, ...  (kTwoPhaseMaxBlocks bounds the grid)
   constexpr int kPer = (kTwoPhaseMaxBlocks * 32 * KPL + kScanThreads - 1) / kScanThreads;
   const int total = blocks * kp;
   KeyId ent[kPer];
+  float exact[kPer];   // fp32 score of the entry, computed by the block that owns the list (scan_one_query)
+  const float* lists_exact = p.part_exact + (size_t)qi * blocks * kp;
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
     const int i = tid + c * kScanThreads;
     ent[c].key = -INFINITY;
     ent[c].id = kEmptyId;
-    if (i < total) ent[c] = ldcg_keyid(lists + i);
+    exact[c] = -INFINITY;
+    if (i < total) {
+      ent[c] = ldcg_keyid(lists + i);
+      exact[c] = __ldcg(lists_exact + i);
+    }
   }
   if (tid == 0) {
     s_t = -INFINITY;
@@ -711,7 +822,10 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
       const int i = tid + c * kScanThreads;
       if (i % kp == kp - 1) s_unproven = 1;
       const int pos = atomicAdd(&s_cnt, 1);
-      if (pos < kRescoreCap) s[pos] = ent[c];
+      if (pos < kRescoreCap) {
+        s[pos].key = exact[c];   // from here on the exact fp32 score
+        s[pos].id = ent[c].id;
+      }
     }
   }
   __syncthreads();
@@ -728,33 +842,8 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     }
     return false;
   }
-  // (D) exact fp32 scores, two candidates in flight per warp (the arithmetic of score_rows)
-  for (int i0 = warp * 2; i0 < keep; i0 += kScanWarps * 2) {
-    const int i1 = min(i0 + 1, keep - 1);
-    const float4* r0 = reinterpret_cast<const float4*>(p.x + (size_t)s[i0].id * 768);
-    const float4* r1 = reinterpret_cast<const float4*>(p.x + (size_t)s[i1].id * 768);
-    float4 v0[6], v1[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      v0[j] = ld_stream_f4(r0 + j * 32 + lane);
-      v1[j] = ld_stream_f4(r1 + j * 32 + lane);
-    }
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + j * 32 + lane);
-      a0 = fmaf(v0[j].x, qv.x, a0); a0 = fmaf(v0[j].y, qv.y, a0); a0 = fmaf(v0[j].z, qv.z, a0); a0 = fmaf(v0[j].w, qv.w, a0);
-      a1 = fmaf(v1[j].x, qv.x, a1); a1 = fmaf(v1[j].y, qv.y, a1); a1 = fmaf(v1[j].z, qv.z, a1); a1 = fmaf(v1[j].w, qv.w, a1);
-    }
-    a0 = warp_sum(a0);
-    a1 = warp_sum(a1);
-    __syncwarp();
-    if (lane == 0) {
-      s[i0].key = a0;
-      if (i1 != i0) s[i1].key = a1;
-    }
-  }
-  __syncthreads();
+  // (D) the candidates' exact fp32 scores were computed by the blocks that own them, in parallel over the grid
+  //     (scan_one_query), so the tail of the query holds no DRAM round trip.
   // (E) order by (score desc, id asc)
   KeyId* out = s;
   if (keep <= kRankSortMax) {
@@ -816,6 +905,27 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   int q1c[12], q2c[12];   // int8 tier: the query's two code vectors
   float a1 = 0.f;
   if constexpr (I8) {
+    if (p.mask == nullptr && lane == 0) {
+      // dense sweep (below): the warp's first two units are requested before anything else, the query is
+      // quantised while they are on their way
+      unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
+      uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
+      const int64_t units0 = (p.n + kRowsPerUnit - 1) / kRowsPerUnit;
+      const int64_t stride0 = (int64_t)gridDim.x * kScanWarps;
+      const int64_t u0 = blockIdx.x + (int64_t)gridDim.x * warp;
+#pragma unroll
+      for (int st = 0; st < kI8Stages; ++st) sb_mbar_init(bars + st, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#pragma unroll
+      for (int st = 0; st < kI8Stages; ++st) {
+        const int64_t us = u0 + st * stride0;
+        if (us < units0) {
+          sb_mbar_expect_tx(bars + st, kI8UnitBytes);
+          sb_bulk_load(ring + st * kI8UnitBytes, p.xq + us * kI8UnitBytes, kI8UnitBytes, bars + st);
+        }
+      }
+    }
     float dq;
     quantize_query_i8(q, lane, q1c, q2c, a1, qn, dq);
     const float e8 = *p.max_err8, mn = *p.max_norm;
@@ -843,7 +953,9 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     __syncthreads();
   }
 
-  WarpTopK<KPL> top;
+  // shadow sweeps with 32-entry lists: buffered selection (see WarpBufTop32); p.k == 32 there
+  constexpr bool kBuffered = SH != 0 && KPL == 1;
+  typename std::conditional<kBuffered, WarpBufTop32, WarpTopK<KPL>>::type top;
   top.init(lane, p.k);
 
   const int64_t units = (p.n + kRowsPerUnit - 1) / kRowsPerUnit;
@@ -866,21 +978,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       const int64_t last = p.n - 1;
       unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
       uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
-      int64_t u = blockIdx.x + (int64_t)gridDim.x * warp;
-      if (lane == 0) {
-#pragma unroll
-        for (int st = 0; st < kI8Stages; ++st) sb_mbar_init(bars + st, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#pragma unroll
-        for (int st = 0; st < kI8Stages; ++st) {
-          const int64_t us = u + st * stride;
-          if (us < units) {
-            sb_mbar_expect_tx(bars + st, kI8UnitBytes);
-            sb_bulk_load(ring + st * kI8UnitBytes, p.xq + us * kI8UnitBytes, kI8UnitBytes, bars + st);
-          }
-        }
-      }
+      int64_t u = blockIdx.x + (int64_t)gridDim.x * warp;   // (the first two units were requested at the top)
       // scales of the rows in flight: lane i < 8 holds row i's of the current (sc_a) and the next unit (sc_b)
       float sc_a = 0.f, sc_b = 0.f;
       if (lane < kRowsPerUnit) {
@@ -910,14 +1008,41 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
           if (lane < kRowsPerUnit) sc_b = __ldg(p.xs + min(u2 * kRowsPerUnit + lane, last));
         }
         const int64_t row0 = u * kRowsPerUnit;
+        const bool tail = row0 + kRowsPerUnit > p.n;   // only the corpus' last unit
+        float f[4];
 #pragma unroll
-        for (int s = 0; s < 4; ++s) {
-          const float f = dot_i8(v[s], q1c, q2c, __shfl_sync(0xffffffffu, sc_cur, 2 * s + half));
-          float a_lo, a_hi;
-          half_sums(f, a_lo, a_hi);
-          if (row0 + 2 * s <= last) top.consider(a_lo, (int)(row0 + 2 * s), lane);
-          if (row0 + 2 * s + 1 <= last) top.consider(a_hi, (int)(row0 + 2 * s + 1), lane);
+        for (int s = 0; s < 4; ++s) f[s] = dot_i8(v[s], q1c, q2c, __shfl_sync(0xffffffffu, sc_cur, 2 * s + half));
+        if constexpr (kBuffered) {
+          // the four butterflies interleave; afterwards the lanes of a half all hold their row's score and ONE vote
+          // decides for the unit's eight rows
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+            for (int s = 0; s < 4; ++s) f[s] += __shfl_xor_sync(0xffffffffu, f[s], o);
+          if (tail) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              if (row0 + 2 * s + half > last) f[s] = -INFINITY;
+          }
+          const float fm = fmaxf(fmaxf(f[0], f[1]), fmaxf(f[2], f[3]));
+          if (__any_sync(0xffffffffu, fm > top.thr)) {
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+              const float a_lo = __shfl_sync(0xffffffffu, f[s], 0), a_hi = __shfl_sync(0xffffffffu, f[s], 16);
+              top.consider(a_lo, (int)(row0 + 2 * s), lane);
+              top.consider(a_hi, (int)(row0 + 2 * s + 1), lane);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int s = 0; s < 4; ++s) {
+            float a_lo, a_hi;
+            half_sums(f[s], a_lo, a_hi);
+            if (row0 + 2 * s <= last) top.consider(a_lo, (int)(row0 + 2 * s), lane);
+            if (row0 + 2 * s + 1 <= last) top.consider(a_hi, (int)(row0 + 2 * s + 1), lane);
+          }
         }
+        top.maybe_compact(lane);
       }
       swept = true;
     }
@@ -940,6 +1065,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 #pragma unroll
         for (int i = 0; i < kRowsPerUnit; ++i)
           if (i < valid) top.consider(acc[i], (int)(row0 + i), lane);
+        top.maybe_compact(lane);
       }
       swept = true;
     }
@@ -969,6 +1095,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 #pragma unroll
           for (int i = 0; i < kRowsPerUnit; ++i)
             if ((m >> i) & 1u) top.consider(acc[i], (int)(row0 + i), lane);
+          top.maybe_compact(lane);
         }
         continue;
       }
@@ -1004,6 +1131,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 #pragma unroll
           for (int i = 0; i < kRowsPerUnit; ++i)
             if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
+          top.maybe_compact(lane);
         }
         __syncwarp();
         continue;
@@ -1018,6 +1146,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 #pragma unroll
           for (int i = 0; i < kRowsPerUnit; ++i)
             if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
+          top.maybe_compact(lane);
         }
         __syncwarp();
         continue;
@@ -1063,6 +1192,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
 
   // ---- block merge: 16 warps x 32 lanes x KPL slots -> sorted smem list ----
   constexpr int kBlockEntries = kScanThreads * KPL;  // power of two
+  if constexpr (kBuffered) top.flush(lane);
   __syncthreads();
 #pragma unroll
   for (int s = 0; s < KPL; ++s) {
@@ -1076,6 +1206,23 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   KeyId* my_part = p.part + ((int64_t)qi * gridDim.x + blockIdx.x) * p.k;
   for (int i = tid; i < p.k; i += kScanThreads) my_part[i] = s_list[i];
   if (p.no_merge) return;
+  if constexpr (SH != 0) {
+    // Two-phase scan: every block re-scores ITS list in fp32 right away -- 148 blocks x one DRAM round trip in
+    // parallel (and overlapping the blocks still sweeping) instead of the last block walking all candidates alone
+    // (int8 tier: ~220 rows within 2 eps of the k-th score, seven dependent round trips = 10 us of a 135 us query).
+    // 32 rows x 3 KB per block: 2 % of the sweep's bytes.
+    float* my_exact = p.part_exact + ((int64_t)qi * gridDim.x + blockIdx.x) * p.k;
+    for (int i0 = warp * 2; i0 < p.k; i0 += kScanWarps * 2) {
+      const int id0 = s_list[i0].id, id1 = s_list[i0 + 1].id;
+      if (id0 == kEmptyId) break;   // sorted: nothing but empty slots from here on
+      float a0, a1;
+      exact_score_pair(p.x, q, id0, id1 == kEmptyId ? id0 : id1, lane, a0, a1);
+      if (lane == 0) {
+        my_exact[i0] = a0;
+        my_exact[i0 + 1] = id1 == kEmptyId ? -INFINITY : a1;
+      }
+    }
+  }
 
   // ---- grid merge by the last block -----------------------------------------
   __threadfence();
