@@ -138,6 +138,7 @@ SIGNATURES = {
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
     "css_debug_scan_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "css_debug_scan_int8": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
+    "css_debug_scan_trace": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "css_tokenizer_create": (c_int, [ctypes.c_char_p, c_int, POINTER(c_void_p)]),
     "css_tokenizer_destroy": (c_int, [c_void_p]),
     "css_tokenizer_vocab_size": (c_int, [c_void_p]),
@@ -488,6 +489,12 @@ class Index:
         check(self._lib.css_debug_scan_int8(self._h, c_void_p(q_ptr), nq, c_void_p(stream)))
 
     # -- persistence --------------------------------------------------------
+    def debug_scan_trace(self, q_ptr: int, k: int = 10, stream: int = 0, blocks: int = 160) -> np.ndarray:
+        """Timeline (ns) of one batch-1 scan, [blocks + 1, 8] (css_debug_scan_trace); all-zero rows are unused."""
+        out = np.zeros((blocks + 1) * 8, dtype=np.int64)
+        check(self._lib.css_debug_scan_trace(self._h, c_void_p(q_ptr), k, out.ctypes.data, out.shape[0], c_void_p(stream)))
+        return out.reshape(-1, 8)
+
     def save(self, path) -> None:
         check(self._lib.css_index_save(self._h, str(path).encode()))
 

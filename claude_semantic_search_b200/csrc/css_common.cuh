@@ -77,6 +77,7 @@ struct Options {
   std::atomic<int> scan_interleave{1};  // dense bf16 sweep deals 8-row units block-cyclically
   std::atomic<int> scan_list{0};        // per-block list length 32 | 64 (0: by k)
   std::atomic<int> scan_adaptive{1};    // bypass phase 1 while most queries cannot be proven
+  std::atomic<int> scan_mapped{1};      // single-query host calls: results + completion flag written to mapped host memory
   std::atomic<int> scan_pdl{1};         // fp32-fallback launch as a programmatic dependent of the bf16 sweep
 };
 Options& options();

@@ -38,6 +38,9 @@ struct css_scan_scratch {
   int* ovf_list = nullptr;           // two-phase scan: [max_nq] queries handed to the fp32 scan
   int* ovf_count = nullptr;          // [1] (inside D_dev's allocation so one D2H returns it with the result)
   void* batched = nullptr;           // BatchedState of search_batched.cu
+  long long* trace = nullptr;        // css_debug_scan_trace: timeline stamps of the next scans on this stream
+  unsigned* done_flag = nullptr;     // set around a single-query host call: mapped host word the scan kernel signals
+  unsigned done_seq = 0;
 };
 
 struct css_exchange {
@@ -94,8 +97,10 @@ struct css_index {
   int64_t* ids_scratch = nullptr;    // css_index_set_alive_ids
   int64_t ids_scratch_n = 0;
   // scratch (pinned host)
-  void* pinned = nullptr;
+  void* pinned = nullptr;            // mapped (the scan kernels write single-query results straight into it)
+  void* pinned_dev = nullptr;        // device view of `pinned`
   size_t pinned_bytes = 0;
+  unsigned call_seq = 0;             // sequence number of the single-query host calls (completion flag value)
 
   // two-phase scan statistics: device counters {queries, unproven} mirrored by the kernel into mapped
   // host memory, read without synchronisation to steer the adaptive path choice

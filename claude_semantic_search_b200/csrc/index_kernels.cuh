@@ -271,6 +271,7 @@ struct ScanParams {
   KeyId* part;           // [nq][gridDim.x][k]
   float* part_exact;     // [nq][gridDim.x][k] two-phase scan: fp32 scores of the list entries (written by the block that owns the list)
   unsigned int* ticket;  // [nq], zero on entry, zero on exit
+  unsigned int* cursor;  // [nq], zero on entry, zero on exit: int8 sweep, next pair of dynamically dealt units
   IdMap idmap;
   float* D;              // [nq, k_out]
   int64_t* I;            // [nq, k_out]
@@ -288,6 +289,9 @@ struct ScanParams {
   int* ovf_count;
   unsigned* stats_dev;   // [2] two-phase queries, unproven queries (device counters)
   volatile unsigned* stats_host;  // nullable: the same two counters mirrored into mapped host memory
+  long long* trace;      // nullable (css_debug_scan_trace): [gridDim.x + 1][8] globaltimer stamps, see scan_stamp
+  unsigned* done_flag;   // nullable (single-query host calls): mapped host word that receives done_seq << 1 | unproven
+  unsigned done_seq;     //   once the query's result (D / I may be mapped host memory too) has been written
   ExchangeDev ex;
 };
 
@@ -651,6 +655,22 @@ __device__ __forceinline__ void await_and_merge(const ScanParams& p, const int q
   }
 }
 
+// Timeline of one query for css_debug_scan_trace: row b = block b {0 start, 1 sweep done, 2 block list merged,
+// 3 list re-scored, 4 ticket drawn}; row gridDim.x = the last block {0 lists loaded, 1 t found, 2 candidates
+// gathered, 3 ordered, 4 emitted}.  Thread 0 only; ns of %globaltimer.
+__device__ __forceinline__ void scan_stamp(const ScanParams& p, const int row, const int slot) {
+  if (p.trace != nullptr && threadIdx.x == 0) p.trace[row * 8 + slot] = (long long)global_timer_ns();
+}
+
+// Single-query host calls: tell the polling host thread that the result is in place (all threads of the CTA that
+// wrote it call this; the result and the flag may both live in mapped host memory).
+__device__ __forceinline__ void signal_done(const ScanParams& p, const int tid, const unsigned unproven) {
+  if (p.done_flag == nullptr) return;
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) st_release_sys(p.done_flag, (p.done_seq << 1) | unproven);
+}
+
 template <int METRIC>
 __device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, KeyId* s, const int tid, const int nthreads) {
   const int k = p.k_out;
@@ -739,11 +759,28 @@ __device__ __forceinline__ KeyId ldcg_keyid(const KeyId* p) {
   return e;
 }
 
+// Number of entries of s[0..n) that come before e in the result order.  Eight loads in flight: the plain loop pays
+// one shared-memory latency per entry (3.5 us for the 220 candidates of an int8-tier query).
+__device__ __forceinline__ int rank_among(const KeyId* s, const int n, const KeyId e) {
+  int rank = 0;
+  int j = 0;
+  for (; j + 8 <= n; j += 8) {
+    KeyId t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = s[j + u];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) rank += better(t[u], e) ? 1 : 0;
+  }
+  for (; j < n; ++j) rank += better(s[j], e) ? 1 : 0;
+  return rank;
+}
+
 template <int KPL>
 __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float eps) {
   __shared__ float s_t;
   __shared__ int s_cnt, s_unproven;
-  const int kp = p.k, k = p.k_out, blocks = gridDim.x;
+  constexpr int kp = 32 * KPL;   // == p.k: the list length is the warp list's capacity
+  const int k = p.k_out, blocks = gridDim.x;
   const KeyId* lists = p.part + (size_t)qi * blocks * kp;
   // every list entry is read ONCE, all loads in flight together (one L2 round trip), and kept in registers for the
   // three selection steps below: thread t holds entries t, t + 512, ...  (kTwoPhaseMaxBlocks bounds the grid)
@@ -768,6 +805,7 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     s_cnt = 0;
     s_unproven = 0;
   }
+  scan_stamp(p, gridDim.x, 0);
   // (A) t0 = k-th best list head (k distinct rows score at least that); with fewer than k lists the
   //     k-th best of their first k entries.
   const int per = blocks >= k ? 1 : k;
@@ -782,9 +820,7 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   for (int i = tid; i < nsel; i += kScanThreads) {
     const KeyId e = s[i];
     if (e.id == kEmptyId) continue;
-    int rank = 0;
-    for (int j = 0; j < nsel; ++j) rank += better(s[j], e) ? 1 : 0;
-    if (rank == k - 1) s_t = e.key;
+    if (rank_among(s, nsel, e) == k - 1) s_t = e.key;
   }
   __syncthreads();
   const float t0 = s_t;
@@ -802,15 +838,14 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (c <= kRankSortMax) {
       for (int i = tid; i < c; i += kScanThreads) {
         const KeyId e = s[i];
-        int rank = 0;
-        for (int j = 0; j < c; ++j) rank += better(s[j], e) ? 1 : 0;
-        if (rank == k - 1) s_t = e.key;
+        if (rank_among(s, c, e) == k - 1) s_t = e.key;
       }
     }
     __syncthreads();
     if (tid == 0) s_cnt = 0;
   }
   __syncthreads();
+  scan_stamp(p, gridDim.x, 1);
   // eps: the tier's bound on |approximate score - exact score| (see scan_one_query); a bound that is not finite
   // (non-finite query or stored row) proves nothing
   const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
@@ -829,6 +864,7 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     }
   }
   __syncthreads();
+  scan_stamp(p, gridDim.x, 2);
   const int keep = s_cnt;
   if (tid == 0) {
     const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
@@ -850,9 +886,7 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     out = s + kRescoreCap;
     for (int i = tid; i < keep; i += kScanThreads) {
       const KeyId e = s[i];
-      int rank = 0;
-      for (int j = 0; j < keep; ++j) rank += better(s[j], e) ? 1 : 0;
-      out[rank] = e;
+      out[rank_among(s, keep, e)] = e;
     }
     for (int i = keep + tid; i < k; i += kScanThreads) {
       out[i].key = -INFINITY;
@@ -875,9 +909,63 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (tid < k) s[tid] = e;
     __syncthreads();
   }
+  scan_stamp(p, gridDim.x, 3);
   emit_topk<CSS_METRIC_INNER_PRODUCT>(p, qi, s, tid, kScanThreads);
+  scan_stamp(p, gridDim.x, 4);
   return true;
 }
+
+// Units of the dense int8 sweep for one warp.  The first three quarters of the warp's share are dealt statically,
+// block-cyclically (round r: unit r * nwarps + gw) -- neighbouring rows land in different blocks, and the addresses
+// are known two units ahead without any traffic.  The rest of the corpus is handed out in pairs of units from a
+// per-query cursor: blocks do not stream at the same rate (sweep ends spread over 88 .. 110 us of a 1 M-row query
+// when every warp gets the same share; SMs further from the memory partitions they read see more latency per bulk
+// copy), so the fast warps take what the slow ones have not reached.  The cursor value is fetched one pair ahead
+// (lane 0's `raw`), its latency never waited for.
+struct UnitFeed {
+  int64_t units, nwarps, gw, stat_rounds, stat_units;
+  int64_t r;           // next static round
+  int64_t dyn_second;  // second unit of the pair in hand, -1: none
+  unsigned raw;        // lane 0: the cursor value fetched ahead
+  unsigned* cursor;
+  bool done;
+
+  __device__ __forceinline__ void init(const ScanParams& p, const int qi, const int64_t units_, const int64_t nwarps_,
+                                       const int64_t gw_, const int lane) {
+    units = units_;
+    nwarps = nwarps_;
+    gw = gw_;
+    const int64_t per_warp = units / nwarps;
+    stat_rounds = per_warp - per_warp / 4;
+    stat_units = stat_rounds * nwarps;
+    r = 0;
+    dyn_second = -1;
+    cursor = p.cursor + qi;
+    done = false;
+    raw = 0;
+    if (lane == 0) raw = atomicAdd(cursor, 1u);
+  }
+  // Next unit of this warp, -1 when the corpus is exhausted.  Warp-uniform.
+  __device__ __forceinline__ int64_t next(const int lane) {
+    if (r < stat_rounds) return (r++) * nwarps + gw;
+    if (done) return -1;
+    if (dyn_second >= 0) {
+      const int64_t u = dyn_second;
+      dyn_second = -1;
+      if (u < units) return u;
+      done = true;
+      return -1;
+    }
+    const int64_t base = stat_units + 2 * (int64_t)__shfl_sync(0xffffffffu, raw, 0);
+    if (base >= units) {
+      done = true;
+      return -1;
+    }
+    if (lane == 0) raw = atomicAdd(cursor, 1u);
+    dyn_second = base + 1;
+    return base;
+  }
+};
 
 // grid = (blocks, nq).  Each warp owns a contiguous range of 8-row units, keeps
 // a register top-k, the block merges its 16 warps in shared memory, and the last
@@ -904,25 +992,30 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   float eps = 0.f;  // two-phase scan: bound on |shadow score - exact score| of any stored row
   int q1c[12], q2c[12];   // int8 tier: the query's two code vectors
   float a1 = 0.f;
+  UnitFeed feed;          // int8 tier, dense sweep: the warp's units
+  int64_t u_cur = -1, u_nxt = -1;
   if constexpr (I8) {
-    if (p.mask == nullptr && lane == 0) {
+    if (p.mask == nullptr) {
       // dense sweep (below): the warp's first two units are requested before anything else, the query is
       // quantised while they are on their way
-      unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
-      uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
       const int64_t units0 = (p.n + kRowsPerUnit - 1) / kRowsPerUnit;
-      const int64_t stride0 = (int64_t)gridDim.x * kScanWarps;
-      const int64_t u0 = blockIdx.x + (int64_t)gridDim.x * warp;
+      feed.init(p, qi, units0, (int64_t)gridDim.x * kScanWarps, blockIdx.x + (int64_t)gridDim.x * warp, lane);
+      u_cur = feed.next(lane);
+      u_nxt = feed.next(lane);
+      if (lane == 0) {
+        unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
+        uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
 #pragma unroll
-      for (int st = 0; st < kI8Stages; ++st) sb_mbar_init(bars + st, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int st = 0; st < kI8Stages; ++st) sb_mbar_init(bars + st, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 #pragma unroll
-      for (int st = 0; st < kI8Stages; ++st) {
-        const int64_t us = u0 + st * stride0;
-        if (us < units0) {
-          sb_mbar_expect_tx(bars + st, kI8UnitBytes);
-          sb_bulk_load(ring + st * kI8UnitBytes, p.xq + us * kI8UnitBytes, kI8UnitBytes, bars + st);
+        for (int st = 0; st < kI8Stages; ++st) {
+          const int64_t us = st ? u_nxt : u_cur;
+          if (us >= 0) {
+            sb_mbar_expect_tx(bars + st, kI8UnitBytes);
+            sb_bulk_load(ring + st * kI8UnitBytes, p.xq + us * kI8UnitBytes, kI8UnitBytes, bars + st);
+          }
         }
       }
     }
@@ -953,6 +1046,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     __syncthreads();
   }
 
+  scan_stamp(p, blockIdx.x, 0);
   // shadow sweeps with 32-entry lists: buffered selection (see WarpBufTop32); p.k == 32 there
   constexpr bool kBuffered = SH != 0 && KPL == 1;
   typename std::conditional<kBuffered, WarpBufTop32, WarpTopK<KPL>>::type top;
@@ -974,19 +1068,19 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       // into registers, re-arms the stage with the unit after next at once and only then does the arithmetic, so
       // both stages stay in flight during the dot products.  A unit is four row pairs, one row per half-warp.
       const int hl = lane & 15, half = lane >> 4;
-      const int64_t stride = (int64_t)gridDim.x * kScanWarps;
       const int64_t last = p.n - 1;
       unsigned char* ring = smem_raw + warp * (kI8Stages * kI8UnitBytes);
       uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kI8RingBytes) + warp * kI8Stages;
-      int64_t u = blockIdx.x + (int64_t)gridDim.x * warp;   // (the first two units were requested at the top)
+      // (u_cur and u_nxt were requested at the top; see UnitFeed for the order of the units)
       // scales of the rows in flight: lane i < 8 holds row i's of the current (sc_a) and the next unit (sc_b)
       float sc_a = 0.f, sc_b = 0.f;
       if (lane < kRowsPerUnit) {
-        if (u < units) sc_a = __ldg(p.xs + min(u * kRowsPerUnit + lane, last));
-        if (u + stride < units) sc_b = __ldg(p.xs + min((u + stride) * kRowsPerUnit + lane, last));
+        if (u_cur >= 0) sc_a = __ldg(p.xs + min(u_cur * kRowsPerUnit + lane, last));
+        if (u_nxt >= 0) sc_b = __ldg(p.xs + min(u_nxt * kRowsPerUnit + lane, last));
       }
       __syncwarp();
-      for (uint32_t it = 0; u < units; ++it, u += stride) {
+      for (uint32_t it = 0; u_cur >= 0; ++it) {
+        const int64_t u = u_cur;
         const uint32_t st = it & 1u;
         sb_mbar_wait(bars + st, (it >> 1) & 1u);
         const unsigned char* src = ring + st * kI8UnitBytes + half * 768 + hl * 16;
@@ -998,8 +1092,10 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
         const float sc_cur = sc_a * a1;
         sc_a = sc_b;
         __syncwarp();   // every lane has read the stage: it may be overwritten
-        const int64_t u2 = u + 2 * stride;
-        if (u2 < units) {
+        const int64_t u2 = feed.next(lane);
+        u_cur = u_nxt;
+        u_nxt = u2;
+        if (u2 >= 0) {
           if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             sb_mbar_expect_tx(bars + st, kI8UnitBytes);
@@ -1190,23 +1286,60 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     }
   }
 
+  scan_stamp(p, blockIdx.x, 1);
   // ---- block merge: 16 warps x 32 lanes x KPL slots -> sorted smem list ----
   constexpr int kBlockEntries = kScanThreads * KPL;  // power of two
-  if constexpr (kBuffered) top.flush(lane);
-  __syncthreads();
+  if constexpr (kBuffered) {
+    // the warps' lists are sorted across the lanes: a tournament of pairwise merges (better(A[i], B[31 - i]) is a
+    // bitonic sequence holding the 32 best of both; five exchange steps sort it) -- four barriers instead of the
+    // 45 of a 512-entry sorting network
+    top.flush(lane);
+    __syncthreads();   // every warp has left the sweep: the lists may overwrite the ring of bulk copies
+    float mk = top.key[0];
+    int mi = top.id[0];
 #pragma unroll
-  for (int s = 0; s < KPL; ++s) {
-    KeyId e;
-    bool live = (lane * KPL + s) < p.k;
-    e.key = live ? top.key[s] : -INFINITY;
-    e.id = live ? top.id[s] : kEmptyId;
-    s_list[tid * KPL + s] = e;
+    for (int stride = 1; stride < kScanWarps; stride <<= 1) {
+      const int role = warp & (2 * stride - 1);
+      if (role == stride) {
+        KeyId e;
+        e.key = mk;
+        e.id = mi;
+        s_list[warp * 32 + lane] = e;
+      }
+      __syncthreads();
+      if (role == 0) {
+        const KeyId o = s_list[(warp + stride) * 32 + (31 - lane)];
+        if (better(o.key, o.id, mk, mi)) {
+          mk = o.key;
+          mi = o.id;
+        }
+#pragma unroll
+        for (int x = 16; x > 0; x >>= 1) WarpBufTop32::exchange(mk, mi, lane, x, (lane & x) == 0);
+      }
+    }
+    if (warp == 0) {
+      KeyId e;
+      e.key = mk;
+      e.id = mi;
+      s_list[lane] = e;   // slot 0 was never a sender's
+    }
+    __syncthreads();
+  } else {
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < KPL; ++s) {
+      KeyId e;
+      bool live = (lane * KPL + s) < p.k;
+      e.key = live ? top.key[s] : -INFINITY;
+      e.id = live ? top.id[s] : kEmptyId;
+      s_list[tid * KPL + s] = e;
+    }
+    bitonic_sort_desc(s_list, kBlockEntries, tid, kScanThreads);
   }
-  bitonic_sort_desc(s_list, kBlockEntries, tid, kScanThreads);
   KeyId* my_part = p.part + ((int64_t)qi * gridDim.x + blockIdx.x) * p.k;
   for (int i = tid; i < p.k; i += kScanThreads) my_part[i] = s_list[i];
-  if (p.no_merge) return;
-  if constexpr (SH != 0) {
+  scan_stamp(p, blockIdx.x, 2);
+  if constexpr (SH != 0) if (!p.no_merge) {
     // Two-phase scan: every block re-scores ITS list in fp32 right away -- 148 blocks x one DRAM round trip in
     // parallel (and overlapping the blocks still sweeping) instead of the last block walking all candidates alone
     // (int8 tier: ~220 rows within 2 eps of the k-th score, seven dependent round trips = 10 us of a 135 us query).
@@ -1225,6 +1358,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   }
 
   // ---- grid merge by the last block -----------------------------------------
+  scan_stamp(p, blockIdx.x, 3);
   __threadfence();
   __syncthreads();
   if (tid == 0) {
@@ -1232,13 +1366,19 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     s_is_last = (t == gridDim.x - 1);
   }
   __syncthreads();
+  scan_stamp(p, blockIdx.x, 4);
   if (!s_is_last) return;
   __threadfence();
-  if (tid == 0) p.ticket[qi] = 0;  // ready for the next launch
+  if (tid == 0) {   // ready for the next launch
+    p.ticket[qi] = 0;
+    if (p.cursor != nullptr) p.cursor[qi] = 0;
+  }
+  if (p.no_merge) return;   // phase 1 timed alone: the lists are all that is wanted
 
   if constexpr (SH != 0) {
     // two-phase scan: prove + re-score in fp32 (or queue the query for the fp32 scan)
-    two_phase_finish<KPL>(p, qi, s_list, tid, eps);
+    const bool proven = two_phase_finish<KPL>(p, qi, s_list, tid, eps);
+    signal_done(p, tid, proven ? 0u : 1u);
     return;
   }
 
@@ -1270,6 +1410,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     first = false;
   }
   emit_topk<METRIC>(p, qi, s_list, tid, kScanThreads);
+  signal_done(p, tid, 0u);
 }
 
 // grid = (blocks, nq) scans query blockIdx.y; with p.qlist set, grid = (blocks, F) and

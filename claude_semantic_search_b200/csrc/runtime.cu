@@ -27,6 +27,7 @@ Options& options() {
     env("CSS_SCAN_LIST", o.scan_list);
     env("CSS_SCAN_ADAPTIVE", o.scan_adaptive);
     env("CSS_SCAN_PDL", o.scan_pdl);
+    env("CSS_SCAN_MAPPED", o.scan_mapped);
     return true;
   }();
   (void)init;
@@ -187,6 +188,7 @@ extern "C" int css_set_option(const char* name, int value) {
   else if (!strcmp(name, "scan_list")) slot = &o.scan_list;
   else if (!strcmp(name, "scan_adaptive")) slot = &o.scan_adaptive;
   else if (!strcmp(name, "scan_pdl")) slot = &o.scan_pdl;
+  else if (!strcmp(name, "scan_mapped")) slot = &o.scan_mapped;
   if (!slot) {
     css::set_error("unknown option %s", name);
     return CSS_ERR_INVALID;

@@ -514,6 +514,7 @@ int batched_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int n
     p.k_out = k;
     p.part = sc->part;
     p.ticket = sc->ticket;
+    p.cursor = sc->ticket + sc->max_nq;
     p.idmap = idmap;
     p.D = sp.D;
     p.I = sp.I;

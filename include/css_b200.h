@@ -336,6 +336,11 @@ int css_debug_attention(const float* qkv, const int32_t* cu_seqlens, int n_seq, 
 int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream);
 /*   scan_int8: the same for the first tier, the int8 shadow sweep (768 + 4 bytes per 768-d row). */
 int css_debug_scan_int8(css_index* h, const float* q_dev, int nq, void* stream);
+/*   scan_trace: one batch-1 scan (current tier, top-k) with a timeline: out_host receives (scan blocks + 1) x 8
+ *              %globaltimer stamps (ns) -- row b = block b {start, sweep done, block list merged, list re-scored,
+ *              ticket drawn}, last row = the finishing block {lists loaded, threshold found, candidates gathered,
+ *              ordered, emitted}; unused slots are 0.  Profiling aid (scripts/scan_trace.py). */
+int css_debug_scan_trace(css_index* h, const float* q_dev, int k, int64_t* out_host, int n_out, void* stream);
 
 /* Process-wide switches (also read from the environment at load: CSS_SCAN_BF16, CSS_SCAN_INT8, CSS_SCAN_INTERLEAVE,
  * CSS_SCAN_LIST, CSS_SCAN_ADAPTIVE): "scan_bf16" 1 = two-phase batch-1 scan, 0 = single fp32 sweep;
