@@ -823,6 +823,7 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (rank_among(s, nsel, e) == k - 1) s_t = e.key;
   }
   __syncthreads();
+  scan_stamp(p, gridDim.x, 5);
   const float t0 = s_t;
   // (B) tighten: the k-th best over all entries >= t0 (there are at least k of them)
   if (t0 > -INFINITY) {
@@ -866,15 +867,15 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   __syncthreads();
   scan_stamp(p, gridDim.x, 2);
   const int keep = s_cnt;
-  if (tid == 0) {
-    const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
-    if (p.stats_host) p.stats_host[0] = nq_seen;
-  }
   if (s_unproven || keep > kRescoreCap) {
     if (tid == 0) {
       p.ovf_list[atomicAdd(p.ovf_count, 1)] = qi;
+      const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
       const unsigned nu = atomicAdd(p.stats_dev + 1, 1u) + 1u;
-      if (p.stats_host) p.stats_host[1] = nu;
+      if (p.stats_host) {
+        p.stats_host[0] = nq_seen;
+        p.stats_host[1] = nu;
+      }
     }
     return false;
   }
@@ -884,10 +885,24 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   KeyId* out = s;
   if (keep <= kRankSortMax) {
     out = s + kRescoreCap;
-    for (int i = tid; i < keep; i += kScanThreads) {
-      const KeyId e = s[i];
-      out[rank_among(s, keep, e)] = e;
+    if (keep <= kScanThreads / 2) {
+      // two threads per candidate, each counting over half of the list
+      const int i = tid >> 1, h0 = (tid & 1) * (keep >> 1), h1 = (tid & 1) ? keep : (keep >> 1);
+      KeyId e;
+      e.key = 0.f;
+      e.id = 0;
+      if (i < keep) e = s[i];
+      int rank = i < keep ? rank_among(s + h0, h1 - h0, e) : 0;
+      rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+      if (i < keep && (tid & 1) == 0 && rank < k) out[rank] = e;
+    } else {
+      for (int i = tid; i < keep; i += kScanThreads) {
+        const KeyId e = s[i];
+        const int rank = rank_among(s, keep, e);
+        if (rank < k) out[rank] = e;
+      }
     }
+    scan_stamp(p, gridDim.x, 6);
     for (int i = keep + tid; i < k; i += kScanThreads) {
       out[i].key = -INFINITY;
       out[i].id = kEmptyId;
@@ -1379,6 +1394,10 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     // two-phase scan: prove + re-score in fp32 (or queue the query for the fp32 scan)
     const bool proven = two_phase_finish<KPL>(p, qi, s_list, tid, eps);
     signal_done(p, tid, proven ? 0u : 1u);
+    if (proven && tid == 0) {   // counters last: their round trip to L2 is not part of the query
+      const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
+      if (p.stats_host) p.stats_host[0] = nq_seen;
+    }
     return;
   }
 

@@ -31,8 +31,8 @@ for rep in range(6):
     for name, col in (("start", 0), ("sweep done", 1), ("list merged", 2), ("re-scored", 3), ("ticket", 4)):
         v = us(blk[:, col])
         print(f"  blocks {name:12s} min {v.min():8.2f}  median {np.median(v):8.2f}  max {v.max():8.2f}")
-    names = ["lists loaded", "threshold", "candidates", "ordered", "emitted"]
-    for i, nme in enumerate(names):
+    names = {0: "lists requested", 5: "t0 from heads", 1: "threshold", 2: "candidates", 6: "rank-sorted", 3: "ordered", 4: "emitted"}
+    for i in (0, 5, 1, 2, 6, 3, 4):
         if fin[i]:
-            print(f"  last block {nme:13s} {us(fin[i]):8.2f}")
+            print(f"  last block {names[i]:16s} {us(fin[i]):8.2f}")
 idx.close()
