@@ -52,7 +52,7 @@ def unit_for(rows: int) -> str:
 # DRAM traffic per launch from the committed ncu --set full captures, keyed by rows per GPU
 NCU_SCAN_TRAFFIC = {1_000_000: 3_072_071_000 + 4_015_872}       # fp32 sweep (profiles/r1_ncu_kernels_summary.txt)
 NCU_SCAN_TRAFFIC_BF16 = {1_000_000: 1_536_171_000 + 7_699_456}  # bf16 sweep incl. its last-CTA finish (profiles/r2_scan_two_phase_ncu_summary.txt)
-NCU_SCAN_TRAFFIC_INT8 = {}                                       # int8 sweep incl. its last-CTA finish (profiles/r2_scan_int8_ncu_summary.txt)
+NCU_SCAN_TRAFFIC_INT8 = {1_000_000: 786_737_152 + 6_053_632}     # int8 sweep incl. block re-scores + last-CTA finish (profiles/r2_scan_int8_ncu_summary.txt)
 INT8_ROW_BYTES = D + 4                                           # 768 codes + the row's fp32 scale
 
 

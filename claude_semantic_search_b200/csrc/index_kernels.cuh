@@ -656,8 +656,8 @@ __device__ __forceinline__ void await_and_merge(const ScanParams& p, const int q
 }
 
 // Timeline of one query for css_debug_scan_trace: row b = block b {0 start, 1 sweep done, 2 block list merged,
-// 3 list re-scored, 4 ticket drawn}; row gridDim.x = the last block {0 lists loaded, 1 t found, 2 candidates
-// gathered, 3 ordered, 4 emitted}.  Thread 0 only; ns of %globaltimer.
+// 3 list re-scored, 4 ticket drawn}; row gridDim.x = the last block {0 lists requested, 4 result emitted}.
+// Thread 0 only; ns of %globaltimer.
 __device__ __forceinline__ void scan_stamp(const ScanParams& p, const int row, const int slot) {
   if (p.trace != nullptr && threadIdx.x == 0) p.trace[row * 8 + slot] = (long long)global_timer_ns();
 }
@@ -823,7 +823,6 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (rank_among(s, nsel, e) == k - 1) s_t = e.key;
   }
   __syncthreads();
-  scan_stamp(p, gridDim.x, 5);
   const float t0 = s_t;
   // (B) tighten: the k-th best over all entries >= t0 (there are at least k of them)
   if (t0 > -INFINITY) {
@@ -846,7 +845,6 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (tid == 0) s_cnt = 0;
   }
   __syncthreads();
-  scan_stamp(p, gridDim.x, 1);
   // eps: the tier's bound on |approximate score - exact score| (see scan_one_query); a bound that is not finite
   // (non-finite query or stored row) proves nothing
   const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
@@ -865,7 +863,6 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     }
   }
   __syncthreads();
-  scan_stamp(p, gridDim.x, 2);
   const int keep = s_cnt;
   if (s_unproven || keep > kRescoreCap) {
     if (tid == 0) {
@@ -885,16 +882,34 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   KeyId* out = s;
   if (keep <= kRankSortMax) {
     out = s + kRescoreCap;
-    if (keep <= kScanThreads / 2) {
-      // two threads per candidate, each counting over half of the list
-      const int i = tid >> 1, h0 = (tid & 1) * (keep >> 1), h1 = (tid & 1) ? keep : (keep >> 1);
+    if (keep <= kScanThreads) {
+      // Every warp sorts 32 candidates across its lanes (bitonic network of shuffles) and hands its best k to a
+      // final rank count over at most 16 k entries: ~1 us.  Rank counting over all ~250 candidates of an int8-tier
+      // query is 60 k comparisons on one SM: 4.5 us.
+      const int lane = tid & 31, warp = tid >> 5;
       KeyId e;
-      e.key = 0.f;
-      e.id = 0;
-      if (i < keep) e = s[i];
-      int rank = i < keep ? rank_among(s + h0, h1 - h0, e) : 0;
-      rank += __shfl_xor_sync(0xffffffffu, rank, 1);
-      if (i < keep && (tid & 1) == 0 && rank < k) out[rank] = e;
+      e.key = -INFINITY;
+      e.id = kEmptyId;
+      if (tid < keep) e = s[tid];
+#pragma unroll
+      for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int o = size >> 1; o > 0; o >>= 1) {
+          const bool desc = (lane & size) == 0 || size == 32;
+          WarpBufTop32::exchange(e.key, e.id, lane, o, ((lane & o) == 0) == desc);
+        }
+      }
+      KeyId* best = s + kRescoreCap + 1024;   // [warps with candidates][k]
+      const int nw = (keep + 31) >> 5;
+      if (warp < nw && lane < k) best[warp * k + lane] = e;
+      __syncthreads();
+      const int nbest = nw * k;
+      for (int i = tid; i < nbest; i += kScanThreads) {
+        const KeyId c = best[i];
+        if (c.id == kEmptyId) continue;
+        const int rank = rank_among(best, nbest, c);
+        if (rank < k) out[rank] = c;
+      }
     } else {
       for (int i = tid; i < keep; i += kScanThreads) {
         const KeyId e = s[i];
@@ -902,7 +917,6 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
         if (rank < k) out[rank] = e;
       }
     }
-    scan_stamp(p, gridDim.x, 6);
     for (int i = keep + tid; i < k; i += kScanThreads) {
       out[i].key = -INFINITY;
       out[i].id = kEmptyId;
@@ -924,60 +938,69 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (tid < k) s[tid] = e;
     __syncthreads();
   }
-  scan_stamp(p, gridDim.x, 3);
   emit_topk<CSS_METRIC_INNER_PRODUCT>(p, qi, s, tid, kScanThreads);
   scan_stamp(p, gridDim.x, 4);
   return true;
 }
 
-// Units of the dense int8 sweep for one warp.  The first three quarters of the warp's share are dealt statically,
-// block-cyclically (round r: unit r * nwarps + gw) -- neighbouring rows land in different blocks, and the addresses
-// are known two units ahead without any traffic.  The rest of the corpus is handed out in pairs of units from a
-// per-query cursor: blocks do not stream at the same rate (sweep ends spread over 88 .. 110 us of a 1 M-row query
-// when every warp gets the same share; SMs further from the memory partitions they read see more latency per bulk
-// copy), so the fast warps take what the slow ones have not reached.  The cursor value is fetched one pair ahead
-// (lane 0's `raw`), its latency never waited for.
+// Units of the dense int8 sweep for one warp.  Most of the warp's share is dealt statically, block-cyclically
+// (round r: unit r * nwarps + gw) -- neighbouring rows land in different blocks, and the addresses are known two
+// units ahead without any traffic.  The last eighth of the corpus (+ two rounds) is handed out from a per-query
+// cursor: blocks do not stream at the same rate (sweep ends spread over 88 .. 110 us of a 1 M-row query when every
+// warp gets the same share; SMs further from the memory partitions they read see more latency per bulk copy), so
+// the fast warps take what the slow ones have not reached.  A ticket is worth four consecutive units, the tickets
+// of the last two rounds one unit each (coarse tickets keep the single-address atomic rate at a quarter of the unit
+// rate -- pairs of units on every ticket made a 4 M-row sweep 15 % slower --, fine ones let the warps finish
+// within a unit of each other).  The cursor value is fetched one ticket ahead (lane 0's `raw`), its latency never
+// waited for.
 struct UnitFeed {
-  int64_t units, nwarps, gw, stat_rounds, stat_units;
-  int64_t r;           // next static round
-  int64_t dyn_second;  // second unit of the pair in hand, -1: none
+  int units, nwarps, gw, stat_rounds, stat_units, a_tickets, a_units;
+  int r;           // next static round
+  int cur;         // next unit of the ticket in hand
+  int left;            // units left of the ticket in hand
   unsigned raw;        // lane 0: the cursor value fetched ahead
   unsigned* cursor;
   bool done;
 
-  __device__ __forceinline__ void init(const ScanParams& p, const int qi, const int64_t units_, const int64_t nwarps_,
-                                       const int64_t gw_, const int lane) {
+  __device__ __forceinline__ void init(const ScanParams& p, const int qi, const int units_, const int nwarps_,
+                                       const int gw_, const int lane) {
     units = units_;
     nwarps = nwarps_;
     gw = gw_;
-    const int64_t per_warp = units / nwarps;
-    stat_rounds = per_warp - per_warp / 4;
+    const int per_warp = units / nwarps;
+    const int dyn_rounds = per_warp / 8 + 2;
+    stat_rounds = per_warp > dyn_rounds ? per_warp - dyn_rounds : 0;
     stat_units = stat_rounds * nwarps;
+    const int dyn_units = units - stat_units;
+    const int b_units = dyn_units < 2 * nwarps ? dyn_units : 2 * nwarps;
+    a_tickets = (dyn_units - b_units) / 4;
+    a_units = a_tickets * 4;
     r = 0;
-    dyn_second = -1;
+    cur = 0;
+    left = 0;
     cursor = p.cursor + qi;
     done = false;
     raw = 0;
     if (lane == 0) raw = atomicAdd(cursor, 1u);
   }
   // Next unit of this warp, -1 when the corpus is exhausted.  Warp-uniform.
-  __device__ __forceinline__ int64_t next(const int lane) {
+  __device__ __forceinline__ int next(const int lane) {
     if (r < stat_rounds) return (r++) * nwarps + gw;
-    if (done) return -1;
-    if (dyn_second >= 0) {
-      const int64_t u = dyn_second;
-      dyn_second = -1;
-      if (u < units) return u;
-      done = true;
-      return -1;
+    if (left > 0) {
+      --left;
+      return cur++;
     }
-    const int64_t base = stat_units + 2 * (int64_t)__shfl_sync(0xffffffffu, raw, 0);
+    if (done) return -1;
+    const int t = (int)__shfl_sync(0xffffffffu, raw, 0);
+    const int base = t < a_tickets ? stat_units + 4 * t : stat_units + a_units + (t - a_tickets);
     if (base >= units) {
       done = true;
       return -1;
     }
     if (lane == 0) raw = atomicAdd(cursor, 1u);
-    dyn_second = base + 1;
+    const int cnt = t < a_tickets ? 4 : 1;
+    left = (cnt < units - base ? cnt : units - base) - 1;
+    cur = base + 1;
     return base;
   }
 };
@@ -1013,8 +1036,9 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
     if (p.mask == nullptr) {
       // dense sweep (below): the warp's first two units are requested before anything else, the query is
       // quantised while they are on their way
-      const int64_t units0 = (p.n + kRowsPerUnit - 1) / kRowsPerUnit;
-      feed.init(p, qi, units0, (int64_t)gridDim.x * kScanWarps, blockIdx.x + (int64_t)gridDim.x * warp, lane);
+      // (a shard holds fewer than 2^31 rows: unit indices fit 32 bits)
+      const int units0 = (int)((p.n + kRowsPerUnit - 1) / kRowsPerUnit);
+      feed.init(p, qi, units0, (int)gridDim.x * kScanWarps, (int)blockIdx.x + (int)gridDim.x * warp, lane);
       u_cur = feed.next(lane);
       u_nxt = feed.next(lane);
       if (lane == 0) {

@@ -338,8 +338,8 @@ int css_debug_scan_bf16(css_index* h, const float* q_dev, int nq, void* stream);
 int css_debug_scan_int8(css_index* h, const float* q_dev, int nq, void* stream);
 /*   scan_trace: one batch-1 scan (current tier, top-k) with a timeline: out_host receives (scan blocks + 1) x 8
  *              %globaltimer stamps (ns) -- row b = block b {start, sweep done, block list merged, list re-scored,
- *              ticket drawn}, last row = the finishing block {lists loaded, threshold found, candidates gathered,
- *              ordered, emitted}; unused slots are 0.  Profiling aid (scripts/scan_trace.py). */
+ *              ticket drawn}, last row = the finishing block {slot 0: lists requested, slot 4: result emitted};
+ *              unused slots are 0.  Profiling aid (scripts/scan_trace.py). */
 int css_debug_scan_trace(css_index* h, const float* q_dev, int k, int64_t* out_host, int n_out, void* stream);
 
 /* Process-wide switches (also read from the environment at load: CSS_SCAN_BF16, CSS_SCAN_INT8, CSS_SCAN_INTERLEAVE,
