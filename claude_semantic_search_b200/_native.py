@@ -6,6 +6,7 @@ present when a compute entry point is called, a NativeError is raised.
 from __future__ import annotations
 
 import ctypes
+import threading
 import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 from pathlib import Path
@@ -325,6 +326,7 @@ class Index:
         self.metric = metric
         self.device = device
         self.devices = [int(d) for d in devices] if devices else [device]
+        self._tl = threading.local()   # per-thread result buffers of single-query searches
 
     # -- lifecycle --------------------------------------------------------
     def close(self) -> None:
@@ -422,6 +424,16 @@ class Index:
         nq = q.shape[0]
         if k > MAX_K:
             return self._search_large_k(q, k, flt)
+        if nq == 1 and flt is None:
+            # the single-query call is ~150 us on the device side: keep the result buffers and their addresses per
+            # thread instead of paying numpy.empty + ndarray.ctypes (1 us each) on every call
+            tl = self._tl
+            ent = tl.__dict__.get(k)
+            if ent is None:
+                D0, I0 = np.empty((1, k), np.float32), np.empty((1, k), np.int64)
+                ent = tl.__dict__[k] = (D0, I0, D0.ctypes.data, I0.ctypes.data)
+            check(self._lib.css_index_search(self._h, q.ctypes.data, 1, k, None, ent[2], ent[3]))
+            return ent[0].copy(), ent[1].copy()
         D = np.empty((nq, k), np.float32)
         I = np.empty((nq, k), np.int64)
         cf = flt.build() if flt is not None else None
