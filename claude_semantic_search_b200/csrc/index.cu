@@ -312,7 +312,7 @@ int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, in
   CSS_CHECK(build_filter_params(h, f, &fp, st, pinned_front));
   if (n_pass) CSS_CUDA(cudaMemsetAsync(h->n_pass_dev, 0, sizeof(unsigned long long), st));
   else fp.n_pass = nullptr;
-  int64_t blocks = (h->ntotal + 255) / 256;
+  int64_t blocks = (h->ntotal + 1023) / 1024;   // four rows per thread
   filter_mask_kernel<<<(unsigned)blocks, 256, 0, st>>>(fp);
   CSS_LAUNCHED();
   *mask_out = h->mask;
