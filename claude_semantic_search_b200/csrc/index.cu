@@ -293,6 +293,11 @@ int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, in
     if (n_pass) *n_pass = h->ntotal;
     return CSS_OK;
   }
+  // no clauses, rows deleted: the alive bits ARE the mask (no evaluation: 27 us per query on a 1 M-row index)
+  if ((!f || (f->n_clauses == 0 && !f->row_mask)) && !ignore_alive && !need_count && h->ntotal > 0) {
+    *mask_out = h->alive;
+    return CSS_OK;
+  }
   if (h->ntotal == 0) {
     *mask_out = h->mask;
     if (n_pass) *n_pass = 0;
@@ -462,6 +467,7 @@ static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev,
   p.no_merge = no_merge;
   p.interleave = interleave;
   p.zero_on_entry = sc->ovf_count;
+  p.mask_dense = (mask_dev != nullptr && mask_dev == h->alive) ? 1 : 0;   // deletions only: sweep every row, drop the dead
   const size_t smem = sizeof(KeyId) * kMergeCap;
   const dim3 grid((unsigned)h->scan_blocks, (unsigned)nq);
   if (tier == 2) {
