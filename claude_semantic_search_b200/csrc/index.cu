@@ -473,6 +473,8 @@ static int launch_phase1(css_index* h, css_scan_scratch* sc, const float* q_dev,
   if (tier == 2) {
     CSS_REQUIRE(h->xq != nullptr, "this index has no int8 shadow copy");
     const size_t smem8 = std::max(smem, (size_t)kI8SmemBytes);   // the sweep's ring of bulk copies; the lists alias it
+    if (mask_dev != nullptr && !p.mask_dense)   // filtered: the gather instantiation
+      return kp == 32 ? launch_phase1_as<1, 3>(p, grid, smem8, st) : launch_phase1_as<2, 3>(p, grid, smem8, st);
     return kp == 32 ? launch_phase1_as<1, 2>(p, grid, smem8, st) : launch_phase1_as<2, 2>(p, grid, smem8, st);
   }
   return kp == 32 ? launch_phase1_as<1, 1>(p, grid, smem, st) : launch_phase1_as<2, 1>(p, grid, smem, st);
@@ -598,6 +600,8 @@ static int preload_index_kernels(int dim) {
   CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, 1>, smem));
   CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, 2>, std::max(smem, (size_t)kI8SmemBytes)));
   CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, 2>, std::max(smem, (size_t)kI8SmemBytes)));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<1, CSS_METRIC_INNER_PRODUCT, true, 3>, std::max(smem, (size_t)kI8SmemBytes)));
+  CSS_CHECK(preload_kernel(scan_topk_kernel<2, CSS_METRIC_INNER_PRODUCT, true, 3>, std::max(smem, (size_t)kI8SmemBytes)));
   CSS_CHECK(preload_kernel(filter_mask_kernel, 0));
   CSS_CHECK(preload_kernel(append_rows_kernel, 0));
   CSS_CHECK(preload_kernel(set_bits_kernel, 0));

@@ -1013,14 +1013,18 @@ struct UnitFeed {
 template <int KPL, int METRIC, bool D768, int SH = 0>
 __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi) {
   static_assert(SH == 0 || (D768 && METRIC == CSS_METRIC_INNER_PRODUCT), "shadow phase: inner product, d = 768");
+  static_assert(SH >= 0 && SH <= 3, "tier");
+  // SH = 2: int8 tier, dense sweep (no mask, or the alive bits alone); SH = 3: int8 tier, filtered sweep (gather).
+  // Two instantiations: the gather code in the dense kernel cost the dense sweep 2 % (register allocation).
   constexpr bool BF16 = SH == 1;
-  constexpr bool I8 = SH == 2;
+  constexpr bool I8 = SH == 2 || SH == 3;
+  constexpr bool I8_GATHER = SH == 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   KeyId* s_list = reinterpret_cast<KeyId*>(smem_raw);  // kMergeCap entries
   float* q_s = reinterpret_cast<float*>(smem_raw + sizeof(KeyId) * kMergeCap);  // d floats (generic path)
   __shared__ int s_is_last;
   // filtered scan: selected rows of a window (int8 tier: of a round of windows, see the masked sweep below)
-  __shared__ unsigned short s_rows[kScanWarps][(SH == 2 ? 64 : 32) * kRowsPerUnit];
+  __shared__ unsigned short s_rows[kScanWarps][(SH == 3 ? 64 : 32) * kRowsPerUnit];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -1035,7 +1039,7 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   UnitFeed feed;          // int8 tier, dense sweep: the warp's units
   int64_t u_cur = -1, u_nxt = -1;
   if constexpr (I8) {
-    if (p.mask == nullptr || p.mask_dense) {
+    if constexpr (!I8_GATHER) {
       // dense sweep (below): the warp's first two units are requested before anything else, the query is
       // quantised while they are on their way
       // (a shard holds fewer than 2^31 rows: unit indices fit 32 bits)
@@ -1101,8 +1105,8 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
   const unsigned char* mask8 = reinterpret_cast<const unsigned char*>(p.mask);
 
   bool swept = false;
-  if constexpr (I8) {
-    if (mask8 == nullptr || p.mask_dense) {
+  if constexpr (I8 && !I8_GATHER) {
+    {
       // Dense sweep, 8-row units dealt block-cyclically (see the bf16 sweep below).  (With the alive bits as the
       // only mask -- an index rows were deleted from -- every row is still streamed and the dead ones are dropped
       // after scoring: gathering the 99.99 % live rows instead costs 15 % more.)  A unit is 6 KB of contiguous
@@ -1195,8 +1199,8 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       swept = true;
     }
   }
-  if constexpr (I8) {
-    if (mask8 != nullptr && !p.mask_dense) {
+  if constexpr (I8_GATHER) {
+    {
       // Filtered sweep.  The warp walks its contiguous range of units in rounds: it compacts the selected rows of
       // as many 256-row windows as it takes to collect ~256 rows (their offsets from the round's first row, 16 bits
       // each), then scores them eight at a time through the warp's two-stage ring in shared memory: a stage is
@@ -1375,21 +1379,6 @@ __device__ __forceinline__ void scan_one_query(const ScanParams& p, const int qi
       }
       __syncwarp();
       const int64_t base = ub * kRowsPerUnit;
-      if constexpr (I8) {
-        for (int g0 = 0; g0 < total; g0 += kRowsPerUnit) {
-          int64_t r[kRowsPerUnit];
-#pragma unroll
-          for (int i = 0; i < kRowsPerUnit; ++i) r[i] = base + s_rows[warp][min(g0 + i, total - 1)];
-          float acc[kRowsPerUnit];
-          score_rows_i8(p, q1c, q2c, a1, r, lane, acc);
-#pragma unroll
-          for (int i = 0; i < kRowsPerUnit; ++i)
-            if (g0 + i < total) top.consider(acc[i], (int)r[i], lane);
-          top.maybe_compact(lane);
-        }
-        __syncwarp();
-        continue;
-      }
       if constexpr (BF16) {
         for (int g0 = 0; g0 < total; g0 += kRowsPerUnit) {
           int64_t r[kRowsPerUnit];
