@@ -567,7 +567,7 @@ def main():
             "e2e": {"value": e2e_qps * world, "unit": UNIT, "h2d_bytes_per_step": D * 4, "d2h_bytes_per_step": K * 12,
                     "qps": e2e_qps,
                     "api": "css_index_search (host q -> host D,I)" if world == 1 else
-                           "ShardedSearch.search_host: pinned H2D, css_index_search_exchange_device, one packed pinned D2H"},
+                           "ShardedSearch.search_host -> css_index_search_exchange (host q -> host D,I on every rank; result through mapped memory, in-kernel exchange)"},
             "gpu_launches": int(n_launch), "launches_per_step": launches_per_step,
             "clocks": clocks, "extra": extra,
         }

@@ -137,6 +137,7 @@ SIGNATURES = {
     "css_encoder_max_tokens": (c_int64, [c_void_p]),
     "css_encoder_max_seq_len": (c_int, [c_void_p]),
     "css_encoder_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int, c_void_p]),
+    "css_index_search_exchange": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "css_debug_scan_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "css_debug_scan_int8": (c_int, [c_void_p, c_void_p, c_int, c_void_p]),
     "css_debug_scan_trace": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
@@ -491,6 +492,15 @@ class Index:
         check(self._lib.css_index_search_exchange_device(self._h, ex._h, c_void_p(q_ptr), nq, k,
                                                          c_void_p(mask_ptr) if mask_ptr else None, id_offset,
                                                          c_void_p(D_ptr), c_void_p(I_ptr), c_void_p(stream)))
+
+    def search_exchange_host(self, ex: "Exchange", q: np.ndarray, k: int, id_offset: int = 0, mask_ptr: int = 0) -> tuple:
+        """One query in host memory, searched collectively over the ranks of `ex` (css_index_search_exchange)."""
+        q = _f32(q).reshape(-1)
+        D = np.empty((1, k), np.float32)
+        I = np.empty((1, k), np.int64)
+        check(self._lib.css_index_search_exchange(self._h, ex._h, q.ctypes.data, k, c_void_p(mask_ptr), id_offset,
+                                                  D.ctypes.data, I.ctypes.data))
+        return D, I
 
     def debug_scan_bf16(self, q_ptr: int, nq: int, stream: int = 0) -> None:
         """Phase 1 alone of the two-phase scan (benchmark hook, css_debug_scan_bf16)."""

@@ -1115,6 +1115,8 @@ int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float
                      /*defer_fallback=*/false, nullptr);
 }
 
+static int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out);
+
 int css_index_search(css_index* h, const float* q_host, int nq, int k, const css_filter* filter,
                      float* D_host, int64_t* I_host) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
@@ -1169,26 +1171,7 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
     sc->done_flag = nullptr;
     CSS_CHECK(rc);
     unsigned seen = 0;
-    for (unsigned spins = 1;; ++spins) {
-      seen = *flag;
-      if ((seen >> 1) == seq) break;
-      if ((spins & 1023u) == 0u) {
-        // a failed kernel never raises the flag; a finished stream means the result (and the flag) are in place
-        const cudaError_t qe = cudaStreamQuery(st);
-        if (qe == cudaSuccess) {
-          seen = *flag;
-          break;
-        }
-        if (qe != cudaErrorNotReady) {
-          set_error("search kernel failed: %s", cudaGetErrorString(qe));
-          return CSS_ERR_CUDA;
-        }
-      }
-    }
-    if ((seen >> 1) != seq) {
-      set_error("search kernel finished without signalling its result");
-      return CSS_ERR_CUDA;
-    }
+    CSS_CHECK(await_done_flag(flag, seq, st, &seen));
     if (seen & 1u) {
       // not proven from the shadow lists: the fp32 scan answers (into the same mapped block)
       CSS_CHECK(scan_fallback(h, sc, sc->q_dev, 1, k, m, index_idmap(h, 0), nullptr, reinterpret_cast<float*>(pdev + d_off),
@@ -1211,6 +1194,83 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
     // some queries could not be proven from the bf16 lists: the fp32 scan answers exactly those
     CSS_CHECK(scan_fallback(h, sc, sc->q_dev, nq, k, m, index_idmap(h, 0), nullptr, sc->D_dev, I_dev, st, /*pdl_ok=*/false));
     CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, (i_off - d_off) + ibytes, cudaMemcpyDeviceToHost, st));
+    CSS_CUDA(cudaStreamSynchronize(st));
+  }
+  memcpy(D_host, pin + d_off, dbytes);
+  memcpy(I_host, pin + i_off, ibytes);
+  return CSS_OK;
+}
+
+// Poll the completion flag of a single-query launch (see css_index_search).  *seen_out: the flag value.
+static int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out) {
+  unsigned seen = 0;
+  for (unsigned spins = 1;; ++spins) {
+    seen = *flag;
+    if ((seen >> 1) == seq) break;
+    if ((spins & 1023u) == 0u) {
+      // a failed kernel never raises the flag; a finished stream means the result (and the flag) are in place
+      const cudaError_t qe = cudaStreamQuery(st);
+      if (qe == cudaSuccess) {
+        seen = *flag;
+        break;
+      }
+      if (qe != cudaErrorNotReady) {
+        set_error("search kernel failed: %s", cudaGetErrorString(qe));
+        return CSS_ERR_CUDA;
+      }
+    }
+  }
+  if ((seen >> 1) != seq) {
+    set_error("search kernel finished without signalling its result");
+    return CSS_ERR_CUDA;
+  }
+  *seen_out = seen;
+  return CSS_OK;
+}
+
+int css_index_search_exchange(css_index* h, css_exchange* ex, const float* q_host, int k, const uint32_t* mask_dev,
+                              int64_t id_offset, float* D_host, int64_t* I_host) {
+  CSS_REQUIRE(h != nullptr && ex != nullptr, "NULL handle");
+  CSS_REQUIRE(!CSS_IS_COMPOSITE(h), "css_index_search_exchange: single-device indexes only");
+  CSS_REQUIRE(q_host && D_host && I_host, "NULL host buffer");
+  CSS_REQUIRE(k >= 1 && k <= CSS_MAX_K, "k=%d outside [1, %d]", k, CSS_MAX_K);
+  CSS_REQUIRE(ex->connected && ex->device == h->device, "exchange not connected / on another device");
+  std::lock_guard<std::mutex> lk(h->mu);
+  CSS_CHECK(ensure_device(h->device));
+  DeviceGuard g(h->device);
+  cudaStream_t st = h->stream;
+  const size_t qbytes = (size_t)h->dim * 4, dbytes = (size_t)k * 4, ibytes = (size_t)k * 8;
+  css_scan_scratch* sc = nullptr;
+  CSS_CHECK(get_scratch(h, st, 1, &sc));
+  const size_t front = (qbytes + dbytes + ibytes + 128 + 63) / 64 * 64;
+  CSS_CHECK(ensure_pinned(h, front));
+  CSS_REQUIRE(h->pinned_dev != nullptr, "no mapped view of the pinned staging block");
+  unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
+  unsigned char* pdev = reinterpret_cast<unsigned char*>(h->pinned_dev);
+  const size_t d_off = (qbytes + 15) / 16 * 16, i_off = (d_off + dbytes + 15) / 16 * 16, c_off = (i_off + ibytes + 15) / 16 * 16;
+  memcpy(pin, q_host, qbytes);
+  CSS_CUDA(cudaMemcpyAsync(sc->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
+  ExchangeDev xd;
+  CSS_CHECK(exchange_next(ex, &xd));
+  xd.deferred = 0;
+  xd.nq = 1;
+  const uint32_t* m = mask_dev;
+  if (!m && h->any_dead) m = h->alive;
+  volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(pin + c_off);
+  const unsigned seq = (++h->call_seq) & 0x3fffffffu;
+  *flag = 0u;
+  sc->done_flag = reinterpret_cast<unsigned*>(pdev + c_off);
+  sc->done_seq = seq;
+  float* Dm = reinterpret_cast<float*>(pdev + d_off);
+  int64_t* Im = reinterpret_cast<int64_t*>(pdev + i_off);
+  const int rc = scan_search(h, sc, sc->q_dev, 1, k, m, index_idmap(h, id_offset), &xd, Dm, Im, st, /*defer_fallback=*/true, nullptr);
+  sc->done_flag = nullptr;
+  CSS_CHECK(rc);
+  unsigned seen = 0;
+  CSS_CHECK(await_done_flag(flag, seq, st, &seen));
+  if (seen & 1u) {
+    // not proven from the shadow lists: the fp32 scan answers, publishes this rank's list and merges
+    CSS_CHECK(scan_fallback(h, sc, sc->q_dev, 1, k, m, index_idmap(h, id_offset), &xd, Dm, Im, st, /*pdl_ok=*/false));
     CSS_CUDA(cudaStreamSynchronize(st));
   }
   memcpy(D_host, pin + d_off, dbytes);

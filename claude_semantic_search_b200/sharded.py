@@ -133,6 +133,9 @@ class ShardedSearch:
             # one pinned block per (nq, k): query in, [scores | ids] out -- one H2D, one D2H, one sync
             dev = torch.device("cuda", self.index.device)
             nq = q.shape[0]
+            if nq == 1 and self.use_exchange:
+                # single query: staged, searched, exchanged and returned through mapped host memory inside the library
+                return self.index.search_exchange_host(self._exchange(), q, k, self.id_offset)
             key = (nq, k, q.shape[1])
             b = self._device_bufs(torch, dev, nq, k)
             if key not in self._pin:

@@ -194,6 +194,13 @@ int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float
                                      const uint32_t* mask_dev, int64_t id_offset, float* D_dev,
                                      int64_t* I_dev, void* stream);
 
+/* The same for ONE query in host memory (collective over the ranks like the call above): the query is staged
+ * through the handle's pinned block, the merged top-k comes back through mapped host memory with a completion
+ * flag the call polls -- no D2H copy, no stream synchronisation.  mask_dev: optional device row mask of this
+ * shard.  Runs on the handle's own stream. */
+int css_index_search_exchange(css_index* h, css_exchange* ex, const float* q_host, int k,
+                              const uint32_t* mask_dev, int64_t id_offset, float* D_host, int64_t* I_host);
+
 /* Counters of the two-phase batch-1 scan since the index was created: out = {queries answered by it,
  * queries it could not prove from the shadow-row lists (re-run by the fp32 sweep), 1 if the adaptive switch
  * currently bypasses a tier, largest ||x - bf16(x)|| of a stored row x 1e9, largest ||x - scale * int8(x)||

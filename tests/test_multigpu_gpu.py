@@ -41,6 +41,11 @@ for name, (D, I, sl) in {"scan": (D1, I1, slice(0, 3)), "batched": (Db, Ib, slic
     assert ok, f"rank {rank} {name}: {why}"
 ok, why = so.compare_topk(Dr[:3], Ir[:3], Dh, Ih)
 assert ok, f"rank {rank} host: {why}"
+# single query in host memory: css_index_search_exchange (mapped result + completion flag, in-kernel exchange)
+for i in range(5):
+    D1h, I1h = ss.search_host(q[i:i + 1], k)
+    ok, why = so.compare_topk(Dr[i:i + 1], Ir[i:i + 1], D1h, I1h)
+    assert ok, f"rank {rank} host single query {i}: {why}"
 assert I1.cpu().numpy()[0][:2].tolist() == [1, n - 3]
 # NCCL exchange (all-gather + merge kernel) of the same scan: identical result
 ss_nccl = ShardedSearch(idx, id_offset=lo); ss_nccl.use_exchange = False
