@@ -345,7 +345,7 @@ int ensure_pinned(css_index* h, size_t bytes) {
   h->pinned_bytes = 0;
   h->pinned_dev = nullptr;
   size_t want = std::max<size_t>(bytes, (size_t)1 << 20);
-  cudaError_t e = cudaHostAlloc(&h->pinned, want, cudaHostAllocMapped);
+  cudaError_t e = cudaHostAlloc(&h->pinned, want, cudaHostAllocMapped | cudaHostAllocPortable);
   if (e != cudaSuccess) {
     (void)cudaGetLastError();
     set_error("cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
@@ -1115,8 +1115,6 @@ int css_index_search_exchange_device(css_index* h, css_exchange* ex, const float
                      /*defer_fallback=*/false, nullptr);
 }
 
-static int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out);
-
 int css_index_search(css_index* h, const float* q_host, int nq, int k, const css_filter* filter,
                      float* D_host, int64_t* I_host) {
   CSS_REQUIRE(h != nullptr, "index is NULL");
@@ -1171,7 +1169,7 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
     sc->done_flag = nullptr;
     CSS_CHECK(rc);
     unsigned seen = 0;
-    CSS_CHECK(await_done_flag(flag, seq, st, &seen));
+    CSS_CHECK(await_done_flag(flag, seq, st, &seen, false));
     if (seen & 1u) {
       // not proven from the shadow lists: the fp32 scan answers (into the same mapped block)
       CSS_CHECK(scan_fallback(h, sc, sc->q_dev, 1, k, m, index_idmap(h, 0), nullptr, reinterpret_cast<float*>(pdev + d_off),
@@ -1201,12 +1199,17 @@ int css_index_search(css_index* h, const float* q_host, int nq, int k, const css
   return CSS_OK;
 }
 
-// Poll the completion flag of a single-query launch (see css_index_search).  *seen_out: the flag value.
-static int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out) {
+}  // extern "C"
+
+namespace css {
+// Poll the completion flag of a single-query launch (see css_index_search).  *seen_out: the flag value.  With
+// `final_only` a flag that says "unproven" is not the end: the fp32 re-run that is already in the stream raises
+// the flag again.
+int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out, bool final_only) {
   unsigned seen = 0;
   for (unsigned spins = 1;; ++spins) {
     seen = *flag;
-    if ((seen >> 1) == seq) break;
+    if ((seen >> 1) == seq && !(final_only && (seen & 1u))) break;
     if ((spins & 1023u) == 0u) {
       // a failed kernel never raises the flag; a finished stream means the result (and the flag) are in place
       const cudaError_t qe = cudaStreamQuery(st);
@@ -1224,9 +1227,12 @@ static int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t s
     set_error("search kernel finished without signalling its result");
     return CSS_ERR_CUDA;
   }
-  *seen_out = seen;
+  if (seen_out) *seen_out = seen;
   return CSS_OK;
 }
+}  // namespace css
+
+extern "C" {
 
 int css_index_search_exchange(css_index* h, css_exchange* ex, const float* q_host, int k, const uint32_t* mask_dev,
                               int64_t id_offset, float* D_host, int64_t* I_host) {
@@ -1267,7 +1273,7 @@ int css_index_search_exchange(css_index* h, css_exchange* ex, const float* q_hos
   sc->done_flag = nullptr;
   CSS_CHECK(rc);
   unsigned seen = 0;
-  CSS_CHECK(await_done_flag(flag, seq, st, &seen));
+  CSS_CHECK(await_done_flag(flag, seq, st, &seen, false));
   if (seen & 1u) {
     // not proven from the shadow lists: the fp32 scan answers, publishes this rank's list and merges
     CSS_CHECK(scan_fallback(h, sc, sc->q_dev, 1, k, m, index_idmap(h, id_offset), &xd, Dm, Im, st, /*pdl_ok=*/false));

@@ -141,6 +141,7 @@ int batched_search(css_index* h, css_scan_scratch* sc, const float* q_dev, int n
 void batched_release(css_scan_scratch* sc);
 int get_scratch(css_index* h, cudaStream_t st, int nq, css_scan_scratch** out);
 int ensure_pinned(css_index* h, size_t bytes);
+int await_done_flag(volatile unsigned* flag, unsigned seq, cudaStream_t st, unsigned* seen_out, bool final_only);
 IdMap index_idmap(const css_index* h, int64_t id_offset);
 int eval_filter(css_index* h, const css_filter* f, const uint32_t** mask_out, int64_t* n_pass, bool need_count,
                 cudaStream_t st, bool* ignore_alive_out, size_t pinned_front);

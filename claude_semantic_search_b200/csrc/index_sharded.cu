@@ -346,6 +346,13 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
   CSS_CHECK(ensure_pinned(h, d_off + res_stride * S + 64));
   unsigned char* pin = reinterpret_cast<unsigned char*>(h->pinned);
   memcpy(pin, q_host, qbytes);
+  // single query on the exchange path: device 0 writes the merged result straight into the mapped staging block and
+  // raises a flag there (see css_index_search); no D2H copy, no stream synchronisation
+  const size_t f_off = d_off + res_stride * S;
+  const bool mapped = exchange && nq == 1 && h->pinned_dev != nullptr && options().scan_mapped.load() != 0;
+  volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(pin + f_off);
+  const unsigned seq = (++h->call_seq) & 0x3fffffffu;
+  if (mapped) *flag = 0u;
   std::vector<std::vector<uint32_t>> rms(filter && filter->row_mask ? S : 0);
   // Pass 1, per shard: scratch, filter evaluation.  Anything that may free device memory (scratch or filter buffers
   // growing) happens here, sequentially: cudaFree waits for ALL work of its device, and once the scans of pass 2
@@ -392,7 +399,15 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
     const uint32_t* m = masks[s];
     CSS_CUDA(cudaMemcpyAsync(sc->q_dev, pin, qbytes, cudaMemcpyHostToDevice, st));
     int64_t* I_dev = reinterpret_cast<int64_t*>(reinterpret_cast<unsigned char*>(sc->D_dev) + i_rel);
-    if (exchange) {
+    if (exchange && mapped && s == 0) {
+      unsigned char* pdev = reinterpret_cast<unsigned char*>(h->pinned_dev);
+      sc->done_flag = reinterpret_cast<unsigned*>(pdev + f_off);
+      sc->done_seq = seq;
+      const int rc = scan_search(sh, sc, sc->q_dev, nq, k, m, index_idmap(sh, 0), &xds[s], reinterpret_cast<float*>(pdev + d_off),
+                                 reinterpret_cast<int64_t*>(pdev + d_off + i_rel), st, /*defer_fallback=*/false, nullptr);
+      sc->done_flag = nullptr;
+      CSS_CHECK(rc);
+    } else if (exchange) {
       CSS_CHECK(scan_search(sh, sc, sc->q_dev, nq, k, m, index_idmap(sh, 0), &xds[s], sc->D_dev, I_dev, st,
                             /*defer_fallback=*/false, nullptr));
       if (s == 0) CSS_CUDA(cudaMemcpyAsync(pin + d_off, sc->D_dev, i_rel + ibytes, cudaMemcpyDeviceToHost, st));
@@ -418,7 +433,8 @@ int sharded_search(css_index* h, const float* q_host, int nq, int k, const css_f
     // every shard has published, i.e. consumed the pinned query.
     css_index* s0 = h->shards[0];
     DeviceGuard g(s0->device);
-    CSS_CUDA(cudaStreamSynchronize(s0->stream));
+    if (mapped) CSS_CHECK(await_done_flag(flag, seq, s0->stream, nullptr, /*final_only=*/true));
+    else CSS_CUDA(cudaStreamSynchronize(s0->stream));
     memcpy(D_host, pin + d_off, dbytes);
     memcpy(I_host, pin + d_off + i_rel, ibytes);
     return CSS_OK;
