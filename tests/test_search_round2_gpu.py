@@ -411,6 +411,15 @@ want = (col >= 3) & (col <= 5)
 Drf, Irf = so.flat_search_c(x, q[:4], k, mask_words=so.pack_mask(want))
 ok, why = so.compare_topk(Drf, Irf, Df.cpu().numpy(), If.cpu().numpy())
 assert ok, f"rank {rank} filtered: {why}"
+# one query in HOST memory per call (css_index_search_exchange: result through mapped memory + completion flag)
+torch.cuda.synchronize(dev)
+for i in range(4):
+    Dh, Ih = idx.search_exchange_host(ss._exchange(), q[i], k, lo)
+    ok, why = so.compare_topk(Dr[i:i + 1], Ir[i:i + 1], Dh, Ih)
+    assert ok, f"rank {rank} host q{i}: {why}"
+Dh, Ih = idx.search_exchange_host(ss._exchange(), q[1], k, lo, mask_ptr=mptr)
+ok, why = so.compare_topk(Drf[1:2], Irf[1:2], Dh, Ih)
+assert ok, f"rank {rank} host filtered: {why}"
 dist.barrier()
 ss.close()
 idx.close()
