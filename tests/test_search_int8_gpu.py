@@ -184,3 +184,58 @@ def test_int8_shadow_follows_compaction_save_load_and_growth(native, tmp_path):
     s = idz.scan_stats()
     assert s["last_tier"] == 2 and s["two_phase_queries"] == 5 and s["unproven_queries"] == 0, s
     idz.close()
+
+
+def test_int8_masked_sweeps_all_list_lengths(native, tiers):
+    """The filtered sweep (gather instantiation) and the alive-bits-only dense sweep, with 32- and 64-entry block
+    lists (k <= 16 / k > 16), against the oracle and bit-identical across the tiers."""
+    rng = np.random.default_rng(41)
+    n, d = 120_005, 768
+    x = so.normalize_rows(rng.standard_normal((n, d), dtype=np.float32))
+    q = so.normalize_rows(rng.standard_normal((3, d), dtype=np.float32))
+    idx = native.Index(d)
+    idx.add(x, normalize=False)
+    sparse = rng.random(n) < 0.03
+    half = rng.random(n) < 0.5
+    dead = rng.choice(n, size=250, replace=False).astype(np.int64)
+    alive = np.ones(n, bool)
+    alive[dead] = False
+
+    def body(name):
+        got = []
+        for mask in (sparse, half):
+            flt = native.Filter().set_row_mask(so.pack_mask(mask))
+            for k in (1, 10, 32):
+                for i in range(3):
+                    D, I = idx.search(q[i:i + 1], k, flt)
+                    _check(*so.flat_search_c(x, q[i:i + 1], k, mask_words=so.pack_mask(mask)), D, I)
+                    got.append((D, I))
+        return got
+
+    out = tiers(body)
+    for name in ("int8", "bf16"):
+        for a, b in zip(out[name], out["fp32"]):
+            np.testing.assert_array_equal(a[1], b[1])
+            np.testing.assert_array_equal(a[0], b[0])
+    # deletions: the alive bits are the mask, the dense sweep drops the dead rows
+    idx.set_alive_ids(dead, False)
+
+    def body2(name):
+        got = []
+        for k in (1, 10, 32):
+            for i in range(3):
+                D, I = idx.search(q[i:i + 1], k)
+                _check(*so.flat_search_c(x, q[i:i + 1], k, mask_words=so.pack_mask(alive)), D, I)
+                assert alive[I[I >= 0]].all()
+                got.append((D, I))
+        D, I = idx.search(q, 10, native.Filter().set_row_mask(so.pack_mask(sparse)))      # filter AND alive, nq = 3
+        _check(*so.flat_search_c(x, q, 10, mask_words=so.pack_mask(sparse & alive)), D, I)
+        got.append((D, I))
+        return got
+
+    out = tiers(body2)
+    for name in ("int8", "bf16"):
+        for a, b in zip(out[name], out["fp32"]):
+            np.testing.assert_array_equal(a[1], b[1])
+            np.testing.assert_array_equal(a[0], b[0])
+    idx.close()
