@@ -444,7 +444,7 @@ static void fill_common(css_index* h, css_scan_scratch* sc, ScanParams* p, const
 template <int KPL, int SH>
 static int launch_phase1_as(const ScanParams& p, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = scan_topk_kernel<KPL, CSS_METRIC_INNER_PRODUCT, true, SH>;
-  CSS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (the dynamic shared-memory limit of every scan kernel was raised when the index was created: preload_index_kernels)
   kern<<<grid, kScanThreads, smem, st>>>(p);
   CSS_LAUNCHED();
   return CSS_OK;

@@ -504,14 +504,6 @@ __device__ __forceinline__ void quantize_query_i8(const float* q, const int lane
   dq = sqrtf(d2) * 1.001f;
 }
 
-__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
-  uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
-  return v;
-}
-
 // This lane's share of x^.q^ for one row (48 elements), already multiplied by the row's scale and a1.
 __device__ __forceinline__ float dot_i8(const uint4 (&v)[3], const int (&q1)[12], const int (&q2)[12], const float scale) {
   int i1 = 0, i2 = 0, j1 = 0, j2 = 0;   // two chains per code vector: six dependent dp4a instead of twelve
@@ -535,24 +527,6 @@ __device__ __forceinline__ void half_sums(float f, float& acc0, float& acc1) {
   for (int o = 8; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
   acc0 = __shfl_sync(0xffffffffu, f, 0);
   acc1 = __shfl_sync(0xffffffffu, f, 16);
-}
-
-// Scores of 8 listed rows (filtered scan; the dense sweep keeps its loads rolling, see scan_one_query).
-__device__ __forceinline__ void score_rows_i8(const ScanParams& p, const int (&q1)[12], const int (&q2)[12], const float a1,
-                                              const int64_t (&r)[kRowsPerUnit], const int lane, float (&acc)[kRowsPerUnit]) {
-  const int hl = lane & 15, half = lane >> 4;
-  uint4 v[4][3];
-  float sc[4];
-#pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    const int64_t row = half ? r[2 * s + 1] : r[2 * s];
-    const uint4* src = reinterpret_cast<const uint4*>(p.xq + row * 768) + hl;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) v[s][j] = ld_stream_u4(src + j * 16);
-    sc[s] = __ldg(p.xs + row);
-  }
-#pragma unroll
-  for (int s = 0; s < 4; ++s) half_sums(dot_i8(v[s], q1, q2, sc[s] * a1), acc[2 * s], acc[2 * s + 1]);
 }
 
 // ------------------------------------------------------------------------
