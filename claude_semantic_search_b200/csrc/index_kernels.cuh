@@ -679,21 +679,19 @@ __device__ __forceinline__ void emit_topk(const ScanParams& p, const int qi, Key
 }
 
 // ------------------------------------------------------------------------
-// Two-phase scan, phase 2, run by the last CTA of a query's phase-1 grid (no extra launch).  Phase 1
-// (BF16 scan) left, per scan block, the kp best rows of that block's rows by their score against the
-// bf16 shadow copy (sorted; `part`).  Rounding a row to bf16 (the query stays fp32) moves its score by
-//   |x.q - bf16(x).q| <= ||x - bf16(x)|| ||q|| <= max_err ||q||      (Cauchy-Schwarz; max_err is the
-// largest rounding-error norm of any stored row, tracked exactly at add time: about 0.4 * 2^-8 ||x||
-// for dense rows, against the worst case 2^-8 ||x|| of round-to-nearest with an 8-bit significand)
-// and the two fp32 summations (24 FMAs per lane + 5 shuffle adds each) by <= 4e-6 ||x|| ||q||, so
-//   eps = ||q|| (1.001 max_err + 4e-6 max_norm).
-// With t = the k-th best bf16 score over ALL list entries (exactly the k-th best bf16 score of the
-// corpus unless a list is cut short, in which case it is a lower bound), the true k-th best score is
-// >= t - eps and every row of the true top-k has a bf16 score >= t - 2 eps =: thr.  A block list
-// whose last entry is still >= thr may have dropped such a row: the query is queued for the fp32 scan
-// (ovf_list), as it is when more than kRescoreCap rows pass -- never answered approximately.
-// Otherwise every row with bf16 score >= thr is in the lists: they are re-scored in fp32 with the
-// arithmetic of the fp32 scan (bit-identical scores) and the best k are the exact result.
+// Two-phase scan, phase 2, run by the last CTA of a query's phase-1 grid (no extra launch).  Phase 1 (the
+// shadow sweep: bf16 or int8 rows) left, per scan block, the kp best rows of that block by shadow score (sorted;
+// `part`) and -- computed by the block itself right after its sweep -- their exact fp32 scores (`part_exact`,
+// the arithmetic of the fp32 scan: bit-identical scores).  `eps` bounds |shadow score - exact score| of any
+// stored row (scan_one_query; bf16: ||q|| (1.001 max_err + 4e-6 max_norm) from |x.q - bf16(x).q| <=
+// ||x - bf16(x)|| ||q|| (Cauchy-Schwarz; max_err is the largest rounding-error norm of any stored row, tracked
+// exactly at add time: about 0.4 * 2^-8 ||x|| for dense rows, against the worst case 2^-8 ||x|| of
+// round-to-nearest with an 8-bit significand) plus the fp32 summations; int8: see quantize_query_i8).
+// With T = the k-th best EXACT score among k or more distinct list entries (a lower bound of the corpus' k-th
+// best exact score), every row of the true top-k has a shadow score >= T - eps =: thr.  A block list whose last
+// entry is still >= thr may have dropped such a row: the query is queued for the fp32 scan (ovf_list), as it
+// is when more than kRescoreCap rows pass -- never answered approximately.  Otherwise every row with shadow
+// score >= thr is in the lists and the best k of them by exact score are the exact result.
 // Selection is by rank counting (no sorting network: one barrier per step); s: kMergeCap entries.
 // Returns true when the result was emitted.
 // ------------------------------------------------------------------------
@@ -753,7 +751,7 @@ __device__ __forceinline__ int rank_among(const KeyId* s, const int n, const Key
 template <int KPL>
 __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int qi, KeyId* s, const int tid, const float eps) {
   __shared__ float s_t;
-  __shared__ int s_cnt, s_unproven;
+  __shared__ int s_cnt, s_unproven, s_anyfull, s_maxlast;   // s_maxlast: float bits, largest last entry of a full list
   constexpr int kp = 32 * KPL;   // == p.k: the list length is the warp list's capacity
   const int k = p.k_out, blocks = gridDim.x;
   const KeyId* lists = p.part + (size_t)qi * blocks * kp;
@@ -773,23 +771,35 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (i < total) {
       ent[c] = ldcg_keyid(lists + i);
       exact[c] = __ldcg(lists_exact + i);
+      if (ent[c].id == kEmptyId) exact[c] = -INFINITY;   // the owning block writes the scores of real entries only
     }
   }
   if (tid == 0) {
     s_t = -INFINITY;
     s_cnt = 0;
     s_unproven = 0;
+    s_anyfull = 0;
+    s_maxlast = __float_as_int(-INFINITY);
   }
   scan_stamp(p, gridDim.x, 0);
-  // (A) t0 = k-th best list head (k distinct rows score at least that); with fewer than k lists the
-  //     k-th best of their first k entries.
+  // (A) T = the k-th best EXACT score among the list heads (k distinct rows score at least that; with fewer than k
+  //     lists: among their first k entries), a lower bound of the k-th best exact score of the corpus.  Every row of
+  //     the true top-k therefore has an exact score >= T and a shadow score >= T - eps =: thr -- ONE eps: the exact
+  //     scores of the list entries are at hand (the owning blocks computed them), so the threshold need not be
+  //     derived from shadow scores (k-th best shadow score - 2 eps: twice the slack, three times the candidates, and a
+  //     second selection pass to tighten it).
   const int per = blocks >= k ? 1 : k;
   const int nsel = blocks * per;
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
     const int i = tid + c * kScanThreads;
     const int within = i % kp;
-    if (i < total && within < per) s[(i / kp) * per + within] = ent[c];
+    if (i < total && within < per) {
+      KeyId e;
+      e.key = exact[c];
+      e.id = ent[c].id;
+      s[(i / kp) * per + within] = e;
+    }
   }
   __syncthreads();
   for (int i = tid; i < nsel; i += kScanThreads) {
@@ -798,38 +808,23 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     if (rank_among(s, nsel, e) == k - 1) s_t = e.key;
   }
   __syncthreads();
-  const float t0 = s_t;
-  // (B) tighten: the k-th best over all entries >= t0 (there are at least k of them)
-  if (t0 > -INFINITY) {
-#pragma unroll
-    for (int c = 0; c < kPer; ++c) {
-      if (ent[c].id != kEmptyId && ent[c].key >= t0) {
-        const int pos = atomicAdd(&s_cnt, 1);
-        if (pos < kRankSortMax) s[pos] = ent[c];
-      }
-    }
-    __syncthreads();
-    const int c = s_cnt;
-    if (c <= kRankSortMax) {
-      for (int i = tid; i < c; i += kScanThreads) {
-        const KeyId e = s[i];
-        if (rank_among(s, c, e) == k - 1) s_t = e.key;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) s_cnt = 0;
-  }
-  __syncthreads();
-  // eps: the tier's bound on |approximate score - exact score| (see scan_one_query); a bound that is not finite
+  // eps: the tier's bound on |shadow score - exact score| (see scan_one_query); a bound that is not finite
   // (non-finite query or stored row) proves nothing
-  const float thr = (s_t > -INFINITY) ? s_t - 2.f * eps : -INFINITY;
+  const float thr = (s_t > -INFINITY) ? s_t - eps : -INFINITY;
   if (tid == 0 && !(eps < INFINITY)) s_unproven = 1;
-  // (C) proof + candidates over the full lists
+  // (C) candidates over the full lists (shadow score >= thr), and the largest last entry of a FULL list: every row
+  //     that is in no list has a shadow score at or below that
 #pragma unroll
   for (int c = 0; c < kPer; ++c) {
-    if (ent[c].id != kEmptyId && ent[c].key >= thr) {
-      const int i = tid + c * kScanThreads;
-      if (i % kp == kp - 1) s_unproven = 1;
+    if (ent[c].id == kEmptyId) continue;
+    const int i = tid + c * kScanThreads;
+    if (i % kp == kp - 1) {
+      s_anyfull = 1;
+      const float f = ent[c].key;   // float maximum on the bit pattern (never NaN: NaN scores enter no list)
+      if (f >= 0.f) atomicMax(&s_maxlast, __float_as_int(f));
+      else atomicMin(reinterpret_cast<unsigned*>(&s_maxlast), __float_as_uint(f));
+    }
+    if (ent[c].key >= thr) {
       const int pos = atomicAdd(&s_cnt, 1);
       if (pos < kRescoreCap) {
         s[pos].key = exact[c];   // from here on the exact fp32 score
@@ -839,7 +834,8 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
   }
   __syncthreads();
   const int keep = s_cnt;
-  if (s_unproven || keep > kRescoreCap) {
+  // queue the query for the fp32 scan (never answered approximately)
+  auto give_up = [&]() {
     if (tid == 0) {
       p.ovf_list[atomicAdd(p.ovf_count, 1)] = qi;
       const unsigned nq_seen = atomicAdd(p.stats_dev, 1u) + 1u;
@@ -849,6 +845,9 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
         p.stats_host[1] = nu;
       }
     }
+  };
+  if (s_unproven || keep > kRescoreCap) {
+    give_up();
     return false;
   }
   // (D) the candidates' exact fp32 scores were computed by the blocks that own them, in parallel over the grid
@@ -912,6 +911,20 @@ __device__ __forceinline__ bool two_phase_finish(const ScanParams& p, const int 
     __syncthreads();
     if (tid < k) s[tid] = e;
     __syncthreads();
+  }
+  // (F) the proof, with the best threshold there is: T1 = the k-th best exact score just found (k distinct rows
+  //     score at least that, T1 >= T), so every row of the true top-k has a shadow score >= T1 - eps -- at or above
+  //     thr, i.e. among the candidates if it is in a list at all; and no row outside the lists reaches it when the
+  //     largest last entry of a full list is below it.  (Fewer than k candidates: T1 = -inf, provable only when no
+  //     list is full, i.e. nothing was dropped anywhere.)
+  {
+    const float t1 = s[k - 1].id != kEmptyId ? s[k - 1].key : -INFINITY;
+    const bool proven = !s_anyfull || __int_as_float(s_maxlast) < t1 - eps;
+    if (!proven) {
+      __syncthreads();
+      give_up();
+      return false;
+    }
   }
   emit_topk<CSS_METRIC_INNER_PRODUCT>(p, qi, s, tid, kScanThreads);
   scan_stamp(p, gridDim.x, 4);
